@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference CPU
+assembler (/root/reference/src/referenceassembler/referenceAssembler.py) in this container.
+
+The reference is Python and cannot travel to the GPU box, so its outputs are committed here as
+small JSON fixtures together with this script.  Re-run:  python tests/golden/make_golden.py
+
+Fixtures
+  g200.json         reference fixture tests/g200reads.fa (the 100 reads pinned by the
+                    reference's own tests/test_fasta_reader.py) x k in {9,11,17,18,21} x
+                    limit in {0,1}: build() table and all_contigs() output.
+  synth_small.json  600 seeded random reads (with N's and ragged lengths) from a 3 kbp genome,
+                    k in {15,16,31}: same outputs.
+"""
+import hashlib
+import json
+import os
+import random
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def load_reference():
+    # its only third-party import (`from dask import delayed`, :5) is unused
+    sys.modules.setdefault("dask", types.SimpleNamespace(delayed=lambda f=None, **kw: f))
+    sys.path.insert(0, os.path.join(REF, "src", "referenceassembler"))
+    import referenceAssembler
+    return referenceAssembler
+
+
+def sha16(items):
+    return hashlib.sha256("\n".join(sorted(items)).encode()).hexdigest()[:16]
+
+
+def run_case(ra, reads, k, limit):
+    d = ra.build(reads, k, limit)
+    _, contigs = ra.all_contigs(d, k)
+    canon = sorted(min(c, ra.twin(c)) for c in contigs)
+    return {
+        "k": k, "limit": limit,
+        "kmers": sorted([km, c] for km, c in d.items()),
+        "kmer_sha": sha16(["%s\t%d" % (km, c) for km, c in d.items()]),
+        "contigs": contigs,
+        "contig_sha": sha16(canon),
+    }
+
+
+def read_fasta_lines(path):
+    out = []
+    with open(path) as f:
+        for line in f:
+            if line[0] != ">":
+                out.append(line.strip())
+    return out
+
+
+def main():
+    ra = load_reference()
+    reads = read_fasta_lines(os.path.join(REF, "tests", "g200reads.fa"))
+    g200 = {"source": "reference tests/g200reads.fa", "reads": reads,
+            "cases": [run_case(ra, reads, k, lim) for k in (9, 11, 17, 18, 21) for lim in (0, 1)]}
+    with open(os.path.join(HERE, "g200.json"), "w") as f:
+        json.dump(g200, f, indent=0)
+
+    rng = random.Random(20261018)
+    genome = "".join(rng.choice("ACGT") for _ in range(3000))
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    sreads = []
+    for _ in range(600):
+        L = rng.choice((20, 33, 47, 60, 60, 60))
+        s = rng.randrange(0, len(genome) - L)
+        r = genome[s:s + L]
+        if rng.random() < 0.5:
+            r = "".join(comp[c] for c in reversed(r))
+        if rng.random() < 0.1:
+            p = rng.randrange(L)
+            r = r[:p] + "N" + r[p + 1:]
+        if rng.random() < 0.03:
+            p = rng.randrange(L)
+            r = r[:p] + rng.choice("ACGT") + r[p + 1:]
+        sreads.append(r)
+    synth = {"source": "random.Random(20261018), see make_golden.py", "reads": sreads,
+             "cases": [run_case(ra, sreads, k, lim) for k in (15, 16, 31) for lim in (0, 1)]}
+    with open(os.path.join(HERE, "synth_small.json"), "w") as f:
+        json.dump(synth, f, indent=0)
+    for name, fx in (("g200", g200), ("synth_small", synth)):
+        for c in fx["cases"]:
+            print(name, c["k"], c["limit"], len(c["kmers"]), c["kmer_sha"], len(c["contigs"]), c["contig_sha"])
+
+
+if __name__ == "__main__":
+    main()
