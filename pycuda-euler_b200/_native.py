@@ -1,0 +1,391 @@
+"""ctypes binding of libeuler_b200.so (the C ABI in include/euler_b200.h).
+
+This is the only place Python touches native code.  There is NO CPU fallback: if the shared
+library is missing or no CUDA device is present, every entry point raises ``EulerError``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeuler_b200.so")
+
+EV_DTYPE = np.dtype([("vid", np.uint64), ("ep", np.uint32), ("ecount", np.uint32),
+                     ("lp", np.uint32), ("lcount", np.uint32)])            # pydebruijn.py:607
+EE_DTYPE = np.dtype([("eid", np.uint64), ("v1", np.uint32), ("v2", np.uint32),
+                     ("s", np.uint32), ("pad", np.uint32)])                # pydebruijn.py:605
+SV_DTYPE = np.dtype([("vid", np.uint32), ("n1", np.uint32), ("n2", np.uint32)])   # pyeulertour.py:735
+CE_DTYPE = np.dtype([("ceid", np.uint32), ("e1", np.uint32), ("e2", np.uint32),
+                     ("c1", np.uint32), ("c2", np.uint32)])                # pyeulertour.py:786
+
+RUN_EXPAND_EDGES = 1
+RUN_CANONICAL_IDS = 2
+
+(ART_LMER_KEYS, ART_LMER_VALUES, ART_LMER_OFFSETS, ART_KMER_KEYS, ART_LCOUNT, ART_ECOUNT, ART_LSTART,
+ ART_ESTART, ART_EV, ART_EDGE_V1, ART_EDGE_V2, ART_EE, ART_LEV, ART_ENT) = range(14)
+
+_ART_DTYPE = {
+    ART_LMER_KEYS: np.uint64, ART_LMER_VALUES: np.uint32, ART_LMER_OFFSETS: np.uint32,
+    ART_KMER_KEYS: np.uint64, ART_LCOUNT: np.uint32, ART_ECOUNT: np.uint32, ART_LSTART: np.uint32,
+    ART_ESTART: np.uint32, ART_EV: EV_DTYPE, ART_EDGE_V1: np.uint32, ART_EDGE_V2: np.uint32,
+    ART_EE: EE_DTYPE, ART_LEV: np.uint32, ART_ENT: np.uint32,
+}
+
+
+class EulerError(RuntimeError):
+    pass
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_bases", C.c_uint64), ("n_kmer_windows", C.c_uint64),
+                ("n_lmer_windows", C.c_uint64), ("distinct_lmers", C.c_uint64), ("distinct_kmers", C.c_uint64),
+                ("edge_count", C.c_uint64), ("lmer_table_capacity", C.c_uint64),
+                ("kmer_table_capacity", C.c_uint64), ("retries", C.c_uint32),
+                ("ms_count", C.c_float), ("ms_graph", C.c_float), ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (raises EulerError if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EulerError("libeuler_b200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    sig = {
+        "euler_ctx_create": [i32, C.POINTER(vp)],
+        "euler_ctx_set_stream": [vp, vp],
+        "euler_ctx_sync": [vp],
+        "euler_encode_lmers": [vp, vp, vp, u64, u32, vp, vp, vp],
+        "euler_compute_kmers": [vp, vp, u64, u64, vp, vp],
+        "euler_count_lmers": [vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp],
+        "euler_count_mers": [vp, vp, vp, u64, u32, u32, vp, vp, vp],
+        "euler_hash_build": [vp, vp, vp, u64, u64, vp, vp],
+        "euler_hash_lookup": [vp, vp, vp, u64, vp, u64, vp],
+        "euler_exclusive_scan_u32": [vp, vp, u64, vp],
+        "euler_debruijn_count": [vp, vp, vp, u64, vp, vp, u64, u32, u64, vp, vp],
+        "euler_setup_vertices": [vp, vp, u64, vp, vp, u64, vp, vp, vp, vp, vp],
+        "euler_setup_edges": [vp, vp, vp, vp, u64, vp, vp, u64, u32, vp, vp, u64, vp, vp, vp],
+        "euler_assign_successor": [vp, vp, vp, vp, u32, vp, u32],
+        "euler_successor_graph": [vp, vp, u32, vp],
+        "euler_find_components": [vp, vp, u32, vp],
+        "euler_circuit_vertices": [vp, vp, u32, vp, vp, vp, vp],
+        "euler_circuit_edges": [vp, vp, vp, u32, vp, vp, u32, vp, vp],
+        "euler_spanning_forest": [vp, vp, u64, u32, vp, vp],
+        "euler_mark_spanning": [vp, vp, u64, vp, u32, u32, vp],
+        "euler_swipe": [vp, vp, vp, u32, vp, vp, u32],
+        "euler_contig_starts": [vp, vp, u32, vp],
+        "euler_emit_contigs": [vp, vp, u32, vp, u32, u32, vp, vp, vp],
+        "euler_pipeline_run_dev": [vp, vp, vp, u64, u64, u32, u32, u64, vp],
+        "euler_pipeline_run_host": [vp, vp, vp, u64, u32, u32, u64, vp],
+        "euler_pipeline_artifact_bytes": [vp, i32, vp],
+        "euler_pipeline_download": [vp, i32, vp, u64],
+        "euler_pipeline_device_ptr": [vp, i32, vp],
+        "euler_pipeline_contigs": [vp, vp, vp, vp],
+        "euler_synth_reads_dev": [vp, u64, u32, u32, u64, u64, vp],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = i32
+    L.euler_ctx_destroy.argtypes = [vp]
+    L.euler_ctx_destroy.restype = None
+    L.euler_last_error.argtypes = [vp]
+    L.euler_last_error.restype = C.c_char_p
+    L.euler_hash_capacity.argtypes = [u64]
+    L.euler_hash_capacity.restype = u64
+    L.euler_version.argtypes = []
+    L.euler_version.restype = i32
+    _lib = L
+    return L
+
+
+def _p(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One euler_ctx: one GPU, one stream (replaces `import pycuda.autoinit`, pyencode.py:3)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.euler_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise EulerError("euler_ctx_create(device=%d) failed with %d: %s" %
+                             (device, rc, "no CUDA device (there is no CPU fallback)" if rc == -7 else "CUDA error"))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.euler_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            msg = self.lib.euler_last_error(self.h)
+            raise EulerError("libeuler_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+    def set_stream(self, cuda_stream):
+        self.check(self.lib.euler_ctx_set_stream(self.h, C.c_void_p(int(cuda_stream))))
+
+    def sync(self):
+        self.check(self.lib.euler_ctx_sync(self.h))
+
+    # ------------------------------------------------------------------ encoder
+    def encode_lmers(self, buf, off, l, want_rc=True, want_valid=True):
+        buf = _arr(buf, np.uint8)
+        off = _arr(off, np.uint64)
+        B = int(off[-1])
+        fwd = np.zeros(B, np.uint64)
+        rc = np.zeros(B, np.uint64) if want_rc else None
+        valid = np.zeros(B, np.uint8) if want_valid else None
+        self.check(self.lib.euler_encode_lmers(self.h, _p(buf), _p(off), len(off) - 1, int(l), _p(fwd), _p(rc), _p(valid)))
+        return fwd, rc, valid
+
+    def compute_kmers(self, lmers, mask):
+        lmers = _arr(lmers, np.uint64)
+        pk = np.zeros_like(lmers)
+        sk = np.zeros_like(lmers)
+        self.check(self.lib.euler_compute_kmers(self.h, _p(lmers), lmers.size, int(mask), _p(pk), _p(sk)))
+        return pk, sk
+
+    def count_mers(self, buf, off, length, limit=0):
+        buf = _arr(buf, np.uint8)
+        off = _arr(off, np.uint64)
+        n = C.c_uint64(0)
+        self.check(self.lib.euler_count_mers(self.h, _p(buf), _p(off), len(off) - 1, int(length), int(limit),
+                                             C.byref(n), None, None))
+        keys = np.zeros(n.value, np.uint64)
+        vals = np.zeros(n.value, np.uint32)
+        if n.value:
+            self.check(self.lib.euler_count_mers(self.h, _p(buf), _p(off), len(off) - 1, int(length), int(limit),
+                                                 C.byref(n), _p(keys), _p(vals)))
+        return keys, vals
+
+    # ------------------------------------------------------------------ gpuhash
+    def hash_capacity(self, n):
+        return int(self.lib.euler_hash_capacity(int(n)))
+
+    def hash_build(self, keys, values, capacity=None):
+        keys = _arr(keys, np.uint64)
+        values = _arr(values, np.uint32)
+        cap = int(capacity) if capacity else self.hash_capacity(keys.size)
+        TK = np.zeros(cap, np.uint64)
+        TV = np.zeros(cap, np.uint32)
+        self.check(self.lib.euler_hash_build(self.h, _p(keys), _p(values), keys.size, cap, _p(TK), _p(TV)))
+        return TK, TV
+
+    def hash_lookup(self, TK, TV, queries):
+        TK = _arr(TK, np.uint64)
+        TV = _arr(TV, np.uint32)
+        q = _arr(queries, np.uint64)
+        out = np.zeros(q.size, np.uint32)
+        self.check(self.lib.euler_hash_lookup(self.h, _p(TK), _p(TV), TK.size, _p(q), q.size, _p(out)))
+        return out
+
+    def exclusive_scan(self, a):
+        a = _arr(a, np.uint32)
+        out = np.zeros_like(a)
+        self.check(self.lib.euler_exclusive_scan_u32(self.h, _p(a), a.size, _p(out)))
+        return out
+
+    # ------------------------------------------------------------------ debruijn
+    def debruijn_count(self, lkeys, lvals, TK, TV, l, vertex_count):
+        lkeys = _arr(lkeys, np.uint64)
+        lvals = _arr(lvals, np.uint32)
+        TK = _arr(TK, np.uint64)
+        TV = _arr(TV, np.uint32)
+        lcount = np.zeros(4 * vertex_count, np.uint32)
+        ecount = np.zeros(4 * vertex_count, np.uint32)
+        self.check(self.lib.euler_debruijn_count(self.h, _p(lkeys), _p(lvals), lkeys.size, _p(TK), _p(TV), TK.size,
+                                                 int(l), int(vertex_count), _p(lcount), _p(ecount)))
+        return lcount, ecount
+
+    def setup_vertices(self, kkeys, TK, TV, lcount, lstart, ecount, estart):
+        kkeys = _arr(kkeys, np.uint64)
+        TK = _arr(TK, np.uint64)
+        TV = _arr(TV, np.uint32)
+        ev = np.zeros(kkeys.size, EV_DTYPE)
+        a = [_arr(x, np.uint32) for x in (lcount, lstart, ecount, estart)]
+        self.check(self.lib.euler_setup_vertices(self.h, _p(kkeys), kkeys.size, _p(TK), _p(TV), TK.size,
+                                                 _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(ev)))
+        return ev
+
+    def setup_edges(self, lkeys, lvals, loffs, TK, TV, l, lstart, estart, edge_count):
+        lkeys = _arr(lkeys, np.uint64)
+        lvals = _arr(lvals, np.uint32)
+        loffs = _arr(loffs, np.uint32)
+        TK = _arr(TK, np.uint64)
+        TV = _arr(TV, np.uint32)
+        lstart = _arr(lstart, np.uint32)
+        estart = _arr(estart, np.uint32)
+        ee = np.zeros(edge_count, EE_DTYPE)
+        lev = np.zeros(edge_count, np.uint32)
+        ent = np.zeros(edge_count, np.uint32)
+        self.check(self.lib.euler_setup_edges(self.h, _p(lkeys), _p(lvals), _p(loffs), lkeys.size, _p(TK), _p(TV),
+                                              TK.size, int(l), _p(lstart), _p(estart), int(edge_count),
+                                              _p(ee), _p(lev), _p(ent)))
+        return ee, lev, ent
+
+    # ------------------------------------------------------------------ eulertour / component
+    def assign_successor(self, ev, lev, ent, ee):
+        ev = _arr(ev, EV_DTYPE)
+        ee = _arr(ee, EE_DTYPE).copy()
+        lev = _arr(lev, np.uint32)
+        ent = _arr(ent, np.uint32)
+        self.check(self.lib.euler_assign_successor(self.h, _p(ev), _p(lev), _p(ent), ev.size, _p(ee), ee.size))
+        return ee
+
+    def successor_graph(self, ee):
+        ee = _arr(ee, EE_DTYPE)
+        v = np.zeros(ee.size, SV_DTYPE)
+        self.check(self.lib.euler_successor_graph(self.h, _p(ee), ee.size, _p(v)))
+        return v
+
+    def find_components(self, v):
+        v = _arr(v, SV_DTYPE)
+        D = np.zeros(v.size, np.uint32)
+        self.check(self.lib.euler_find_components(self.h, _p(v), v.size, _p(D)))
+        return D
+
+    def circuit_vertices(self, D):
+        D = _arr(D, np.uint32)
+        Cm = np.zeros(D.size, np.uint32)
+        off = np.zeros(D.size, np.uint32)
+        cv = np.zeros(D.size, np.uint32)
+        n = C.c_uint32(0)
+        self.check(self.lib.euler_circuit_vertices(self.h, _p(D), D.size, _p(Cm), _p(off), _p(cv), C.byref(n)))
+        return Cm, off, cv[:n.value].copy(), n.value
+
+    def circuit_edges(self, ev, ent, D, cmap):
+        ev = _arr(ev, EV_DTYPE)
+        ent = _arr(ent, np.uint32)
+        D = _arr(D, np.uint32)
+        cmap = _arr(cmap, np.uint32)
+        n = C.c_uint64(0)
+        self.check(self.lib.euler_circuit_edges(self.h, _p(ev), _p(ent), ev.size, _p(D), _p(cmap), D.size, None, C.byref(n)))
+        out = np.zeros(n.value, CE_DTYPE)
+        if n.value:
+            self.check(self.lib.euler_circuit_edges(self.h, _p(ev), _p(ent), ev.size, _p(D), _p(cmap), D.size,
+                                                    _p(out), C.byref(n)))
+        return out
+
+    def spanning_forest(self, cg, cg_vcount):
+        cg = _arr(cg, CE_DTYPE)
+        tree = np.zeros(max(cg.size, 1), np.uint32)
+        n = C.c_uint32(0)
+        self.check(self.lib.euler_spanning_forest(self.h, _p(cg), cg.size, int(cg_vcount), _p(tree), C.byref(n)))
+        return tree[:n.value].copy()
+
+    def mark_spanning(self, cg, tree, ecount):
+        cg = _arr(cg, CE_DTYPE)
+        tree = _arr(tree, np.uint32)
+        mark = np.zeros(ecount, np.uint32)
+        self.check(self.lib.euler_mark_spanning(self.h, _p(cg), cg.size, _p(tree), tree.size, int(ecount), _p(mark)))
+        return mark
+
+    def swipe(self, ev, ent, ee, mark):
+        ev = _arr(ev, EV_DTYPE)
+        ent = _arr(ent, np.uint32)
+        ee = _arr(ee, EE_DTYPE).copy()
+        mark = _arr(mark, np.uint32)
+        self.check(self.lib.euler_swipe(self.h, _p(ev), _p(ent), ev.size, _p(ee), _p(mark), ee.size))
+        return ee
+
+    def contig_starts(self, ee):
+        ee = _arr(ee, EE_DTYPE)
+        st = np.zeros(ee.size, np.uint32)
+        self.check(self.lib.euler_contig_starts(self.h, _p(ee), ee.size, _p(st)))
+        return st
+
+    def emit_contigs(self, ev, ee, l):
+        ev = _arr(ev, EV_DTYPE)
+        ee = _arr(ee, EE_DTYPE)
+        nb, nc = C.c_uint64(0), C.c_uint64(0)
+        self.check(self.lib.euler_emit_contigs(self.h, _p(ev), ev.size, _p(ee), ee.size, int(l), None,
+                                               C.byref(nb), C.byref(nc)))
+        if not nb.value:
+            return []
+        out = np.zeros(nb.value, np.uint8)
+        cap = C.c_uint64(nb.value)
+        self.check(self.lib.euler_emit_contigs(self.h, _p(ev), ev.size, _p(ee), ee.size, int(l), _p(out),
+                                               C.byref(cap), C.byref(nc)))
+        return out.tobytes().decode("ascii").split("\n")[:-1]
+
+    # ------------------------------------------------------------------ fused pipeline
+    def run_host(self, buf, off, l, flags=0, distinct_hint=0):
+        buf = _arr(buf, np.uint8)
+        off = _arr(off, np.uint64)
+        st = Stats()
+        self.check(self.lib.euler_pipeline_run_host(self.h, _p(buf), _p(off), len(off) - 1, int(l), int(flags),
+                                                    int(distinct_hint), C.byref(st)))
+        return st
+
+    def run_dev(self, d_buf, d_off, nreads, n_bases, l, flags=0, distinct_hint=0):
+        st = Stats()
+        self.check(self.lib.euler_pipeline_run_dev(self.h, C.c_void_p(int(d_buf)), C.c_void_p(int(d_off)), int(nreads),
+                                                   int(n_bases), int(l), int(flags), int(distinct_hint), C.byref(st)))
+        return st
+
+    def download(self, which):
+        nb = C.c_uint64(0)
+        self.check(self.lib.euler_pipeline_artifact_bytes(self.h, which, C.byref(nb)))
+        dt = np.dtype(_ART_DTYPE[which])
+        out = np.zeros(nb.value // dt.itemsize, dt)
+        if nb.value:
+            self.check(self.lib.euler_pipeline_download(self.h, which, _p(out), nb.value))
+        return out
+
+    def device_ptr(self, which):
+        p = C.c_void_p()
+        self.check(self.lib.euler_pipeline_device_ptr(self.h, which, C.byref(p)))
+        return p.value
+
+    def pipeline_contigs(self):
+        nb, nc = C.c_uint64(0), C.c_uint64(0)
+        self.check(self.lib.euler_pipeline_contigs(self.h, None, C.byref(nb), C.byref(nc)))
+        if not nb.value:
+            return []
+        out = np.zeros(nb.value, np.uint8)
+        cap = C.c_uint64(nb.value)
+        self.check(self.lib.euler_pipeline_contigs(self.h, _p(out), C.byref(cap), C.byref(nc)))
+        return out.tobytes().decode("ascii").split("\n")[:-1]
+
+    def synth_reads_dev(self, d_out, G, L, err_ppm, first, nreads):
+        self.check(self.lib.euler_synth_reads_dev(self.h, int(G), int(L), int(err_ppm), int(first), int(nreads),
+                                                  C.c_void_p(int(d_out))))
+
+
+_default_ctx = None
+
+
+def default_context():
+    """Process-wide context on device 0 (the reference's implicit pycuda.autoinit context)."""
+    global _default_ctx
+    if _default_ctx is None:
+        dev = int(os.environ.get("EULER_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        _default_ctx = Context(dev)
+    return _default_ctx

@@ -1,0 +1,399 @@
+// graph.cu -- vertex table, id assignment and de Bruijn graph construction (D1-D6).
+// Replaces pygpuhash.py H1-H4, pydebruijn.py getHashValue/debruijnCount/setupVertices/setupEdges.
+#include "kernels.h"
+#include "scan.cuh"
+
+#define GB 256  // block size for the element-wise kernels here
+
+int graph_table_clear(euler_ctx *ctx, u64 *keys, u32 *vals, u64 cap)
+{
+    CUDA_TRY(ctx, cudaMemsetAsync(keys, 0xFF, cap * sizeof(u64), ctx->stream));
+    if (vals) CUDA_TRY(ctx, cudaMemsetAsync(vals, 0, cap * sizeof(u32), ctx->stream));
+    return EULER_OK;
+}
+
+__device__ __forceinline__ u64 canon64(u64 x, u32 len)
+{
+    const u64 r = revcomp64(x, len);
+    return x < r ? x : r;
+}
+
+// ---- vertex table build ------------------------------------------------------------------------
+__global__ void __launch_bounds__(GB) vertex_insert_kernel(const u64 *__restrict__ lt_keys, u64 lt_cap, u32 l,
+                                                            u64 *__restrict__ vt_keys, u64 vt_cap, u64 *flags)
+{
+    const u64 slot = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= lt_cap) return;
+    const u64 key = lt_keys[slot];
+    if (key == EULER_EMPTY_KEY) return;
+    const u32 k = l - 1;
+    const u64 kmask = key_mask_d(k);
+    const u64 max_probe = vt_cap < 8192 ? vt_cap : 8192;
+    const u64 a = table_insert(vt_keys, vt_cap, canon64(key >> 2, k), max_probe);
+    const u64 b = table_insert(vt_keys, vt_cap, canon64(key & kmask, k), max_probe);
+    if (a == EULER_NO_SLOT || b == EULER_NO_SLOT) atomicOr((unsigned long long *)flags, 2ull);
+}
+
+int graph_vertex_insert(euler_ctx *ctx, const u64 *lt_keys, u64 lt_cap, u32 l, u64 *vt_keys, u64 vt_cap, u64 *d_flags)
+{
+    vertex_insert_kernel<<<grid_for(lt_cap, GB), GB, 0, ctx->stream>>>(lt_keys, lt_cap, l, vt_keys, vt_cap, d_flags);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+// ---- strand-weight scan over slots -------------------------------------------------------------
+struct SlotWeight {
+    const u64 *keys;
+    u32 len;
+    __device__ __forceinline__ u32 operator()(u64 i) const
+    {
+        const u64 k = keys[i];
+        if (k == EULER_EMPTY_KEY) return 0u;
+        return k == revcomp64(k, len) ? 1u : 2u;
+    }
+};
+
+int graph_slot_scan(euler_ctx *ctx, const u64 *keys, u64 cap, u32 len, u32 *d_base, u64 *d_total)
+{
+    return scan_exclusive(ctx, SlotWeight{keys, len}, cap, d_base, d_total);
+}
+
+__global__ void __launch_bounds__(GB) compact_lmers_kernel(const u64 *__restrict__ lt_keys, const u32 *__restrict__ lt_cnt,
+                                                            const u32 *__restrict__ base, u64 cap, u32 l,
+                                                            u64 *__restrict__ lkeys, u32 *__restrict__ lvals)
+{
+    const u64 slot = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= cap) return;
+    const u64 c = lt_keys[slot];
+    if (c == EULER_EMPTY_KEY) return;
+    const u32 n = lt_cnt[slot];
+    const u32 idx = base[slot];
+    const u64 r = revcomp64(c, l);
+    if (c == r) {  // palindrome: both strands hit the same key (eulercuda.py:151-161)
+        lkeys[idx] = c;
+        lvals[idx] = 2u * n;
+    } else {
+        lkeys[idx] = c;
+        lvals[idx] = n;
+        lkeys[idx + 1] = r;
+        lvals[idx + 1] = n;
+    }
+}
+
+int graph_compact_lmers(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, const u32 *lt_base, u64 lt_cap, u32 l,
+                        u64 *lkeys, u32 *lvals)
+{
+    compact_lmers_kernel<<<grid_for(lt_cap, GB), GB, 0, ctx->stream>>>(lt_keys, lt_cnt, lt_base, lt_cap, l, lkeys, lvals);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+__global__ void __launch_bounds__(GB) compact_vertices_kernel(const u64 *__restrict__ vt_keys, const u32 *__restrict__ base,
+                                                               u64 cap, u32 k, u64 *__restrict__ vkeys)
+{
+    const u64 slot = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= cap) return;
+    const u64 c = vt_keys[slot];
+    if (c == EULER_EMPTY_KEY) return;
+    const u32 idx = base[slot];
+    const u64 r = revcomp64(c, k);
+    vkeys[idx] = c;
+    if (c != r) vkeys[idx + 1] = r;
+}
+
+int graph_compact_vertices(euler_ctx *ctx, const u64 *vt_keys, const u32 *vt_base, u64 vt_cap, u32 k, u64 *vkeys)
+{
+    compact_vertices_kernel<<<grid_for(vt_cap, GB), GB, 0, ctx->stream>>>(vt_keys, vt_base, vt_cap, k, vkeys);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+__global__ void __launch_bounds__(GB) assign_sorted_ids_kernel(const u64 *__restrict__ vkeys, u64 nv,
+                                                                const u64 *__restrict__ vt_keys, u64 vt_cap, u32 k,
+                                                                u32 *__restrict__ id0, u32 *__restrict__ id1)
+{
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nv) return;
+    const u64 x = vkeys[r];
+    const u64 rc = revcomp64(x, k);
+    const u64 c = x < rc ? x : rc;
+    const u64 slot = table_find(vt_keys, vt_cap, c);
+    if (slot == EULER_NO_SLOT) return;
+    if (x == c) id0[slot] = (u32)r;
+    if (x == rc || x != c) id1[slot] = (u32)r;
+}
+
+int graph_assign_sorted_ids(euler_ctx *ctx, const u64 *vkeys, u64 nv, const u64 *vt_keys, u64 vt_cap, u32 k, u32 *id0,
+                            u32 *id1)
+{
+    if (!nv) return EULER_OK;
+    assign_sorted_ids_kernel<<<grid_for(nv, GB), GB, 0, ctx->stream>>>(vkeys, nv, vt_keys, vt_cap, k, id0, id1);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+// ---- D1: degree slots + compressed edges -------------------------------------------------------
+__device__ __forceinline__ u32 vt_lookup(const VertexTable &vt, u64 v)
+{
+    const u64 r = revcomp64(v, vt.k);
+    const u64 c = v < r ? v : r;
+    const u64 slot = table_find(vt.keys, vt.cap, c);
+    if (slot == EULER_NO_SLOT) return EULER_NO_ID;
+    if (v == c) return vt.id0[slot];
+    return vt.id1 ? vt.id1[slot] : vt.id0[slot] + 1u;
+}
+__device__ __forceinline__ u32 pt_lookup(const PlainTable &pt, u64 v)
+{
+    // getHashValue pydebruijn.py:57-88: value or MAX_INT
+    const u64 slot = table_find(pt.keys, pt.cap, v);
+    return slot == EULER_NO_SLOT ? EULER_NO_ID : pt.vals[slot];
+}
+
+template <typename Table, typename Lookup>
+__global__ void __launch_bounds__(GB) degree_slots_kernel(const u64 *__restrict__ lkeys, const u32 *__restrict__ lvals,
+                                                           u64 nl, u32 l, Table tab, Lookup lookup, u64 size,
+                                                           u32 *__restrict__ lcount, u32 *__restrict__ ecount,
+                                                           u32 *__restrict__ ev1, u32 *__restrict__ ev2)
+{
+    // debruijnCount pydebruijn.py:107-141
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nl) return;
+    const u64 x = lkeys[i];
+    const u32 m = lvals[i];
+    const u32 k = l - 1;
+    const u64 kmask = key_mask_d(k);
+    const u32 pid = lookup(tab, x >> 2);
+    const u32 sid = lookup(tab, x & kmask);
+    const u32 to = (u32)(x & 3), from = (u32)((x >> (2 * k)) & 3);
+    const u64 to_index = ((u64)pid << 2) + to, from_index = ((u64)sid << 2) + from;
+    if (pid != EULER_NO_ID && to_index < size) lcount[to_index] = m;
+    if (sid != EULER_NO_ID && from_index < size) ecount[from_index] = m;
+    if (ev1) { ev1[i] = pid; ev2[i] = sid; }
+}
+
+struct VtLookupFn { __device__ __forceinline__ u32 operator()(const VertexTable &t, u64 v) const { return vt_lookup(t, v); } };
+struct PtLookupFn { __device__ __forceinline__ u32 operator()(const PlainTable &t, u64 v) const { return pt_lookup(t, v); } };
+
+int graph_degree_slots(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, u64 nl, u32 l, const VertexTable &vt,
+                       u32 *lcount, u32 *ecount, u32 *ev1, u32 *ev2)
+{
+    if (!nl) return EULER_OK;
+    degree_slots_kernel<<<grid_for(nl, GB), GB, 0, ctx->stream>>>(lkeys, lvals, nl, l, vt, VtLookupFn(), ~0ull, lcount,
+                                                                  ecount, ev1, ev2);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+int graph_degree_slots_plain(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, u64 nl, u32 l, const PlainTable &pt,
+                             u64 nv, u32 *lcount, u32 *ecount)
+{
+    if (!nl) return EULER_OK;
+    degree_slots_kernel<<<grid_for(nl, GB), GB, 0, ctx->stream>>>(lkeys, lvals, nl, l, pt, PtLookupFn(), 4 * nv, lcount,
+                                                                  ecount, (u32 *)nullptr, (u32 *)nullptr);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+// ---- D5: vertices ------------------------------------------------------------------------------
+__device__ __forceinline__ void fill_vertex(euler_vertex *ev, u64 id, u64 key, const u32 *lcount, const u32 *lstart,
+                                            const u32 *ecount, const u32 *estart)
+{
+    // setupVertices pydebruijn.py:280-294
+    const uint4 lc = *reinterpret_cast<const uint4 *>(lcount + 4 * id);
+    const uint4 ec = *reinterpret_cast<const uint4 *>(ecount + 4 * id);
+    euler_vertex v;
+    v.vid = key;
+    v.lp = lstart[4 * id];
+    v.lcount = lc.x + lc.y + lc.z + lc.w;
+    v.ep = estart[4 * id];
+    v.ecount = ec.x + ec.y + ec.z + ec.w;
+    ev[id] = v;
+}
+
+__global__ void __launch_bounds__(GB) setup_vertices_kernel(const u64 *__restrict__ vkeys, u64 nv,
+                                                             const u32 *__restrict__ lcount, const u32 *__restrict__ lstart,
+                                                             const u32 *__restrict__ ecount, const u32 *__restrict__ estart,
+                                                             euler_vertex *__restrict__ ev)
+{
+    const u64 id = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= nv) return;
+    fill_vertex(ev, id, vkeys[id], lcount, lstart, ecount, estart);
+}
+
+int graph_setup_vertices(euler_ctx *ctx, const u64 *vkeys, u64 nv, const u32 *lcount, const u32 *lstart,
+                         const u32 *ecount, const u32 *estart, euler_vertex *ev)
+{
+    if (!nv) return EULER_OK;
+    setup_vertices_kernel<<<grid_for(nv, GB), GB, 0, ctx->stream>>>(vkeys, nv, lcount, lstart, ecount, estart, ev);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+__global__ void __launch_bounds__(GB) setup_vertices_plain_kernel(const u64 *__restrict__ kmer_keys, u64 nk, PlainTable pt,
+                                                                   u64 nv, const u32 *__restrict__ lcount,
+                                                                   const u32 *__restrict__ lstart,
+                                                                   const u32 *__restrict__ ecount,
+                                                                   const u32 *__restrict__ estart,
+                                                                   euler_vertex *__restrict__ ev)
+{
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nk) return;
+    const u64 key = kmer_keys[t];
+    const u32 index = pt_lookup(pt, key);
+    if (index != EULER_NO_ID && index < nv) fill_vertex(ev, index, key, lcount, lstart, ecount, estart);
+}
+
+int graph_setup_vertices_plain(euler_ctx *ctx, const u64 *kmer_keys, u64 nk, const PlainTable &pt, u64 nv,
+                               const u32 *lcount, const u32 *lstart, const u32 *ecount, const u32 *estart,
+                               euler_vertex *ev)
+{
+    if (!nk) return EULER_OK;
+    setup_vertices_plain_kernel<<<grid_for(nk, GB), GB, 0, ctx->stream>>>(kmer_keys, nk, pt, nv, lcount, lstart, ecount,
+                                                                          estart, ev);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+// ---- D6: expanded edges ------------------------------------------------------------------------
+// One warp per group of 32 distinct l-mers; the multiplicity loop is spread over the lanes so
+// that the ee[] / l[] / e[] writes of one l-mer are contiguous (setupEdges pydebruijn.py:426-475).
+template <bool PLAIN>
+__global__ void __launch_bounds__(GB) setup_edges_kernel(const u64 *__restrict__ lkeys, const u32 *__restrict__ lvals,
+                                                          const u32 *__restrict__ loffs, u64 nl, u32 l,
+                                                          const u32 *__restrict__ ev1, const u32 *__restrict__ ev2,
+                                                          PlainTable pt, const u32 *__restrict__ lstart,
+                                                          const u32 *__restrict__ estart, u32 ecount,
+                                                          euler_edge *__restrict__ ee, u32 *__restrict__ lev,
+                                                          u32 *__restrict__ ent)
+{
+    const int lane = threadIdx.x & 31;
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 i = warp * 32 + lane;
+    u32 m = 0, off = 0, pid = EULER_NO_ID, sid = EULER_NO_ID, lo = 0, eo = 0;
+    if (i < nl) {
+        const u64 x = lkeys[i];
+        const u32 k = l - 1;
+        m = lvals[i];
+        off = loffs[i];
+        if (PLAIN) {
+            pid = pt_lookup(pt, x >> 2);
+            sid = pt_lookup(pt, x & key_mask_d(k));
+        } else {
+            pid = ev1[i];
+            sid = ev2[i];
+        }
+        if (pid == EULER_NO_ID || sid == EULER_NO_ID) m = 0;
+        else {
+            lo = lstart[((u64)pid << 2) + (u32)(x & 3)];
+            eo = estart[((u64)sid << 2) + (u32)((x >> (2 * k)) & 3)];
+        }
+    }
+    for (int src = 0; src < 32; src++) {
+        const u32 mm = __shfl_sync(0xffffffffu, m, src);
+        if (!mm) continue;
+        const u32 o = __shfl_sync(0xffffffffu, off, src);
+        const u32 p = __shfl_sync(0xffffffffu, pid, src);
+        const u32 s = __shfl_sync(0xffffffffu, sid, src);
+        const u32 a = __shfl_sync(0xffffffffu, lo, src);
+        const u32 b = __shfl_sync(0xffffffffu, eo, src);
+        for (u32 t = lane; t < mm; t += 32) {
+            const u32 id = o + t;
+            if (id >= ecount) break;
+            euler_edge e;
+            e.eid = id; e.v1 = p; e.v2 = s; e.s = ecount; e.pad = 0;
+            ee[id] = e;
+            lev[a + t] = id;
+            ent[b + t] = id;
+        }
+    }
+}
+
+int graph_setup_edges(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, const u32 *loffs, u64 nl, u32 l,
+                      const u32 *ev1, const u32 *ev2, const u32 *lstart, const u32 *estart, u32 ecount,
+                      euler_edge *ee, u32 *lev, u32 *ent)
+{
+    if (!nl) return EULER_OK;
+    PlainTable none = {nullptr, nullptr, 0};
+    setup_edges_kernel<false><<<grid_for(nl, GB), GB, 0, ctx->stream>>>(lkeys, lvals, loffs, nl, l, ev1, ev2, none, lstart,
+                                                                        estart, ecount, ee, lev, ent);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+int graph_setup_edges_plain(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, const u32 *loffs, u64 nl, u32 l,
+                            const PlainTable &pt, const u32 *lstart, const u32 *estart, u32 ecount, euler_edge *ee,
+                            u32 *lev, u32 *ent)
+{
+    if (!nl) return EULER_OK;
+    setup_edges_kernel<true><<<grid_for(nl, GB), GB, 0, ctx->stream>>>(lkeys, lvals, loffs, nl, l, nullptr, nullptr, pt,
+                                                                       lstart, estart, ecount, ee, lev, ent);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+// ---- plain table (module-level gpuhash API) ----------------------------------------------------
+__global__ void __launch_bounds__(GB) plain_build_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, u64 n,
+                                                          u64 *__restrict__ TK, u32 *__restrict__ TV, u64 cap, u64 *flags)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 slot = table_insert(TK, cap, keys[i], cap);
+    if (slot == EULER_NO_SLOT) { atomicOr((unsigned long long *)flags, 1ull); return; }
+    TV[slot] = vals[i];
+}
+
+int graph_plain_build(euler_ctx *ctx, const u64 *keys, const u32 *vals, u64 n, u64 *TK, u32 *TV, u64 cap, u64 *d_flags)
+{
+    CUDA_TRY(ctx, cudaMemsetAsync(TK, 0xFF, cap * sizeof(u64), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(TV, 0xFF, cap * sizeof(u32), ctx->stream));
+    if (!n) return EULER_OK;
+    plain_build_kernel<<<grid_for(n, GB), GB, 0, ctx->stream>>>(keys, vals, n, TK, TV, cap, d_flags);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+__global__ void __launch_bounds__(GB) plain_lookup_kernel(PlainTable pt, const u64 *__restrict__ q, u64 nq,
+                                                           u32 *__restrict__ out)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    out[i] = pt_lookup(pt, q[i]);
+}
+
+int graph_plain_lookup(euler_ctx *ctx, const PlainTable &pt, const u64 *q, u64 nq, u32 *out)
+{
+    if (!nq) return EULER_OK;
+    plain_lookup_kernel<<<grid_for(nq, GB), GB, 0, ctx->stream>>>(pt, q, nq, out);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+// ---- count filter (referenceAssembler.build limit, :37-39) -------------------------------------
+struct KeepWeight {
+    const u32 *vals;
+    u32 limit;
+    __device__ __forceinline__ u32 operator()(u64 i) const { return vals[i] > limit ? 1u : 0u; }
+};
+
+__global__ void __launch_bounds__(GB) filter_scatter_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, u64 n,
+                                                             u32 limit, const u32 *__restrict__ base,
+                                                             u64 *__restrict__ out_keys, u32 *__restrict__ out_vals)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 v = vals[i];
+    if (v > limit) {
+        out_keys[base[i]] = keys[i];
+        out_vals[base[i]] = v;
+    }
+}
+
+int graph_filter_counts(euler_ctx *ctx, const u64 *keys, const u32 *vals, u64 n, u32 limit, u32 *d_base, u64 *out_keys,
+                        u32 *out_vals, u64 *d_total)
+{
+    EULER_TRY(scan_exclusive(ctx, KeepWeight{vals, limit}, n, d_base, d_total));
+    if (!n) return EULER_OK;
+    filter_scatter_kernel<<<grid_for(n, GB), GB, 0, ctx->stream>>>(keys, vals, n, limit, d_base, out_keys, out_vals);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}

@@ -1,0 +1,91 @@
+// kernels.h -- internal device-pointer launchers (all asynchronous on ctx->stream).
+#pragma once
+#include "common.cuh"
+
+// ---- encode.cu
+int enc_mark_starts(euler_ctx *ctx, const u64 *d_off, u64 nreads, u64 n_bases, u32 *d_bits);
+int enc_positions(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u64 *d_fwd, u64 *d_rc,
+                  unsigned char *d_valid);
+int enc_compute_kmers(euler_ctx *ctx, const u64 *d_lmers, u64 n, u64 mask, u64 *d_pk, u64 *d_sk);
+// d_stats: [0] += forward l-windows, [1] += forward (l-1)-windows, [2] |= 1 on table overflow
+int enc_count_canonical(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u64 *tab_keys,
+                        u32 *tab_cnt, u64 cap, u64 *d_stats);
+
+// ---- graph.cu
+// vertex-id lookup over the canonical k-mer table: id of strand 0 (canonical orientation) in id0,
+// strand 1 in id1 (id1 == NULL: slot-order ids, strand 1 = id0 + 1)
+struct VertexTable {
+    const u64 *keys;
+    const u32 *id0;
+    const u32 *id1;
+    u64 cap;
+    u32 k;
+};
+// plain key -> value table of the module-level API (pygpuhash TK/TV)
+struct PlainTable {
+    const u64 *keys;
+    const u32 *vals;
+    u64 cap;
+};
+
+int graph_table_clear(euler_ctx *ctx, u64 *keys, u32 *vals, u64 cap);
+// insert canon(prefix) and canon(suffix) of every key of the canonical l-mer table
+int graph_vertex_insert(euler_ctx *ctx, const u64 *lt_keys, u64 lt_cap, u32 l, u64 *vt_keys, u64 vt_cap, u64 *d_flags);
+// exclusive scan of strand weights (0 empty / 1 palindrome / 2) over table slots
+int graph_slot_scan(euler_ctx *ctx, const u64 *keys, u64 cap, u32 len, u32 *d_base, u64 *d_total);
+// both-strand (key, multiplicity) pairs in slot order
+int graph_compact_lmers(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, const u32 *lt_base, u64 lt_cap, u32 l,
+                        u64 *lkeys, u32 *lvals);
+// both-strand vertex keys in slot order
+int graph_compact_vertices(euler_ctx *ctx, const u64 *vt_keys, const u32 *vt_base, u64 vt_cap, u32 k, u64 *vkeys);
+// id0/id1 of the table slot of each (sorted) vertex key: id = index in vkeys
+int graph_assign_sorted_ids(euler_ctx *ctx, const u64 *vkeys, u64 nv, const u64 *vt_keys, u64 vt_cap, u32 k, u32 *id0,
+                            u32 *id1);
+// D1 debruijnCount (+ compressed edges ev1/ev2) over explicit l-mer arrays
+int graph_degree_slots(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, u64 nl, u32 l, const VertexTable &vt,
+                       u32 *lcount, u32 *ecount, u32 *ev1, u32 *ev2);
+int graph_degree_slots_plain(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, u64 nl, u32 l, const PlainTable &pt,
+                             u64 nv, u32 *lcount, u32 *ecount);
+// D5 setupVertices
+int graph_setup_vertices(euler_ctx *ctx, const u64 *vkeys, u64 nv, const u32 *lcount, const u32 *lstart,
+                         const u32 *ecount, const u32 *estart, euler_vertex *ev);
+int graph_setup_vertices_plain(euler_ctx *ctx, const u64 *kmer_keys, u64 nk, const PlainTable &pt, u64 nv,
+                               const u32 *lcount, const u32 *lstart, const u32 *ecount, const u32 *estart,
+                               euler_vertex *ev);
+// D6 setupEdges (expanded): ee / l[] / e[]
+int graph_setup_edges(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, const u32 *loffs, u64 nl, u32 l,
+                      const u32 *ev1, const u32 *ev2, const u32 *lstart, const u32 *estart, u32 ecount,
+                      euler_edge *ee, u32 *lev, u32 *ent);
+int graph_setup_edges_plain(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, const u32 *loffs, u64 nl, u32 l,
+                            const PlainTable &pt, const u32 *lstart, const u32 *estart, u32 ecount, euler_edge *ee,
+                            u32 *lev, u32 *ent);
+// plain table build / lookup
+int graph_plain_build(euler_ctx *ctx, const u64 *keys, const u32 *vals, u64 n, u64 *TK, u32 *TV, u64 cap, u64 *d_flags);
+int graph_plain_lookup(euler_ctx *ctx, const PlainTable &pt, const u64 *q, u64 nq, u32 *out);
+// (key,count) filter: keep count > limit, compact
+int graph_filter_counts(euler_ctx *ctx, const u64 *keys, const u32 *vals, u64 n, u32 limit, u32 *d_base,
+                        u64 *out_keys, u32 *out_vals, u64 *d_total);
+
+// ---- tour.cu
+int tour_reset_successors(euler_ctx *ctx, euler_edge *ee, u32 ecount);
+int tour_assign_successor(euler_ctx *ctx, const euler_vertex *ev, const u32 *lev, const u32 *ent, u32 vcount,
+                          euler_edge *ee, u32 ecount);
+int tour_successor_graph(euler_ctx *ctx, const euler_edge *ee, u32 ecount, euler_succ_vertex *v);
+int tour_components(euler_ctx *ctx, const euler_succ_vertex *v, u32 n, u32 *D);
+int tour_circuit_vertices(euler_ctx *ctx, const u32 *D, u32 ecount, u32 *C, u32 *offset, u32 *cv, u64 *d_count);
+// circuit edges, sorted; *out is a ctx-owned device array valid until the next call
+int tour_circuit_edges(euler_ctx *ctx, const euler_vertex *ev, const euler_edge *ee, const u32 *ent, u32 vcount,
+                       const u32 *D, const u32 *cmap, u32 ecount, euler_circuit_edge **out, u64 *count);
+int tour_spanning_forest(euler_ctx *ctx, const euler_circuit_edge *cg, u64 cg_count, u32 cg_vcount, u32 *tree,
+                         u32 *tree_count);
+int tour_mark_spanning(euler_ctx *ctx, const euler_circuit_edge *cg, const u32 *tree, u32 tree_count, u32 ecount,
+                       u32 *mark);
+int tour_swipe(euler_ctx *ctx, const euler_vertex *ev, const u32 *ent, u32 vcount, euler_edge *ee, const u32 *mark,
+               u32 ecount);
+int tour_contig_starts(euler_ctx *ctx, const euler_edge *ee, u32 ecount, u32 *start);
+// contig emission; *d_out ctx-owned device text, '\n'-terminated contigs
+int tour_emit_contigs(euler_ctx *ctx, const euler_vertex *ev, u32 vcount, const euler_edge *ee, u32 ecount, u32 l,
+                      char **d_out, u64 *out_bytes, u64 *ncontigs);
+
+// ---- synth.cu
+int synth_reads(euler_ctx *ctx, u64 G, u32 L, u32 err_ppm, u64 first, u64 nreads, void *d_out);

@@ -1,0 +1,326 @@
+// pipeline.cu -- the fused, device-resident hot path: encode -> canonical l-mer table ->
+// vertex table -> ids -> D1-D6, plus the Euler tour / contig stage on the resident graph.
+// Replaces eulercuda.constructDebruijnGraph (:183-264) + readLmersKmersCuda (:74-180) +
+// findEulerTour (:407-436) with everything kept in HBM between stages.
+#include "kernels.h"
+#include "scan.cuh"
+#include "sort.cuh"
+#include "tmp.cuh"
+
+struct Pipeline {
+    u32 l = 0, flags = 0;
+    const void *d_buf = nullptr;
+    const u64 *d_off = nullptr;
+    u64 nreads = 0, n_bases = 0;
+    // staged inputs of the host entry point
+    DevArr<unsigned char> in_buf;
+    DevArr<u64> in_off;
+    DevArr<u32> start_bits;
+    // canonical l-mer table (SoA) and canonical k-mer (vertex) table
+    DevArr<u64> lt_keys;
+    DevArr<u32> lt_cnt, lt_base;
+    u64 lt_cap = 0;
+    DevArr<u64> vt_keys;
+    DevArr<u32> vt_id0, vt_id1;
+    u64 vt_cap = 0;
+    DevArr<u64> stats;  // [0] N_l [1] N_k [2] flags [3] U_l [4] V [5] E
+    // graph artefacts
+    DevArr<u64> lkeys, vkeys;
+    DevArr<u32> lvals, loffs, ev1, ev2, lcount, ecount, lstart, estart;
+    DevArr<euler_vertex> ev;
+    DevArr<euler_edge> ee;
+    DevArr<u32> lev, ent;
+    // sort scratch (canonical ids)
+    DevArr<u64> sort_k;
+    DevArr<u32> sort_v, sort_hist;
+    u64 U_l = 0, V = 0, E = 0;
+    bool have_graph = false, expanded = false;
+    // capacity memory: distinct canonical l-mers / k-mers seen on the last run of this input size
+    u64 learned_bases = 0, learned_lc = 0, learned_vc = 0;
+    u64 text_bytes = 0, text_n = 0;
+    euler_stats st = {};
+};
+
+void pipeline_destroy(Pipeline *p)
+{
+    if (!p) return;
+    p->in_buf.free(); p->in_off.free(); p->start_bits.free();
+    p->lt_keys.free(); p->lt_cnt.free(); p->lt_base.free();
+    p->vt_keys.free(); p->vt_id0.free(); p->vt_id1.free(); p->stats.free();
+    p->lkeys.free(); p->vkeys.free(); p->lvals.free(); p->loffs.free(); p->ev1.free(); p->ev2.free();
+    p->lcount.free(); p->ecount.free(); p->lstart.free(); p->estart.free(); p->ev.free(); p->ee.free();
+    p->lev.free(); p->ent.free(); p->sort_k.free(); p->sort_v.free(); p->sort_hist.free();
+    delete p;
+}
+
+static u64 round_up(u64 x, u64 m) { return (x + m - 1) / m * m; }
+// table capacity for `n` expected distinct keys at load factor ~0.55
+static u64 cap_for(u64 n) { return round_up((u64)((double)(n < 64 ? 64 : n) / 0.55) + 1, 1024); }
+
+static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 distinct_hint, euler_stats *stats)
+{
+    if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
+    P->l = l; P->flags = flags; P->have_graph = false; P->expanded = false;
+    const u32 k = l - 1;
+    const u64 B = P->n_bases;
+    cudaStream_t s = ctx->stream;
+    memset(&P->st, 0, sizeof(P->st));
+    P->st.n_reads = P->nreads; P->st.n_bases = B;
+
+    EULER_TRY(P->stats.reserve(ctx, 16));
+    EULER_TRY(P->start_bits.reserve(ctx, B / 32 + 2));
+
+    // expected distinct canonical l-mers / k-mers
+    u64 est_l, est_v;
+    if (distinct_hint) { est_l = distinct_hint; est_v = distinct_hint + distinct_hint / 16; }
+    else if (P->learned_bases == B && P->learned_lc) { est_l = P->learned_lc + P->learned_lc / 32; est_v = P->learned_vc + P->learned_vc / 32; }
+    else { est_l = B ? B : 1; est_v = est_l; }
+    u64 lt_cap = cap_for(est_l), vt_cap = cap_for(est_v);
+
+    u64 h[8] = {0};
+    u32 retries = 0;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    EULER_TRY(enc_mark_starts(ctx, P->d_off, P->nreads, B, P->start_bits.ptr()));
+    while (true) {
+        P->lt_cap = lt_cap; P->vt_cap = vt_cap;
+        EULER_TRY(P->lt_keys.reserve(ctx, lt_cap));
+        EULER_TRY(P->lt_cnt.reserve(ctx, lt_cap));
+        EULER_TRY(P->lt_base.reserve(ctx, lt_cap));
+        EULER_TRY(P->vt_keys.reserve(ctx, vt_cap));
+        EULER_TRY(P->vt_id0.reserve(ctx, vt_cap));
+        CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 16 * sizeof(u64), s));
+        EULER_TRY(graph_table_clear(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap));
+        EULER_TRY(graph_table_clear(ctx, P->vt_keys.ptr(), nullptr, vt_cap));
+        EULER_TRY(enc_count_canonical(ctx, P->d_buf, B, P->start_bits.ptr(), l, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap,
+                                      P->stats.ptr()));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+        EULER_TRY(graph_slot_scan(ctx, P->lt_keys.ptr(), lt_cap, l, P->lt_base.ptr(), P->stats.ptr() + 3));
+        EULER_TRY(graph_vertex_insert(ctx, P->lt_keys.ptr(), lt_cap, l, P->vt_keys.ptr(), vt_cap, P->stats.ptr() + 2));
+        EULER_TRY(graph_slot_scan(ctx, P->vt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(), P->stats.ptr() + 4));
+        EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 6));
+        if ((h[2] & 3) == 0) break;
+        if (++retries > 8) return euler_fail(ctx, EULER_ERR_OVERFLOW, "hash table overflow after %u regrows", retries);
+        if (h[2] & 1) lt_cap *= 2;
+        if (h[2] & 2) vt_cap *= 2;
+    }
+    const u64 N_l = h[0], N_k = h[1], U_l = h[3], V = h[4];
+    const u64 E = 2 * N_l;
+    P->U_l = U_l; P->V = V; P->E = E;
+    if (V >= 0x3fffffffull || U_l >= 0xffffffffull || E >= 0xffffffffull)
+        return euler_fail(ctx, EULER_ERR_RANGE, "graph exceeds u32 ids (U_l=%llu V=%llu E=%llu)", U_l, V, E);
+
+    EULER_TRY(P->lkeys.reserve(ctx, U_l)); EULER_TRY(P->lvals.reserve(ctx, U_l)); EULER_TRY(P->loffs.reserve(ctx, U_l));
+    EULER_TRY(P->ev1.reserve(ctx, U_l)); EULER_TRY(P->ev2.reserve(ctx, U_l));
+    EULER_TRY(P->vkeys.reserve(ctx, V));
+    EULER_TRY(P->lcount.reserve(ctx, 4 * V + 4)); EULER_TRY(P->ecount.reserve(ctx, 4 * V + 4));
+    EULER_TRY(P->lstart.reserve(ctx, 4 * V + 4)); EULER_TRY(P->estart.reserve(ctx, 4 * V + 4));
+    EULER_TRY(P->ev.reserve(ctx, V));
+
+    EULER_TRY(graph_compact_lmers(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), P->lt_base.ptr(), lt_cap, l, P->lkeys.ptr(),
+                                  P->lvals.ptr()));
+    EULER_TRY(graph_compact_vertices(ctx, P->vt_keys.ptr(), P->vt_id0.ptr(), vt_cap, k, P->vkeys.ptr()));
+    VertexTable vt = {P->vt_keys.ptr(), P->vt_id0.ptr(), nullptr, vt_cap, k};
+    if (flags & EULER_RUN_CANONICAL_IDS) {
+        const u64 nmax = U_l > V ? U_l : V;
+        const u32 nblocks = (u32)((nmax + RS_TILE - 1) / RS_TILE);
+        EULER_TRY(P->sort_k.reserve(ctx, nmax)); EULER_TRY(P->sort_v.reserve(ctx, nmax));
+        EULER_TRY(P->sort_hist.reserve(ctx, (u64)256 * nblocks));
+        EULER_TRY(P->vt_id1.reserve(ctx, vt_cap));
+        EULER_TRY(radix_sort_pairs(ctx, P->lkeys.ptr(), P->lvals.ptr(), U_l, 2 * (int)l, P->sort_k.ptr(), P->sort_v.ptr(),
+                                   P->sort_hist.ptr()));
+        EULER_TRY(radix_sort_pairs(ctx, P->vkeys.ptr(), nullptr, V, 2 * (int)k, P->sort_k.ptr(), nullptr, P->sort_hist.ptr()));
+        EULER_TRY(graph_assign_sorted_ids(ctx, P->vkeys.ptr(), V, P->vt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(),
+                                          P->vt_id1.ptr()));
+        vt.id1 = P->vt_id1.ptr();
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(P->lcount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+    EULER_TRY(graph_degree_slots(ctx, P->lkeys.ptr(), P->lvals.ptr(), U_l, l, vt, P->lcount.ptr(), P->ecount.ptr(),
+                                 P->ev1.ptr(), P->ev2.ptr()));
+    EULER_TRY(scan_exclusive(ctx, ScanInU32{P->lcount.ptr()}, 4 * V, P->lstart.ptr(), (u64 *)nullptr));
+    EULER_TRY(scan_exclusive(ctx, ScanInU32{P->ecount.ptr()}, 4 * V, P->estart.ptr(), (u64 *)nullptr));
+    EULER_TRY(scan_exclusive(ctx, ScanInU32{P->lvals.ptr()}, U_l, P->loffs.ptr(), P->stats.ptr() + 5));
+    EULER_TRY(graph_setup_vertices(ctx, P->vkeys.ptr(), V, P->lcount.ptr(), P->lstart.ptr(), P->ecount.ptr(),
+                                   P->estart.ptr(), P->ev.ptr()));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+    if (flags & EULER_RUN_EXPAND_EDGES) {
+        EULER_TRY(P->ee.reserve(ctx, E)); EULER_TRY(P->lev.reserve(ctx, E)); EULER_TRY(P->ent.reserve(ctx, E));
+        EULER_TRY(graph_setup_edges(ctx, P->lkeys.ptr(), P->lvals.ptr(), P->loffs.ptr(), U_l, l, P->ev1.ptr(), P->ev2.ptr(),
+                                    P->lstart.ptr(), P->estart.ptr(), (u32)E, P->ee.ptr(), P->lev.ptr(), P->ent.ptr()));
+        P->expanded = true;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    P->have_graph = true;
+    P->learned_bases = B;
+    // canonical distinct counts: palindromes are rare, U/2 rounded up is a safe learned size
+    P->learned_lc = (U_l + 1) / 2 + 16; P->learned_vc = (V + 1) / 2 + 16;
+
+    euler_stats &st = P->st;
+    st.n_kmer_windows = N_k; st.n_lmer_windows = N_l; st.distinct_lmers = U_l; st.distinct_kmers = V; st.edge_count = E;
+    st.lmer_table_capacity = lt_cap; st.kmer_table_capacity = vt_cap; st.retries = retries;
+    cudaEventElapsedTime(&st.ms_count, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&st.ms_graph, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[2]);
+    if (stats) *stats = st;
+    return EULER_OK;
+}
+
+static Pipeline *get_pipe(euler_ctx *ctx)
+{
+    if (!ctx->pipe) ctx->pipe = new Pipeline();
+    return ctx->pipe;
+}
+
+extern "C" {
+
+int euler_pipeline_run_dev(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads, uint64_t n_bases,
+                           uint32_t l, uint32_t flags, uint64_t distinct_hint, euler_stats *stats)
+{
+    if (!ctx) return EULER_ERR_ARG;
+    if ((!d_buf && n_bases) || !d_read_off) return euler_fail(ctx, EULER_ERR_ARG, "null device input");
+    if (((uintptr_t)d_buf & 15) != 0) return euler_fail(ctx, EULER_ERR_ARG, "d_buf must be 16-byte aligned");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Pipeline *P = get_pipe(ctx);
+    P->d_buf = d_buf; P->d_off = (const u64 *)d_read_off; P->nreads = nreads; P->n_bases = n_bases;
+    return pipeline_run(ctx, P, l, flags, distinct_hint, stats);
+}
+
+int euler_pipeline_run_host(euler_ctx *ctx, const char *buf, const uint64_t *read_off, uint64_t nreads, uint32_t l,
+                            uint32_t flags, uint64_t distinct_hint, euler_stats *stats)
+{
+    if (!ctx) return EULER_ERR_ARG;
+    if (!read_off) return euler_fail(ctx, EULER_ERR_ARG, "null read_off");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Pipeline *P = get_pipe(ctx);
+    const u64 B = read_off[nreads];
+    if (B && !buf) return euler_fail(ctx, EULER_ERR_ARG, "null buf");
+    EULER_TRY(P->in_buf.reserve(ctx, B + 16));
+    EULER_TRY(P->in_off.reserve(ctx, nreads + 1));
+    if (B) CUDA_TRY(ctx, cudaMemcpyAsync(P->in_buf.ptr(), buf, B, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(P->in_off.ptr(), read_off, (nreads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    P->d_buf = P->in_buf.ptr(); P->d_off = P->in_off.ptr(); P->nreads = nreads; P->n_bases = B;
+    return pipeline_run(ctx, P, l, flags, distinct_hint, stats);
+}
+
+static int artifact(euler_ctx *ctx, int which, void **p, u64 *bytes)
+{
+    Pipeline *P = ctx->pipe;
+    if (!P || !P->have_graph) return euler_fail(ctx, EULER_ERR_STATE, "no pipeline run to read from");
+    const u64 U = P->U_l, V = P->V, E = P->E;
+    switch (which) {
+    case EULER_ART_LMER_KEYS: *p = P->lkeys.ptr(); *bytes = U * 8; break;
+    case EULER_ART_LMER_VALUES: *p = P->lvals.ptr(); *bytes = U * 4; break;
+    case EULER_ART_LMER_OFFSETS: *p = P->loffs.ptr(); *bytes = U * 4; break;
+    case EULER_ART_KMER_KEYS: *p = P->vkeys.ptr(); *bytes = V * 8; break;
+    case EULER_ART_LCOUNT: *p = P->lcount.ptr(); *bytes = 4 * V * 4; break;
+    case EULER_ART_ECOUNT: *p = P->ecount.ptr(); *bytes = 4 * V * 4; break;
+    case EULER_ART_LSTART: *p = P->lstart.ptr(); *bytes = 4 * V * 4; break;
+    case EULER_ART_ESTART: *p = P->estart.ptr(); *bytes = 4 * V * 4; break;
+    case EULER_ART_EV: *p = P->ev.ptr(); *bytes = V * sizeof(euler_vertex); break;
+    case EULER_ART_EDGE_V1: *p = P->ev1.ptr(); *bytes = U * 4; break;
+    case EULER_ART_EDGE_V2: *p = P->ev2.ptr(); *bytes = U * 4; break;
+    case EULER_ART_EE:
+    case EULER_ART_LEV:
+    case EULER_ART_ENT:
+        if (!P->expanded) return euler_fail(ctx, EULER_ERR_STATE, "edges were not expanded (EULER_RUN_EXPAND_EDGES)");
+        if (which == EULER_ART_EE) { *p = P->ee.ptr(); *bytes = E * sizeof(euler_edge); }
+        else if (which == EULER_ART_LEV) { *p = P->lev.ptr(); *bytes = E * 4; }
+        else { *p = P->ent.ptr(); *bytes = E * 4; }
+        break;
+    default: return euler_fail(ctx, EULER_ERR_ARG, "unknown artefact %d", which);
+    }
+    return EULER_OK;
+}
+
+int euler_pipeline_artifact_bytes(euler_ctx *ctx, int which, uint64_t *bytes)
+{
+    if (!ctx || !bytes) return EULER_ERR_ARG;
+    void *p; u64 b;
+    EULER_TRY(artifact(ctx, which, &p, &b));
+    *bytes = b;
+    return EULER_OK;
+}
+
+int euler_pipeline_download(euler_ctx *ctx, int which, void *host_dst, uint64_t cap_bytes)
+{
+    if (!ctx) return EULER_ERR_ARG;
+    void *p; u64 b;
+    EULER_TRY(artifact(ctx, which, &p, &b));
+    if (b > cap_bytes) return euler_fail(ctx, EULER_ERR_ARG, "destination too small (%llu > %llu)", b, (u64)cap_bytes);
+    if (b) {
+        if (!host_dst) return euler_fail(ctx, EULER_ERR_ARG, "null destination");
+        CUDA_TRY(ctx, cudaMemcpyAsync(host_dst, p, b, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return EULER_OK;
+}
+
+int euler_pipeline_device_ptr(euler_ctx *ctx, int which, void **dptr)
+{
+    if (!ctx || !dptr) return EULER_ERR_ARG;
+    u64 b;
+    return artifact(ctx, which, dptr, &b);
+}
+
+// findEulerTour eulercuda.py:407-436 + findEulerDevice pyeulertour.py:715-793 on the resident graph
+int euler_pipeline_contigs(euler_ctx *ctx, char *out, uint64_t *out_bytes, uint64_t *ncontigs)
+{
+    if (!ctx || !out_bytes || !ncontigs) return EULER_ERR_ARG;
+    Pipeline *P = ctx->pipe;
+    if (!P || !P->have_graph || !P->expanded)
+        return euler_fail(ctx, EULER_ERR_STATE, "contigs need a pipeline run with EULER_RUN_EXPAND_EDGES");
+    const u32 E = (u32)P->E, V = (u32)P->V;
+    *ncontigs = 0;
+    if (!E) { *out_bytes = 0; return EULER_OK; }
+    if (!out) {  // sizing call: run the tour now, keep the text resident for the second call
+        DevTmp<euler_succ_vertex> sv(ctx, E);
+        DevTmp<u32> D(ctx, E), C(ctx, E), cmap(ctx, E), mark(ctx, E);
+        DevTmp<u64> cnt(ctx, 1);
+        TMP_CHECK(ctx, sv); TMP_CHECK(ctx, D); TMP_CHECK(ctx, C); TMP_CHECK(ctx, cmap); TMP_CHECK(ctx, mark); TMP_CHECK(ctx, cnt);
+        EULER_TRY(tour_reset_successors(ctx, P->ee.ptr(), E));  // idempotent across repeated calls
+        EULER_TRY(tour_assign_successor(ctx, P->ev.ptr(), P->lev.ptr(), P->ent.ptr(), V, P->ee.ptr(), E));
+        EULER_TRY(tour_successor_graph(ctx, P->ee.ptr(), E, sv));
+        EULER_TRY(tour_components(ctx, sv, E, D));
+        EULER_TRY(tour_circuit_vertices(ctx, D, E, C, cmap, nullptr, cnt));
+        u64 ncirc = 0;
+        EULER_TRY(read_u64(ctx, cnt, &ncirc));
+        if (ncirc > 1) {
+            euler_circuit_edge *cg = nullptr;
+            u64 ncg = 0;
+            EULER_TRY(tour_circuit_edges(ctx, P->ev.ptr(), P->ee.ptr(), P->ent.ptr(), V, D, cmap, E, &cg, &ncg));
+            if (ncg) {
+                DevTmp<u32> tree(ctx, ncg);
+                TMP_CHECK(ctx, tree);
+                u32 nt = 0;
+                EULER_TRY(tour_spanning_forest(ctx, cg, ncg, (u32)ncirc, tree, &nt));
+                EULER_TRY(tour_mark_spanning(ctx, cg, tree, nt, E, mark));
+                EULER_TRY(tour_swipe(ctx, P->ev.ptr(), P->ent.ptr(), V, P->ee.ptr(), mark, E));
+            }
+        }
+        char *d_text = nullptr;
+        u64 bytes = 0, nc = 0;
+        EULER_TRY(tour_emit_contigs(ctx, P->ev.ptr(), V, P->ee.ptr(), E, P->l, &d_text, &bytes, &nc));
+        P->text_bytes = bytes; P->text_n = nc;
+        *out_bytes = bytes; *ncontigs = nc;
+        return EULER_OK;
+    }
+    const u64 bytes = P->text_bytes, nc = P->text_n;
+    if (*out_bytes < bytes) return euler_fail(ctx, EULER_ERR_ARG, "contig buffer too small");
+    if (bytes) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->text_buf.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *out_bytes = bytes; *ncontigs = nc;
+    return EULER_OK;
+}
+
+int euler_synth_reads_dev(euler_ctx *ctx, uint64_t genome_len, uint32_t read_len, uint32_t err_ppm, uint64_t first_read,
+                          uint64_t nreads, void *d_out)
+{
+    if (!ctx || !d_out) return EULER_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return synth_reads(ctx, genome_len, read_len, err_ppm, first_read, nreads, d_out);
+}
+
+}  // extern "C"
