@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (encode -> canonical l-mer table -> de Bruijn
+graph build) in forward k-mer windows per second (BASELINE.json `metric`).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One process per GPU (torchrun for N > 1).  A step is one pass of the hot path over one batch of
+synthetic reads.  Rank 0 prints ONE JSON line.
+
+* value      k-mer windows / s, reads already resident in HBM (CUDA events, max over ranks)
+* e2e        the same through the host-buffer C-ABI call: pinned host reads -> H2D -> pipeline ->
+             D2H of the compressed graph, all inside the timed region
+* roofline   the dominant kernel (fused encode+count) against the measured HBM peak
+* cpu_baseline / --impl reference   the oracle's C restatement of the reference CPU path
+             (kind "port": the reference is pure Python and cannot be compiled or shipped), timed on
+             this box's host cores on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "pycuda-euler_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on for 1 GPU
+    "ecoli_4.6Mbp_100bp_30x_k31": dict(G=4_600_000, L=100, cov=30, err_ppm=0, k=31),
+    # configs[2] (per-GPU share when sharded)
+    "100Mbp_150bp_40x_1pct_k31": dict(G=100_000_000, L=150, cov=40, err_ppm=10_000, k=31),
+    "small_smoke": dict(G=200_000, L=100, cov=20, err_ppm=0, k=31),
+}
+DEFAULT_WORKLOAD = "ecoli_4.6Mbp_100bp_30x_k31"
+METRIC = "k-mers/sec (encode+hash+graph build, device-timed)"
+UNIT = "k-mers/s"
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                getattr(pynvml, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            while not self.stop_flag:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:  # NVML not available: report that instead of inventing numbers
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def algorithmic_bytes(st, w=8):
+    """A = B + N_l (w+8) + U_l (w+16) + U_k (2w+84); the count kernel's share is the
+    first two terms (every base read once, one table-slot touch per forward l-mer window)."""
+    B, Nl, Ul, Uk = st.n_bases, st.n_lmer_windows, st.distinct_lmers, st.distinct_kmers
+    kernel = B + Nl * (w + 8)
+    return kernel, kernel + Ul * (w + 16) + Uk * (2 * w + 84)
+
+
+def cpu_port_rate(wl, nreads_sample, repeats=1):
+    """Oracle (C restatement of the reference CPU path) on the first `nreads_sample` reads."""
+    import oracle
+    L, l = wl["L"], wl["k"] + 1
+    buf = oracle.synth_reads(wl["G"], L, err_ppm=wl["err_ppm"], first=0, count=nreads_sample)
+    off = oracle.fixed_offsets(nreads_sample, L)
+    nk = nreads_sample * (L - wl["k"] + 1)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        g = oracle.graph_build(buf, off, l, expand=False)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return nk / best, best, nk, g
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the reference's CPU path (oracle port), all host threads, bounded sample."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nsample = min(wl["R"], 400_000)
+    for _ in range(args.warmup):
+        cpu_port_rate(wl, min(nsample, 50_000))
+    times, nk = [], 0
+    for _ in range(args.steps):
+        rate, dt, nk, _ = cpu_port_rate(wl, nsample)
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = nk / (ms / 1e3)
+    sample = "first %d reads of the workload (%d k-mer windows) per step" % (nsample, nk)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": args.workload, "k": wl["k"], "sample": sample,
+                   "note": "reference CPU path = oracle C restatement (the reference is pure Python; kind=port)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = dict(WORKLOADS[args.workload])
+    wl["R"] = -(-wl["G"] * wl["cov"] // wl["L"])
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import _native as N
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ctx = N.Context(local_rank)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    G, L, k, l = wl["G"], wl["L"], wl["k"], wl["k"] + 1
+    R = wl["R"]
+    # N > 1: each rank owns its own partition of R reads (weak scaling): reads [rank*R, (rank+1)*R)
+    first = rank * R
+    d_reads = torch.empty(R * L, dtype=torch.uint8, device="cuda")
+    ctx.synth_reads_dev(d_reads.data_ptr(), G, L, wl["err_ppm"], first, R)
+    d_off = torch.arange(R + 1, dtype=torch.int64, device="cuda") * L
+    ctx.sync()
+    torch.cuda.synchronize()
+    hint = G if wl["err_ppm"] == 0 else 0   # a user knows the genome size; with errors let the table learn
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    st = None
+    for _ in range(args.warmup):
+        st = ctx.run_dev(d_reads.data_ptr(), d_off.data_ptr(), R, R * L, l, 0, hint)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms, graph_ms, launches = 0.0, 0.0, 0
+    t_wall0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        st = ctx.run_dev(d_reads.data_ptr(), d_off.data_ptr(), R, R * L, l, 0, hint)
+        kern_ms += st.ms_count_kernel
+        graph_ms += st.ms_graph
+        launches += st.kernel_launches
+    e1.record(stream)
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall0) / args.steps
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.result()
+    kern_ms /= args.steps
+    graph_ms /= args.steps
+
+    # ---- e2e: host buffers through the reference-facing C-ABI call, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_reads = torch.empty(R * L, dtype=torch.uint8, pin_memory=True)
+        h_reads.copy_(d_reads)
+        h_off = torch.empty(R + 1, dtype=torch.int64, pin_memory=True)
+        h_off.copy_(d_off)
+        torch.cuda.synchronize()
+        arts = [N.ART_LMER_KEYS, N.ART_LMER_VALUES, N.ART_LMER_OFFSETS, N.ART_EDGE_V1, N.ART_EDGE_V2, N.ART_EV]
+        width = {N.ART_LMER_KEYS: 8, N.ART_LMER_VALUES: 4, N.ART_LMER_OFFSETS: 4, N.ART_EDGE_V1: 4, N.ART_EDGE_V2: 4,
+                 N.ART_EV: 24}
+        cap_items = int(max(st.distinct_lmers, st.distinct_kmers) * 1.05) + 1024
+        h_out = {a: torch.empty(cap_items * width[a], dtype=torch.uint8, pin_memory=True) for a in arts}
+
+        def e2e_step():
+            s = ctx.run_host_ptr(h_reads.data_ptr(), h_off.data_ptr(), R, l, 0, hint)
+            nb = 0
+            for a in arts:
+                nb += ctx.download_into(a, h_out[a].data_ptr(), h_out[a].numel())
+            return s, nb
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        d2h = 0
+        for _ in range(args.steps):
+            s2, d2h = e2e_step()
+        e1.record(stream)
+        barrier()
+        e2e_wall = 1e3 * (time.perf_counter() - t0) / args.steps
+        e2e_ms = max(e0.elapsed_time(e1) / args.steps, e2e_wall)  # the call returns synchronously: wall is the truth
+        e2e = {"ms": e2e_ms, "h2d": int(R * L + (R + 1) * 8), "d2h": int(d2h)}
+
+    # ---- reduce over ranks
+    nk_local = float(st.n_kmer_windows)
+    vals = torch.tensor([ms, e2e["ms"] if e2e else 0.0, kern_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([nk_local, float(launches)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_max, e2e_ms_max, kern_ms_max = [float(x) for x in vals.tolist()]
+    nk_total, launches_total = [float(x) for x in tot.tolist()]
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        a_kernel, a_path = algorithmic_bytes(st)
+        achieved = a_kernel / (kern_ms_max * 1e-3) / 1e9
+        traffic = None
+        tfile = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
+        if os.path.exists(tfile) and args.workload == DEFAULT_WORKLOAD:
+            try:
+                with open(tfile) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": nk_total / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {
+                "workload": args.workload, "genome_bp": G, "read_len": L, "coverage": wl["cov"], "err_ppm": wl["err_ppm"],
+                "k": k, "reads_per_gpu": R, "bases_per_gpu": R * L,
+                "parallelism": "1 GPU" if world == 1 else "%d read partitions, one per GPU, no merge (reference mapPartitions semantics)" % world,
+                "l2": "inputs (%d MB ASCII) + table (%d MB) exceed the 126 MB L2; the table is re-initialised every step"
+                      % (R * L // 10 ** 6, st.lmer_table_capacity * 12 // 10 ** 6),
+                "distinct_hint": hint, "ids": "slot order (canonical-id sort not in the timed region)",
+            },
+            "counts": {"n_kmer_windows": int(st.n_kmer_windows), "n_lmer_windows": int(st.n_lmer_windows),
+                       "distinct_lmers": int(st.distinct_lmers), "distinct_kmers": int(st.distinct_kmers),
+                       "edges": int(st.edge_count), "lmer_table_capacity": int(st.lmer_table_capacity),
+                       "retries": int(st.retries)},
+            "stage_ms": {"count_kernel": kern_ms_max, "graph": graph_ms, "step_wall": wall_ms},
+            "roofline": {"bound": "hbm", "kernel": "count_canonical_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": a_kernel,
+                         "path_algorithmic_bytes": a_path,
+                         "path_frac": a_path / (ms_max * 1e-3) / 1e9 / peak},
+            "clocks": clocks,
+            "gpu_launches": int(launches_total),
+        }
+        if e2e:
+            line["e2e"] = {"value": nk_total / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
+                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                           "api": "euler_pipeline_run_host + euler_pipeline_download (compressed graph)"}
+        if world == 1 and not args.no_cpu:
+            nsample = min(R, 200_000)
+            rate, dt, nk_s, _ = cpu_port_rate(wl, nsample)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": "first %d reads of the workload (%d k-mer windows), %.2f s" % (nsample, nk_s, dt)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,13 @@ int euler_contig_starts(euler_ctx *ctx, const euler_edge *ee, uint32_t ecount, u
 int euler_emit_contigs(euler_ctx *ctx, const euler_vertex *ev, uint32_t vcount, const euler_edge *ee,
                        uint32_t ecount, uint32_t l, char *out, uint64_t *out_bytes, uint64_t *ncontigs);
 
+/* referenceAssembler.build (:25-42) + all_contigs (:79-88) on device: unitigs of the both-strand
+ * K-mer graph restricted to K-mers with count > limit.  Each unitig is written once, in one of its
+ * two orientations; isolated cycles start at an implementation-chosen node.  '\n'-terminated
+ * contigs; two-call protocol on out (NULL -> sizes).  K in [2,32]. */
+int euler_unitigs(euler_ctx *ctx, const char *buf, const uint64_t *read_off, uint64_t nreads, uint32_t K,
+                  uint32_t limit, char *out, uint64_t *out_bytes, uint64_t *ncontigs);
+
 /* =========================================================================================
  * Fused device-resident pipeline (the measured hot path)
  * ======================================================================================= */
@@ -156,7 +163,9 @@ typedef struct {
     uint64_t edge_count;          /* E = 2 N_l */
     uint64_t lmer_table_capacity, kmer_table_capacity;
     uint32_t retries;             /* table regrow-and-rerun count */
-    float ms_count, ms_graph, ms_total;   /* CUDA-event times of the last run */
+    float ms_count, ms_graph, ms_total;   /* CUDA-event times of the last run: table init + count | graph | both */
+    float ms_count_kernel;                /* the fused encode+count kernel alone */
+    uint32_t kernel_launches;             /* kernels of this library launched by the run */
 } euler_stats;
 
 #define EULER_RUN_EXPAND_EDGES 1u   /* also materialise ee[] / l[] / e[] (needs E < 2^32) */
@@ -195,6 +204,27 @@ int euler_pipeline_device_ptr(euler_ctx *ctx, int which, void **dptr);
 
 /* Euler tour + contigs on the resident graph (needs EXPAND_EDGES); two-call protocol on out */
 int euler_pipeline_contigs(euler_ctx *ctx, char *out, uint64_t *out_bytes, uint64_t *ncontigs);
+
+/* =========================================================================================
+ * Step-level entry points of the reference's fine-grained wrappers (kept for callers; the
+ * product path uses the open-addressing table and union-find components instead)
+ * ======================================================================================= */
+/* pygpuhash.phase1_device (:19): offset[i] = arrival order of key i in bucket hash_h(key), count[] += */
+int euler_compat_phase1(euler_ctx *ctx, const uint64_t *keys, uint64_t n, uint32_t bucketCount,
+                        uint32_t *offset, uint32_t *count);
+/* pygpuhash.copy_to_bucket_device (:77) */
+int euler_compat_copy_to_bucket(euler_ctx *ctx, const uint64_t *keys, const uint32_t *values,
+                                const uint32_t *offset, uint64_t n, const uint32_t *start,
+                                uint32_t bucketCount, uint64_t *bufferK, uint32_t *bufferV);
+/* pygpuhash.bucket_sort_device (:174): TK/TV have bucketCount*520 entries */
+int euler_compat_bucket_sort(euler_ctx *ctx, const uint64_t *bufferK, const uint32_t *bufferV, uint64_t n,
+                             const uint32_t *start, const uint32_t *bucketSize, uint32_t bucketCount,
+                             uint64_t *TK, uint32_t *TV);
+/* pycomponent sub-steps (:17-:654). step: 0 init, 1 s1p1, 2 s1p2, 3 s2p1, 4 s2p2, 5 s3p1, 6 s3p2,
+ * 7 s4p1, 8 s4p2, 9 s5.  Arrays are in/out, n entries each (NULL = zeroed scratch); flag: one u32 */
+int euler_compat_cc_step(euler_ctx *ctx, int step, uint32_t n, uint32_t s, const euler_succ_vertex *v,
+                         uint32_t *prevD, uint32_t *D, uint32_t *Q, uint32_t *t1, uint32_t *val1,
+                         uint32_t *t2, uint32_t *val2, uint32_t *flag);
 
 /* =========================================================================================
  * Deterministic synthetic reads on device, L bytes per read, no separators

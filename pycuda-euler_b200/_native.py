@@ -42,7 +42,8 @@ class Stats(C.Structure):
                 ("n_lmer_windows", C.c_uint64), ("distinct_lmers", C.c_uint64), ("distinct_kmers", C.c_uint64),
                 ("edge_count", C.c_uint64), ("lmer_table_capacity", C.c_uint64),
                 ("kmer_table_capacity", C.c_uint64), ("retries", C.c_uint32),
-                ("ms_count", C.c_float), ("ms_graph", C.c_float), ("ms_total", C.c_float)]
+                ("ms_count", C.c_float), ("ms_graph", C.c_float), ("ms_total", C.c_float),
+                ("ms_count_kernel", C.c_float), ("kernel_launches", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -69,6 +70,7 @@ def load():
         "euler_compute_kmers": [vp, vp, u64, u64, vp, vp],
         "euler_count_lmers": [vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp],
         "euler_count_mers": [vp, vp, vp, u64, u32, u32, vp, vp, vp],
+        "euler_unitigs": [vp, vp, vp, u64, u32, u32, vp, vp, vp],
         "euler_hash_build": [vp, vp, vp, u64, u64, vp, vp],
         "euler_hash_lookup": [vp, vp, vp, u64, vp, u64, vp],
         "euler_exclusive_scan_u32": [vp, vp, u64, vp],
@@ -92,6 +94,10 @@ def load():
         "euler_pipeline_device_ptr": [vp, i32, vp],
         "euler_pipeline_contigs": [vp, vp, vp, vp],
         "euler_synth_reads_dev": [vp, u64, u32, u32, u64, u64, vp],
+        "euler_compat_phase1": [vp, vp, u64, u32, vp, vp],
+        "euler_compat_copy_to_bucket": [vp, vp, vp, vp, u64, vp, u32, vp, vp],
+        "euler_compat_bucket_sort": [vp, vp, vp, u64, vp, vp, u32, vp, vp],
+        "euler_compat_cc_step": [vp, i32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -184,6 +190,20 @@ class Context:
             self.check(self.lib.euler_count_mers(self.h, _p(buf), _p(off), len(off) - 1, int(length), int(limit),
                                                  C.byref(n), _p(keys), _p(vals)))
         return keys, vals
+
+    def unitigs(self, buf, off, K, limit=1):
+        buf = _arr(buf, np.uint8)
+        off = _arr(off, np.uint64)
+        nb, nc = C.c_uint64(0), C.c_uint64(0)
+        self.check(self.lib.euler_unitigs(self.h, _p(buf), _p(off), len(off) - 1, int(K), int(limit), None,
+                                          C.byref(nb), C.byref(nc)))
+        if not nb.value:
+            return []
+        out = np.zeros(nb.value, np.uint8)
+        cap = C.c_uint64(nb.value)
+        self.check(self.lib.euler_unitigs(self.h, _p(buf), _p(off), len(off) - 1, int(K), int(limit), _p(out),
+                                          C.byref(cap), C.byref(nc)))
+        return out.tobytes().decode("ascii").split("\n")[:-1]
 
     # ------------------------------------------------------------------ gpuhash
     def hash_capacity(self, n):
@@ -335,6 +355,50 @@ class Context:
                                                C.byref(cap), C.byref(nc)))
         return out.tobytes().decode("ascii").split("\n")[:-1]
 
+    # ------------------------------------------------------------------ step-level compat wrappers
+    def compat_phase1(self, keys, bucket_count, count=None):
+        keys = _arr(keys, np.uint64)
+        offset = np.zeros(keys.size, np.uint32)
+        count = np.zeros(bucket_count, np.uint32) if count is None else _arr(count, np.uint32).copy()
+        self.check(self.lib.euler_compat_phase1(self.h, _p(keys), keys.size, int(bucket_count), _p(offset), _p(count)))
+        return offset, count
+
+    def compat_copy_to_bucket(self, keys, values, offset, start, bucket_count):
+        keys = _arr(keys, np.uint64)
+        values = _arr(values, np.uint32)
+        offset = _arr(offset, np.uint32)
+        start = _arr(start, np.uint32)
+        bk = np.zeros(keys.size, np.uint64)
+        bv = np.zeros(keys.size, np.uint32)
+        self.check(self.lib.euler_compat_copy_to_bucket(self.h, _p(keys), _p(values), _p(offset), keys.size, _p(start),
+                                                        int(bucket_count), _p(bk), _p(bv)))
+        return bk, bv
+
+    def compat_bucket_sort(self, bufK, bufV, start, bucket_size, bucket_count):
+        bufK = _arr(bufK, np.uint64)
+        bufV = _arr(bufV, np.uint32)
+        start = _arr(start, np.uint32)
+        bucket_size = _arr(bucket_size, np.uint32)
+        TK = np.zeros(int(bucket_count) * 520, np.uint64)
+        TV = np.zeros(int(bucket_count) * 520, np.uint32)
+        self.check(self.lib.euler_compat_bucket_sort(self.h, _p(bufK), _p(bufV), bufK.size, _p(start), _p(bucket_size),
+                                                     int(bucket_count), _p(TK), _p(TV)))
+        return TK, TV
+
+    _CC_STEPS = {"init": 0, "s1p1": 1, "s1p2": 2, "s2p1": 3, "s2p2": 4, "s3p1": 5, "s3p2": 6, "s4p1": 7, "s4p2": 8, "s5": 9}
+
+    def compat_cc_step(self, step, n, v=None, prevD=None, D=None, Q=None, t1=None, val1=None, t2=None, val2=None, s=0):
+        """One Shiloach-Vishkin sub-step; returns what the reference wrapper of that step returns."""
+        def a32(x):
+            return np.zeros(n, np.uint32) if x is None else _arr(x, np.uint32)[:n].copy()
+        vv = np.zeros(n, SV_DTYPE) if v is None else _arr(v, SV_DTYPE)[:n]
+        prevD, D, Q, t1, val1, t2, val2 = (a32(x) for x in (prevD, D, Q, t1, val1, t2, val2))
+        flag = np.zeros(1, np.uint32)
+        self.check(self.lib.euler_compat_cc_step(self.h, self._CC_STEPS[step], int(n), int(s), _p(vv), _p(prevD), _p(D),
+                                                 _p(Q), _p(t1), _p(val1), _p(t2), _p(val2), _p(flag)))
+        return {"init": (D, Q), "s1p1": D, "s1p2": Q, "s2p1": (t1, t2, val1, val2), "s2p2": (D, Q),
+                "s3p1": (t1, t2, val1, val2), "s3p2": D, "s4p1": val1, "s4p2": D, "s5": int(flag[0])}[step]
+
     # ------------------------------------------------------------------ fused pipeline
     def run_host(self, buf, off, l, flags=0, distinct_hint=0):
         buf = _arr(buf, np.uint8)
@@ -343,6 +407,19 @@ class Context:
         self.check(self.lib.euler_pipeline_run_host(self.h, _p(buf), _p(off), len(off) - 1, int(l), int(flags),
                                                     int(distinct_hint), C.byref(st)))
         return st
+
+    def run_host_ptr(self, buf_ptr, off_ptr, nreads, l, flags=0, distinct_hint=0):
+        """run_host on raw host pointers (e.g. pinned torch tensors)."""
+        st = Stats()
+        self.check(self.lib.euler_pipeline_run_host(self.h, C.c_void_p(int(buf_ptr)), C.c_void_p(int(off_ptr)), int(nreads),
+                                                    int(l), int(flags), int(distinct_hint), C.byref(st)))
+        return st
+
+    def download_into(self, which, host_ptr, cap_bytes):
+        nb = C.c_uint64(0)
+        self.check(self.lib.euler_pipeline_artifact_bytes(self.h, which, C.byref(nb)))
+        self.check(self.lib.euler_pipeline_download(self.h, which, C.c_void_p(int(host_ptr)), int(cap_bytes)))
+        return nb.value
 
     def run_dev(self, d_buf, d_off, nreads, n_bases, l, flags=0, distinct_hint=0):
         st = Stats()

@@ -147,6 +147,44 @@ int euler_count_mers(euler_ctx *ctx, const char *buf, const uint64_t *read_off, 
     FINISH(ctx);
 }
 
+int euler_unitigs(euler_ctx *ctx, const char *buf, const uint64_t *read_off, uint64_t nreads, uint32_t K, uint32_t limit,
+                  char *out, uint64_t *out_bytes, uint64_t *ncontigs)
+{
+    ENTER(ctx);
+    if (!read_off || !out_bytes || !ncontigs) return euler_fail(ctx, EULER_ERR_ARG, "null argument");
+    if (K < 2 || K > 32) return euler_fail(ctx, EULER_ERR_ARG, "K %u out of range [2,32]", K);
+    const u64 cap_out = *out_bytes;
+    *out_bytes = 0; *ncontigs = 0;
+    const u64 B = read_off[nreads];
+    if (!B) return EULER_OK;
+    DevTmp<unsigned char> d_buf(ctx, B + 16);
+    DevTmp<u64> d_off(ctx, nreads + 1), d_stats(ctx, 8);
+    DevTmp<u32> d_bits(ctx, B / 32 + 2);
+    TMP_CHECK(ctx, d_bits); TMP_CHECK(ctx, d_stats);
+    EULER_TRY(upload(ctx, d_buf, (const unsigned char *)buf, B));
+    EULER_TRY(upload(ctx, d_off, (const u64 *)read_off, nreads + 1));
+    EULER_TRY(enc_mark_starts(ctx, d_off, nreads, B, d_bits));
+    const u64 cap = euler_hash_capacity(B);
+    DevTmp<u64> tk(ctx, cap);
+    DevTmp<u32> tc(ctx, cap);
+    TMP_CHECK(ctx, tk); TMP_CHECK(ctx, tc);
+    CUDA_TRY(ctx, cudaMemsetAsync(d_stats, 0, 8 * sizeof(u64), ctx->stream));
+    EULER_TRY(graph_table_clear(ctx, tk, tc, cap));
+    EULER_TRY(enc_count_canonical(ctx, d_buf, B, d_bits, K, tk, tc, cap, d_stats));
+    u64 h[3];
+    EULER_TRY(read_u64s(ctx, d_stats, h, 3));
+    if (h[2]) return euler_fail(ctx, EULER_ERR_OVERFLOW, "count table overflow");
+    char *d_text = nullptr;
+    u64 bytes = 0, nc = 0, nn = 0;
+    EULER_TRY(unitig_from_table(ctx, tk, tc, cap, K, limit, &d_text, &bytes, &nc, &nn));
+    *out_bytes = bytes; *ncontigs = nc;
+    if (out) {
+        if (cap_out < bytes) return euler_fail(ctx, EULER_ERR_ARG, "output capacity too small");
+        EULER_TRY(download(ctx, out, (const char *)d_text, bytes));
+    }
+    FINISH(ctx);
+}
+
 int euler_hash_build(euler_ctx *ctx, const uint64_t *keys, const uint32_t *values, uint64_t n, uint64_t capacity,
                      uint64_t *TK, uint32_t *TV)
 {

@@ -89,3 +89,7 @@ int tour_emit_contigs(euler_ctx *ctx, const euler_vertex *ev, u32 vcount, const 
 
 // ---- synth.cu
 int synth_reads(euler_ctx *ctx, u64 G, u32 L, u32 err_ppm, u64 first, u64 nreads, void *d_out);
+
+// ---- unitig.cu
+int unitig_from_table(euler_ctx *ctx, const u64 *keys, const u32 *cnt, u64 cap, u32 K, u32 limit, char **d_out,
+                      u64 *out_bytes, u64 *ncontigs, u64 *n_nodes);

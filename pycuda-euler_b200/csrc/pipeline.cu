@@ -78,7 +78,7 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
     u64 lt_cap = cap_for(est_l), vt_cap = cap_for(est_v);
 
     u64 h[8] = {0};
-    u32 retries = 0;
+    u32 retries = 0, launches = 1;  // mark_starts
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
     EULER_TRY(enc_mark_starts(ctx, P->d_off, P->nreads, B, P->start_bits.ptr()));
     while (true) {
@@ -91,9 +91,11 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
         CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 16 * sizeof(u64), s));
         EULER_TRY(graph_table_clear(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap));
         EULER_TRY(graph_table_clear(ctx, P->vt_keys.ptr(), nullptr, vt_cap));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
         EULER_TRY(enc_count_canonical(ctx, P->d_buf, B, P->start_bits.ptr(), l, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap,
                                       P->stats.ptr()));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+        launches += 4;  // count, slot scan, vertex insert, slot scan
         EULER_TRY(graph_slot_scan(ctx, P->lt_keys.ptr(), lt_cap, l, P->lt_base.ptr(), P->stats.ptr() + 3));
         EULER_TRY(graph_vertex_insert(ctx, P->lt_keys.ptr(), lt_cap, l, P->vt_keys.ptr(), vt_cap, P->stats.ptr() + 2));
         EULER_TRY(graph_slot_scan(ctx, P->vt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(), P->stats.ptr() + 4));
@@ -132,6 +134,7 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
         EULER_TRY(graph_assign_sorted_ids(ctx, P->vkeys.ptr(), V, P->vt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(),
                                           P->vt_id1.ptr()));
         vt.id1 = P->vt_id1.ptr();
+        launches += 3 * ((2 * l + 7) / 8) + 3 * ((2 * k + 7) / 8) + 1;
     }
     CUDA_TRY(ctx, cudaMemsetAsync(P->lcount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
     CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
@@ -142,8 +145,10 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
     EULER_TRY(scan_exclusive(ctx, ScanInU32{P->lvals.ptr()}, U_l, P->loffs.ptr(), P->stats.ptr() + 5));
     EULER_TRY(graph_setup_vertices(ctx, P->vkeys.ptr(), V, P->lcount.ptr(), P->lstart.ptr(), P->ecount.ptr(),
                                    P->estart.ptr(), P->ev.ptr()));
+    launches += 7;  // 2 compactions, degree slots, 3 scans, vertices
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
     if (flags & EULER_RUN_EXPAND_EDGES) {
+        launches += 1;
         EULER_TRY(P->ee.reserve(ctx, E)); EULER_TRY(P->lev.reserve(ctx, E)); EULER_TRY(P->ent.reserve(ctx, E));
         EULER_TRY(graph_setup_edges(ctx, P->lkeys.ptr(), P->lvals.ptr(), P->loffs.ptr(), U_l, l, P->ev1.ptr(), P->ev2.ptr(),
                                     P->lstart.ptr(), P->estart.ptr(), (u32)E, P->ee.ptr(), P->lev.ptr(), P->ent.ptr()));
@@ -162,6 +167,8 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
     cudaEventElapsedTime(&st.ms_count, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&st.ms_graph, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[2]);
+    cudaEventElapsedTime(&st.ms_count_kernel, ctx->ev[4], ctx->ev[1]);
+    st.kernel_launches = launches;
     if (stats) *stats = st;
     return EULER_OK;
 }

@@ -428,157 +428,26 @@ int tour_contig_starts(euler_ctx *ctx, const euler_edge *ee, u32 ecount, u32 *st
     return EULER_OK;
 }
 
-// ---- contig emission: the host walk eulercuda.py:351-402 as list ranking + scatter -------------
-// chain node = Euler edge.  pred/succ links come from ee[].s; cycles are cut at their minimum
-// edge id (where the reference's second loop :378-402 enters them).  A contig is the first
-// vertex's k-mer followed by the last base of v2 of every edge of the chain (B12).
-__global__ void __launch_bounds__(TB) emit_pred_kernel(const euler_edge *__restrict__ ee, u32 n, u32 *__restrict__ pred)
-{
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const u32 s = ee[t].s;
-    if (s < n) pred[s] = t;
-}
-__global__ void __launch_bounds__(TB) emit_succ_vertex_kernel(const euler_edge *__restrict__ ee, const u32 *__restrict__ pred, u32 n,
-                                                               euler_succ_vertex *__restrict__ v)
-{
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    euler_succ_vertex x;
-    x.vid = t;
-    x.n1 = ee[t].s < n ? ee[t].s : n;
-    x.n2 = pred[t];
-    v[t] = x;
-}
-__global__ void __launch_bounds__(TB) emit_has_start_kernel(const u32 *__restrict__ pred, const u32 *__restrict__ D, u32 n,
-                                                             u32 *__restrict__ has_start)
-{
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n && pred[t] >= n) has_start[D[t]] = 1u;
-}
-// anc[i] = (ancestor << 32) | distance; heads point to themselves with distance 0
-__global__ void __launch_bounds__(TB) emit_rank_init_kernel(const u32 *__restrict__ pred, const u32 *__restrict__ D,
-                                                             const u32 *__restrict__ has_start, u32 n, u64 *__restrict__ anc,
-                                                             u32 *__restrict__ head_kind)
-{
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const u32 p = pred[t];
-    u32 kind = 0;  // 0 not a head, 1 path head (contig start), 2 cycle head
-    if (p >= n) kind = 1;
-    else if (D[t] == t && !has_start[t]) kind = 2;
-    head_kind[t] = kind;
-    anc[t] = kind ? ((u64)t << 32) : (((u64)p << 32) | 1ull);
-}
-__global__ void __launch_bounds__(TB) emit_rank_step_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, u32 n, u32 *changed)
-{
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const u64 a = in[t];
-    const u32 anc = (u32)(a >> 32);
-    const u64 b = in[anc];
-    const u32 anc2 = (u32)(b >> 32);
-    if (anc2 != anc) {
-        out[t] = ((u64)anc2 << 32) | (u64)((u32)a + (u32)b);
-        *changed = 1u;
-    } else {
-        out[t] = a + (anc == t ? 0ull : (u64)(u32)b);  // ancestor is a head: its distance is 0
-    }
-}
-struct KindIn {
-    const u32 *k;
-    u32 want;
-    __device__ __forceinline__ u32 operator()(u64 i) const { return k[i] == want ? 1u : 0u; }
+// ---- contig emission: generatePartialContig host walk eulercuda.py:351-402 on device -----------
+// chain node = Euler edge.  A contig is the first vertex's k-mer followed by the last base of v2
+// of every edge of the chain (B12).  See chain.cuh.
+#include "chain.cuh"
+
+struct EulerChainModel {
+    const euler_vertex *ev;
+    const euler_edge *ee;
+    u32 n;
+    static constexpr u32 HEAD_APPENDS = 1;
+    __device__ __forceinline__ u32 succ(u32 i) const { return ee[i].s; }
+    __device__ __forceinline__ u64 head_key(u32 i) const { return ev[ee[i].v1].vid; }
+    __device__ __forceinline__ char base(u32 i) const { return "ACGT"[ev[ee[i].v2].vid & 3]; }
+    __device__ __forceinline__ bool emit(const u32 *, u32) const { return true; }
 };
-// per tail node: contig length bytes at the contig's ordinal
-__global__ void __launch_bounds__(TB) emit_len_kernel(const euler_edge *__restrict__ ee, const u32 *__restrict__ head_kind,
-                                                       const u64 *__restrict__ anc, const u32 *__restrict__ ord1,
-                                                       const u32 *__restrict__ ord2, u32 n_starts, u32 n, u32 k,
-                                                       const u32 *__restrict__ pred, u32 *__restrict__ len_by_ord)
-{
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    // tail: no successor, or successor is the (cut) cycle head
-    const u32 s = ee[t].s;
-    const u32 head = (u32)(anc[t] >> 32);
-    const bool tail = (s >= n) || (s == head && head_kind[head] == 2);
-    if (!tail) return;
-    const u32 dist = (u32)anc[t];
-    const u32 ord = head_kind[head] == 1 ? ord1[head] : n_starts + ord2[head];
-    len_by_ord[ord] = k + dist + 1 + 1;  // k-mer + (dist+1) bases + '\n'
-}
-__global__ void __launch_bounds__(TB) emit_write_kernel(const euler_vertex *__restrict__ ev, const euler_edge *__restrict__ ee,
-                                                         const u32 *__restrict__ head_kind, const u64 *__restrict__ anc,
-                                                         const u32 *__restrict__ ord1, const u32 *__restrict__ ord2,
-                                                         u32 n_starts, u32 n, u32 k, const u32 *__restrict__ off_by_ord,
-                                                         const u32 *__restrict__ len_by_ord, char *__restrict__ out)
-{
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const u32 head = (u32)(anc[t] >> 32), dist = (u32)anc[t];
-    const u32 ord = head_kind[head] == 1 ? ord1[head] : n_starts + ord2[head];
-    const u64 o = off_by_ord[ord];
-    const euler_edge e = ee[t];
-    out[o + k + dist] = "ACGT"[ev[e.v2].vid & 3];
-    if (t == head) {
-        u64 x = ev[e.v1].vid;  // getString eulercuda.py:315-321
-        for (u32 i = 0; i < k; i++) { out[o + k - 1 - i] = "ACGT"[x & 3]; x >>= 2; }
-        out[o + len_by_ord[ord] - 1] = '\n';
-    }
-}
 
 int tour_emit_contigs(euler_ctx *ctx, const euler_vertex *ev, u32 vcount, const euler_edge *ee, u32 n, u32 l,
                       char **d_out, u64 *out_bytes, u64 *ncontigs)
 {
     (void)vcount;
-    *d_out = nullptr; *out_bytes = 0; *ncontigs = 0;
-    if (!n) return EULER_OK;
-    const u32 k = l - 1;
-    DevTmp<u32> pred(ctx, n), D(ctx, n), has_start(ctx, n), head_kind(ctx, n), ord1(ctx, n), ord2(ctx, n), changed(ctx, 1);
-    DevTmp<euler_succ_vertex> sv(ctx, n);
-    DevTmp<u64> ancA(ctx, n), ancB(ctx, n), totals(ctx, 4);
-    TMP_CHECK(ctx, pred); TMP_CHECK(ctx, D); TMP_CHECK(ctx, has_start); TMP_CHECK(ctx, head_kind); TMP_CHECK(ctx, ord1);
-    TMP_CHECK(ctx, ord2); TMP_CHECK(ctx, changed); TMP_CHECK(ctx, sv); TMP_CHECK(ctx, ancA); TMP_CHECK(ctx, ancB);
-    TMP_CHECK(ctx, totals);
-    const unsigned g = grid_for(n, TB);
-    fill_u32_kernel<<<g, TB, 0, ctx->stream>>>(pred, n, n);
-    emit_pred_kernel<<<g, TB, 0, ctx->stream>>>(ee, n, pred);
-    emit_succ_vertex_kernel<<<g, TB, 0, ctx->stream>>>(ee, pred, n, sv);
-    EULER_TRY(tour_components(ctx, sv, n, D));
-    CUDA_TRY(ctx, cudaMemsetAsync(has_start, 0, (size_t)n * 4, ctx->stream));
-    emit_has_start_kernel<<<g, TB, 0, ctx->stream>>>(pred, D, n, has_start);
-    emit_rank_init_kernel<<<g, TB, 0, ctx->stream>>>(pred, D, has_start, n, ancA, head_kind);
-    CUDA_TRY(ctx, cudaGetLastError());
-    u64 *cur = ancA, *nxt = ancB;
-    for (int round = 0; round < 40; round++) {
-        CUDA_TRY(ctx, cudaMemsetAsync(changed, 0, 4, ctx->stream));
-        emit_rank_step_kernel<<<g, TB, 0, ctx->stream>>>(cur, nxt, n, changed);
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_pinned, changed.get(), 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        u64 *t = cur; cur = nxt; nxt = t;
-        if (!*(u32 *)ctx->h_pinned) break;
-    }
-    EULER_TRY(scan_exclusive(ctx, KindIn{head_kind, 1u}, n, ord1.get(), totals.get() + 0));
-    EULER_TRY(scan_exclusive(ctx, KindIn{head_kind, 2u}, n, ord2.get(), totals.get() + 1));
-    u64 h[2];
-    EULER_TRY(read_u64s(ctx, totals, h, 2));
-    const u64 nc = h[0] + h[1];
-    if (!nc) return EULER_OK;
-    DevTmp<u32> len_by_ord(ctx, nc), off_by_ord(ctx, nc);
-    TMP_CHECK(ctx, len_by_ord); TMP_CHECK(ctx, off_by_ord);
-    emit_len_kernel<<<g, TB, 0, ctx->stream>>>(ee, head_kind, cur, ord1, ord2, (u32)h[0], n, k, pred, len_by_ord);
-    EULER_TRY(scan_exclusive(ctx, ScanInU32{len_by_ord}, nc, off_by_ord.get(), totals.get() + 2));
-    u64 bytes = 0;
-    EULER_TRY(read_u64(ctx, totals.get() + 2, &bytes));
-    if (bytes >= 0xffffffffull) return euler_fail(ctx, EULER_ERR_RANGE, "contig text %llu bytes exceeds u32 offsets", bytes);
-    DevBuf &text = ctx->text_buf;
-    EULER_TRY(dev_reserve(ctx, text, bytes));
-    emit_write_kernel<<<g, TB, 0, ctx->stream>>>(ev, ee, head_kind, cur, ord1, ord2, (u32)h[0], n, k, off_by_ord, len_by_ord,
-                                                 (char *)text.p);
-    CUDA_TRY(ctx, cudaGetLastError());
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    *d_out = (char *)text.p;
-    *out_bytes = bytes;
-    *ncontigs = nc;
-    return EULER_OK;
+    EulerChainModel m = {ev, ee, n};
+    return chain_emit(ctx, m, n, l - 1, d_out, out_bytes, ncontigs);
 }

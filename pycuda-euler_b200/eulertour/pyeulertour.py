@@ -1,0 +1,5 @@
+"""src/eulertour/pyeulertour.py layout: same module as eulercuda.pyeulertour."""
+from eulercuda.pyeulertour import *  # noqa: F401,F403
+from eulercuda import pyeulertour as _m
+__all__ = [n for n in dir(_m) if not n.startswith("__")]
+globals().update({n: getattr(_m, n) for n in __all__})
