@@ -108,34 +108,39 @@ __global__ void __launch_bounds__(CNT_BLOCK) count_canonical_kernel(const uint4 
         nl_tot += cnts & 0xffffu;
         nk_tot += cnts >> 16;
 
-        // two batches of 8 independent probes: issue the home-slot loads first, then resolve
+        // Two batches of 8 keys.  Probing proceeds in warp-uniform rounds: every round first issues
+        // the loads of all still-pending keys of the batch (8 independent requests per lane in
+        // flight), then resolves them, so lanes that need another probe take it together instead
+        // of serialising one lane at a time.
 #pragma unroll
         for (int b = 0; b < 16; b += 8) {
             u64 slot[8], cur[8];
+            u32 pend = (okmask >> b) & 0xffu;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (okmask & (1u << (b + i))) {
-                    slot[i] = hash_slot(keys[b + i], cap);
-                    cur[i] = ld_cg_u64(tab_keys + slot[i]);
-                }
-            }
+            for (int i = 0; i < 8; i++) slot[i] = hash_slot(keys[b + i], cap);
+            u64 probes = 0;
+            while (__any_sync(0xffffffffu, pend != 0)) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (!(okmask & (1u << (b + i)))) continue;
-                const u64 key = keys[b + i];
-                u64 s = slot[i], kv = cur[i];
-                u64 probe = 0;
-                while (true) {
-                    if (kv == key) break;
-                    if (kv == EULER_EMPTY_KEY) {
-                        const u64 old = atomicCAS(tab_keys + s, EULER_EMPTY_KEY, key);
-                        if (old == EULER_EMPTY_KEY || old == key) break;
+                for (int i = 0; i < 8; i++)
+                    if (pend & (1u << i)) cur[i] = ld_cg_u64(tab_keys + slot[i]);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (pend & (1u << i)) {
+                        const u64 key = keys[b + i];
+                        bool done = cur[i] == key;
+                        if (!done && cur[i] == EULER_EMPTY_KEY) {
+                            const u64 old = atomicCAS(tab_keys + slot[i], EULER_EMPTY_KEY, key);
+                            done = (old == EULER_EMPTY_KEY) || (old == key);
+                        }
+                        if (done) {
+                            atomicAdd(tab_cnt + slot[i], 1u);
+                            pend &= ~(1u << i);
+                        } else if (++slot[i] == cap) {
+                            slot[i] = 0;
+                        }
                     }
-                    if (++probe >= max_probe) { overflow = true; break; }
-                    if (++s == cap) s = 0;
-                    kv = ld_cg_u64(tab_keys + s);
                 }
-                if (probe < max_probe) atomicAdd(tab_cnt + s, 1u);
+                if (++probes >= max_probe && pend) { overflow = true; pend = 0; }
             }
         }
     }
