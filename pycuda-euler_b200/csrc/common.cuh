@@ -41,6 +41,7 @@ struct euler_ctx {
     int num_sms = EULER_SMS;
     size_t l2_bytes = 0;
     size_t persist_max = 0;
+    size_t l2_part_budget = 0;  // table bytes one count pass may own (0 = default)
 };
 
 int euler_fail(euler_ctx *ctx, int code, const char *fmt, ...);
@@ -84,19 +85,15 @@ static inline unsigned grid_for(u64 n, unsigned block)
 // ---------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
-__device__ __forceinline__ u64 mix64(u64 x)
+// Table hash: xor-fold, one 64-bit multiply (Fibonacci), then the top 32 bits scaled into the
+// bucket range with a single 32x32->64 multiply.  Buckets are 4 consecutive slots (one 32-byte
+// sector), so a probe is one 256-bit load.
+#define EULER_BUCKET 4
+__device__ __forceinline__ u64 hash_bucket(u64 key, u32 nbuckets)
 {
-    // murmur3 fmix64
-    x ^= x >> 33;
-    x *= 0xff51afd7ed558ccdull;
-    x ^= x >> 33;
-    x *= 0xc4ceb9fe1a85ec53ull;
-    x ^= x >> 33;
-    return x;
+    const u64 h = (key ^ (key >> 29)) * 0x9E3779B97F4A7C15ull;
+    return ((h >> 32) * (u64)nbuckets) >> 32;
 }
-
-// slot in [0, cap) from a 64-bit hash (Lemire fastrange)
-__device__ __forceinline__ u64 hash_slot(u64 key, u64 cap) { return __umul64hi(mix64(key), cap); }
 
 __device__ __forceinline__ u64 key_mask_d(u32 len) { return len >= 32 ? ~0ull : ((1ull << (2 * len)) - 1ull); }
 
@@ -130,37 +127,71 @@ __device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p)
     return r;
 }
 
-// ---- open-addressing table primitives (linear probing, out-of-band-free sentinel) --------------
-// Canonical l-mers never equal all-ones (canon(T^32)=A^32=0) and k-mers use <= 62 bits, so
-// 0xFFFF... is a safe EMPTY for every key this library stores.
-
-// returns slot of `key` after inserting it if absent; EULER_NO_SLOT on overflow
+// ---- open-addressing table primitives ---------------------------------------------------------
+// Bucketised linear probing: a key lives in its home bucket (4 slots = one 32 B sector) or, when
+// that is full, in the following buckets.  Slots of a bucket fill in order, so the first EMPTY
+// slot ends a lookup.  Canonical l-mers never equal all-ones (canon(T^32)=A^32=0) and k-mers use
+// <= 62 bits, so 0xFFFF... is a safe EMPTY for every key this library stores.
 #define EULER_NO_SLOT 0xFFFFFFFFFFFFFFFFull
+struct K4 {
+    u64 k[4];
+};
+__device__ __forceinline__ K4 ld_bucket_cg(const u64 *p)
+{
+    K4 r;
+    asm volatile("ld.global.cg.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.k[0]), "=l"(r.k[1]), "=l"(r.k[2]), "=l"(r.k[3]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ K4 ld_bucket_nc(const u64 *p)
+{
+    K4 r;
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.k[0]), "=l"(r.k[1]), "=l"(r.k[2]), "=l"(r.k[3]) : "l"(p));
+    return r;
+}
+
+// Try to place / find `key` in the bucket `q` loaded from keys + 4*bucket.  Returns the slot
+// index inside the bucket (0..3) or -1 when the bucket is full of other keys.
+__device__ __forceinline__ int bucket_claim(u64 *bucket_keys, const K4 &q, u64 key)
+{
+#pragma unroll
+    for (int j = 0; j < EULER_BUCKET; j++) {
+        const u64 kv = q.k[j];
+        if (kv == key) return j;
+        if (kv == EULER_EMPTY_KEY) {
+            const u64 old = atomicCAS(bucket_keys + j, EULER_EMPTY_KEY, key);
+            if (old == EULER_EMPTY_KEY || old == key) return j;
+        }
+    }
+    return -1;
+}
+
+// returns slot of `key` after inserting it if absent; EULER_NO_SLOT on overflow. cap % 4 == 0.
 __device__ __forceinline__ u64 table_insert(u64 *keys, u64 cap, u64 key, u64 max_probe)
 {
-    u64 slot = hash_slot(key, cap);
+    const u32 nb = (u32)(cap / EULER_BUCKET);
+    u64 b = hash_bucket(key, nb);
     for (u64 probe = 0; probe < max_probe; probe++) {
-        u64 k = ld_cg_u64(keys + slot);
-        if (k == key) return slot;
-        if (k == EULER_EMPTY_KEY) {
-            u64 old = atomicCAS(keys + slot, EULER_EMPTY_KEY, key);
-            if (old == EULER_EMPTY_KEY || old == key) return slot;
-        }
-        slot++;
-        if (slot == cap) slot = 0;
+        u64 *bk = keys + b * EULER_BUCKET;
+        const K4 q = ld_bucket_cg(bk);
+        const int j = bucket_claim(bk, q, key);
+        if (j >= 0) return b * EULER_BUCKET + j;
+        if (++b == nb) b = 0;
     }
     return EULER_NO_SLOT;
 }
 
 __device__ __forceinline__ u64 table_find(const u64 *keys, u64 cap, u64 key)
 {
-    u64 slot = hash_slot(key, cap);
-    for (u64 probe = 0; probe < cap; probe++) {
-        u64 k = __ldg(keys + slot);
-        if (k == key) return slot;
-        if (k == EULER_EMPTY_KEY) return EULER_NO_SLOT;
-        slot++;
-        if (slot == cap) slot = 0;
+    const u32 nb = (u32)(cap / EULER_BUCKET);
+    u64 b = hash_bucket(key, nb);
+    for (u64 probe = 0; probe < nb; probe++) {
+        const K4 q = ld_bucket_nc(keys + b * EULER_BUCKET);
+#pragma unroll
+        for (int j = 0; j < EULER_BUCKET; j++) {
+            if (q.k[j] == key) return b * EULER_BUCKET + j;
+            if (q.k[j] == EULER_EMPTY_KEY) return EULER_NO_SLOT;
+        }
+        if (++b == nb) b = 0;
     }
     return EULER_NO_SLOT;
 }

@@ -1,6 +1,7 @@
 // encode.cu -- encoder kernels and the fused encode+count kernel (the hot kernel of the path).
 #include "encode.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 // ---- read-start bitmap: bit t set iff a read starts at byte t ---------------------------------
 __global__ void mark_starts_kernel(const u64 *__restrict__ off, u64 nreads, u32 *__restrict__ bits)
@@ -83,60 +84,92 @@ int enc_compute_kmers(euler_ctx *ctx, const u64 *d_lmers, u64 n, u64 mask, u64 *
 // Table: SoA keys u64[cap] / counts u32[cap], linear probing, EMPTY = all-ones (never canonical).
 #define CNT_BLOCK 256
 
-__global__ void __launch_bounds__(CNT_BLOCK) count_canonical_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
-                                                                     const u32 *__restrict__ start_bits, u32 l,
-                                                                     u64 *__restrict__ tab_keys, u32 *__restrict__ tab_cnt,
-                                                                     u64 cap, u64 ntiles, u64 *__restrict__ stats)
+// Rolling formulation: each lane walks the 16 bases of its chunk once, keeping the forward and
+// reverse-complement l-mers in two 64-bit registers (shift in / shift out), plus two run lengths
+// (valid bases, bases since the last read start) that decide whether the window ending here is a
+// whole l-mer / k-mer of one read.  Keys are produced four at a time and probed right away, so the
+// live state is ~60 registers and the loop body stays inside the instruction cache.
+__global__ void __launch_bounds__(CNT_BLOCK, 4) count_canonical_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
+                                                                        const u32 *__restrict__ start_bits, u32 l,
+                                                                        u64 *__restrict__ tab_keys, u32 *__restrict__ tab_cnt,
+                                                                        u64 cap, u64 ntiles, u64 *__restrict__ stats,
+                                                                        u64 part_lo, u64 part_hi, int count_windows)
 {
     const int lane = threadIdx.x & 31;
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
-    const u64 max_probe = cap < 8192 ? cap : 8192;
+    const u32 nbuckets = (u32)(cap / EULER_BUCKET);
+    const u32 max_probe = nbuckets < 4096 ? nbuckets : 4096;
+    const u32 k = l - 1;
+    const u32 top = 2 * (l - 1);
+    const u64 kmask = key_mask_d(l);
     u32 nl_tot = 0, nk_tot = 0;
     bool overflow = false;
 
     for (u64 tile = warp; tile < ntiles; tile += nwarps) {
         const long long chunk = (long long)(tile * ENC_ADV) - ENC_HALO + lane;
         const Chunk c = load_chunk(buf16, chunk, n_bases, start_bits);
-        u64 keys[16];
-        u32 okmask = 0;
-        const u32 cnts = for_each_window(c, l, lane, [&](int i, u64 key) {
-            const u64 rc = revcomp64(key, l);
-            keys[i] = key < rc ? key : rc;
-            okmask |= 1u << i;
-        });
-        nl_tot += cnts & 0xffffu;
-        nk_tot += cnts >> 16;
+        const u32 p1 = __shfl_up_sync(0xffffffffu, c.codes, 1), p2 = __shfl_up_sync(0xffffffffu, c.codes, 2);
+        const u32 v1 = __shfl_up_sync(0xffffffffu, c.vmask, 1), v2 = __shfl_up_sync(0xffffffffu, c.vmask, 2);
+        const u32 s1 = __shfl_up_sync(0xffffffffu, c.smask, 1), s2 = __shfl_up_sync(0xffffffffu, c.smask, 2);
+        // state after the base just before this chunk
+        u64 f = ((u64)p2 << 32) | p1;
+        u64 rc = revcomp64(f & kmask, l);
+        const u32 pv = (v2 << 16) | v1, ps = (s2 << 16) | s1;   // bit 0 = the most recent base
+        u32 vrun = (pv == 0xffffffffu) ? 32u : (u32)__ffs(~pv) - 1u;
+        u32 srun = ps ? (u32)__ffs(ps) - 1u : 32u;
+        u32 codes = c.codes;
+        u32 vm = (lane < ENC_HALO) ? 0u : (c.vmask << 16);     // halo lanes own no windows
+        u32 sm = c.smask << 16;
+        if (lane < ENC_HALO) vrun = 0;
 
-        // Two batches of 8 keys.  Probing proceeds in warp-uniform rounds: every round first issues
-        // the loads of all still-pending keys of the batch (8 independent requests per lane in
-        // flight), then resolves them, so lanes that need another probe take it together instead
-        // of serialising one lane at a time.
+#pragma unroll 1
+        for (int b = 0; b < 4; b++) {
+            u64 key[4];
+            u32 pend = 0;
 #pragma unroll
-        for (int b = 0; b < 16; b += 8) {
-            u64 slot[8], cur[8];
-            u32 pend = (okmask >> b) & 0xffu;
+            for (int i = 0; i < 4; i++) {
+                const u32 cc = codes >> 30;
+                codes <<= 2;
+                const bool valid = (vm >> 31) != 0, start = (sm >> 31) != 0;
+                vm <<= 1;
+                sm <<= 1;
+                f = (f << 2) | cc;
+                rc = (rc >> 2) | ((u64)(3u - cc) << top);
+                vrun = valid ? vrun + 1u : 0u;
+                srun = start ? 0u : srun + 1u;
+                nk_tot += (vrun >= k && srun + 1u >= k) ? 1u : 0u;
+                const bool ok = vrun >= l && srun + 1u >= l;
+                nl_tot += ok ? 1u : 0u;
+                const u64 fm = f & kmask;
+                key[i] = fm < rc ? fm : rc;
+                pend |= (ok ? 1u : 0u) << i;
+            }
+            // Probing proceeds in warp-uniform rounds: every round first issues the 256-bit bucket
+            // loads of all still-pending keys (4 independent 32 B requests per lane in flight), then
+            // resolves them, so lanes that need another bucket take it together.
+            u32 bucket[4];
+            K4 q[4];
 #pragma unroll
-            for (int i = 0; i < 8; i++) slot[i] = hash_slot(keys[b + i], cap);
-            u64 probes = 0;
+            for (int i = 0; i < 4; i++) {
+                bucket[i] = (u32)hash_bucket(key[i], nbuckets);
+                // L2 blocking knob: this launch only owns home buckets in [part_lo, part_hi)
+                if (bucket[i] < part_lo || bucket[i] >= part_hi) pend &= ~(1u << i);
+            }
+            u32 probes = 0;
             while (__any_sync(0xffffffffu, pend != 0)) {
 #pragma unroll
-                for (int i = 0; i < 8; i++)
-                    if (pend & (1u << i)) cur[i] = ld_cg_u64(tab_keys + slot[i]);
+                for (int i = 0; i < 4; i++)
+                    if (pend & (1u << i)) q[i] = ld_bucket_cg(tab_keys + (u64)bucket[i] * EULER_BUCKET);
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
+                for (int i = 0; i < 4; i++) {
                     if (pend & (1u << i)) {
-                        const u64 key = keys[b + i];
-                        bool done = cur[i] == key;
-                        if (!done && cur[i] == EULER_EMPTY_KEY) {
-                            const u64 old = atomicCAS(tab_keys + slot[i], EULER_EMPTY_KEY, key);
-                            done = (old == EULER_EMPTY_KEY) || (old == key);
-                        }
-                        if (done) {
-                            atomicAdd(tab_cnt + slot[i], 1u);
+                        const int j = bucket_claim(tab_keys + (u64)bucket[i] * EULER_BUCKET, q[i], key[i]);
+                        if (j >= 0) {
+                            atomicAdd(tab_cnt + (u64)bucket[i] * EULER_BUCKET + j, 1u);
                             pend &= ~(1u << i);
-                        } else if (++slot[i] == cap) {
-                            slot[i] = 0;
+                        } else if (++bucket[i] == nbuckets) {
+                            bucket[i] = 0;
                         }
                     }
                 }
@@ -150,7 +183,7 @@ __global__ void __launch_bounds__(CNT_BLOCK) count_canonical_kernel(const uint4 
         nl_tot += __shfl_xor_sync(0xffffffffu, nl_tot, d);
         nk_tot += __shfl_xor_sync(0xffffffffu, nk_tot, d);
     }
-    if (lane == 0) {
+    if (lane == 0 && count_windows) {
         if (nl_tot) atomicAdd(stats + 0, (u64)nl_tot);
         if (nk_tot) atomicAdd(stats + 1, (u64)nk_tot);
     }
@@ -167,8 +200,24 @@ int enc_count_canonical(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u3
     u64 grid = (u64)ctx->num_sms * 4;
     const u64 need = (ntiles + warps_per_block - 1) / warps_per_block;
     if (grid > need) grid = need;
-    count_canonical_kernel<<<(unsigned)(grid ? grid : 1), CNT_BLOCK, 0, ctx->stream>>>(
-        (const uint4 *)d_buf, n_bases, d_bits, l, tab_keys, tab_cnt, cap, ntiles, d_stats);
+    // L2 blocking: split the table into `parts` contiguous slot ranges small enough to stay
+    // resident in L2 and make one pass over the reads per range (re-encoding is cheaper than
+    // missing L2 on every probe).
+    u64 parts = 1;
+    const char *env = getenv("EULER_B200_COUNT_PARTS");
+    if (env && atoi(env) > 0) parts = (u64)atoi(env);
+    else {
+        const u64 table_bytes = cap * 12;
+        const u64 budget = ctx->l2_part_budget ? ctx->l2_part_budget : (48ull << 20);
+        parts = 1;  // re-encoding costs more than the misses it saves (measured); kept as a knob
+        (void)table_bytes; (void)budget;
+    }
+    for (u64 p = 0; p < parts; p++) {
+        const u64 nb = cap / EULER_BUCKET;
+        const u64 lo = nb * p / parts, hi = nb * (p + 1) / parts;
+        count_canonical_kernel<<<(unsigned)(grid ? grid : 1), CNT_BLOCK, 0, ctx->stream>>>(
+            (const uint4 *)d_buf, n_bases, d_bits, l, tab_keys, tab_cnt, cap, ntiles, d_stats, lo, hi, p == 0 ? 1 : 0);
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(GB) vertex_insert_kernel(const u64 *__restrict
     if (key == EULER_EMPTY_KEY) return;
     const u32 k = l - 1;
     const u64 kmask = key_mask_d(k);
-    const u64 max_probe = vt_cap < 8192 ? vt_cap : 8192;
+    const u64 max_probe = vt_cap / EULER_BUCKET < 4096 ? vt_cap / EULER_BUCKET : 4096;
     const u64 a = table_insert(vt_keys, vt_cap, canon64(key >> 2, k), max_probe);
     const u64 b = table_insert(vt_keys, vt_cap, canon64(key & kmask, k), max_probe);
     if (a == EULER_NO_SLOT || b == EULER_NO_SLOT) atomicOr((unsigned long long *)flags, 2ull);
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(GB) plain_build_kernel(const u64 *__restrict__
 {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const u64 slot = table_insert(TK, cap, keys[i], cap);
+    const u64 slot = table_insert(TK, cap, keys[i], cap / EULER_BUCKET);
     if (slot == EULER_NO_SLOT) { atomicOr((unsigned long long *)flags, 1ull); return; }
     TV[slot] = vals[i];
 }

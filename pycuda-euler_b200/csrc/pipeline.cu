@@ -6,6 +6,7 @@
 #include "scan.cuh"
 #include "sort.cuh"
 #include "tmp.cuh"
+#include <stdlib.h>
 
 struct Pipeline {
     u32 l = 0, flags = 0;
@@ -55,7 +56,17 @@ void pipeline_destroy(Pipeline *p)
 
 static u64 round_up(u64 x, u64 m) { return (x + m - 1) / m * m; }
 // table capacity for `n` expected distinct keys at load factor ~0.55
-static u64 cap_for(u64 n) { return round_up((u64)((double)(n < 64 ? 64 : n) / 0.55) + 1, 1024); }
+static double table_load()
+{
+    static double lf = 0;
+    if (lf == 0) {
+        const char *e = getenv("EULER_B200_LOAD");
+        lf = e ? atof(e) : 0.55;
+        if (lf < 0.05 || lf > 0.95) lf = 0.55;
+    }
+    return lf;
+}
+static u64 cap_for(u64 n) { return round_up((u64)((double)(n < 64 ? 64 : n) / table_load()) + 1, 1024); }
 
 static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 distinct_hint, euler_stats *stats)
 {
