@@ -47,10 +47,11 @@ void dev_free(DevBuf &b)
     b.cap = 0;
 }
 
-int scan_state_reserve(euler_ctx *ctx, u64 ntiles, u64 **state)
+int scan_state_reserve(euler_ctx *ctx, u64 ntiles, ScanState **state, u64 **counter)
 {
-    EULER_TRY(dev_reserve(ctx, ctx->scan_state, (ntiles + 1) * sizeof(u64)));
-    *state = (u64 *)ctx->scan_state.p;
+    EULER_TRY(dev_reserve(ctx, ctx->scan_state, (ntiles + 1) * sizeof(ScanState)));
+    *state = (ScanState *)ctx->scan_state.p;
+    *counter = (u64 *)(*state + ntiles);
     return EULER_OK;
 }
 

@@ -397,3 +397,115 @@ int graph_filter_counts(euler_ctx *ctx, const u64 *keys, const u32 *vals, u64 n,
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
+
+// ================================================================================================
+// Fused fast path (slot-order ids): three passes instead of nine.
+// ================================================================================================
+
+// ---- pair scan over l-mer table slots: distinct both-strand l-mers (lo) and edge offsets (hi) ----
+struct LtScanPolicy {
+    typedef u64 T;
+    const u64 *keys;
+    const u32 *cnt;
+    u32 l;
+    u32 *base, *eoff;
+    __device__ __forceinline__ u64 load(u64 i) const
+    {
+        const u64 k = keys[i];
+        if (k == EULER_EMPTY_KEY) return 0ull;
+        const u64 m = 2ull * cnt[i];                        // both strands together (n + n, or 2n on a palindrome)
+        return (m << 32) | (k == revcomp64(k, l) ? 1ull : 2ull);
+    }
+    __device__ __forceinline__ void store(u64 i, u64 ex, u64, bool valid) const
+    {
+        if (valid) { base[i] = (u32)ex; eoff[i] = (u32)(ex >> 32); }
+    }
+};
+
+int graph_lt_scan(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, u64 cap, u32 l, u32 *base, u32 *eoff,
+                  u64 *d_total_packed)
+{
+    return scan_run(ctx, LtScanPolicy{lt_keys, lt_cnt, l, base, eoff}, cap, d_total_packed);
+}
+
+// ---- edge kernel: one thread per table slot ------------------------------------------------------
+// Emits both strands of the slot's canonical l-mer: lmerKeys / lmerValues / lmerOffsets, the
+// compressed edge (v1, v2) and the four degree slots (debruijnCount pydebruijn.py:107-141).
+__global__ void __launch_bounds__(GB) edges_fused_kernel(const u64 *__restrict__ lt_keys, const u32 *__restrict__ lt_cnt,
+                                                          const u32 *__restrict__ base, const u32 *__restrict__ eoff, u64 cap,
+                                                          u32 l, VertexTable vt, u64 *__restrict__ lkeys, u32 *__restrict__ lvals,
+                                                          u32 *__restrict__ loffs, u32 *__restrict__ ev1, u32 *__restrict__ ev2,
+                                                          u32 *__restrict__ lcount, u32 *__restrict__ ecount)
+{
+    const u64 slot = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= cap) return;
+    const u64 c = lt_keys[slot];
+    if (c == EULER_EMPTY_KEY) return;
+    const u32 n = lt_cnt[slot];
+    const u32 idx = base[slot], eo = eoff[slot];
+    const u32 k = l - 1;
+    const u64 kmask = key_mask_d(k);
+    const u64 r = revcomp64(c, l);
+    const bool pal = c == r;
+    // vertex ids of prefix / suffix on both strands from two table probes
+    const u64 p = c >> 2, s = c & kmask;
+    const u64 rp = revcomp64(p, k), rs = revcomp64(s, k);
+    const u64 cp = p < rp ? p : rp, cs = s < rs ? s : rs;
+    const u64 sp = table_find(vt.keys, vt.cap, cp), ss = table_find(vt.keys, vt.cap, cs);
+    if (sp == EULER_NO_SLOT || ss == EULER_NO_SLOT) return;  // cannot happen: both were inserted from this slot
+    const u32 p0 = vt.id0[sp], s0 = vt.id0[ss];
+    const u32 p1 = vt.id1 ? vt.id1[sp] : (p == rp ? p0 : p0 + 1u);
+    const u32 s1 = vt.id1 ? vt.id1[ss] : (s == rs ? s0 : s0 + 1u);
+    const u32 id_p = (p == cp) ? p0 : p1, id_rp = (p == cp) ? p1 : p0;   // id(prefix c), id(rc prefix c)
+    const u32 id_s = (s == cs) ? s0 : s1, id_rs = (s == cs) ? s1 : s0;
+    const u32 m0 = pal ? 2u * n : n;
+    lkeys[idx] = c; lvals[idx] = m0; loffs[idx] = eo; ev1[idx] = id_p; ev2[idx] = id_s;
+    lcount[4ull * id_p + (u32)(c & 3)] = m0;
+    ecount[4ull * id_s + (u32)((c >> (2 * k)) & 3)] = m0;
+    if (!pal) {  // reverse strand: rc(c) runs from rc(suffix c) to rc(prefix c)
+        lkeys[idx + 1] = r; lvals[idx + 1] = n; loffs[idx + 1] = eo + n; ev1[idx + 1] = id_rs; ev2[idx + 1] = id_rp;
+        lcount[4ull * id_rs + (u32)(r & 3)] = n;
+        ecount[4ull * id_rp + (u32)((r >> (2 * k)) & 3)] = n;
+    }
+}
+
+int graph_edges_fused(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, const u32 *base, const u32 *eoff, u64 cap,
+                      u32 l, const VertexTable &vt, u64 *lkeys, u32 *lvals, u32 *loffs, u32 *ev1, u32 *ev2, u32 *lcount,
+                      u32 *ecount)
+{
+    edges_fused_kernel<<<grid_for(cap, GB), GB, 0, ctx->stream>>>(lt_keys, lt_cnt, base, eoff, cap, l, vt, lkeys, lvals, loffs,
+                                                                  ev1, ev2, lcount, ecount);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+// ---- vertex pass: pair scan of (lcount, ecount) that also writes the EulerVertex records ---------
+// scans pydebruijn.py:560-567 + setupVertices :280-294 in one read of the degree slots
+struct VertexScanPolicy {
+    typedef u64 T;
+    const u32 *lcount, *ecount;
+    const u64 *vkeys;
+    u32 *lstart, *estart;
+    euler_vertex *ev;
+    __device__ __forceinline__ u64 load(u64 i) const { return ((u64)ecount[i] << 32) | lcount[i]; }
+    __device__ __forceinline__ void store(u64 i, u64 ex, u64 v, bool valid) const
+    {
+        if (valid) { lstart[i] = (u32)ex; estart[i] = (u32)(ex >> 32); }
+        // the four slots of a vertex sit in four adjacent lanes of this row
+        u64 sum = v + __shfl_xor_sync(0xffffffffu, v, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        if (valid && (i & 3) == 0) {
+            euler_vertex x;
+            x.vid = vkeys[i >> 2];
+            x.lp = (u32)ex; x.lcount = (u32)sum;
+            x.ep = (u32)(ex >> 32); x.ecount = (u32)(sum >> 32);
+            ev[i >> 2] = x;
+        }
+    }
+};
+
+int graph_vertices_fused(euler_ctx *ctx, const u32 *lcount, const u32 *ecount, const u64 *vkeys, u64 nv, u32 *lstart,
+                         u32 *estart, euler_vertex *ev)
+{
+    return scan_run(ctx, VertexScanPolicy{lcount, ecount, vkeys, lstart, estart, ev}, 4 * nv, (u64 *)nullptr);
+}

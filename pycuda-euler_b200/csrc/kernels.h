@@ -93,3 +93,14 @@ int synth_reads(euler_ctx *ctx, u64 G, u32 L, u32 err_ppm, u64 first, u64 nreads
 // ---- unitig.cu
 int unitig_from_table(euler_ctx *ctx, const u64 *keys, const u32 *cnt, u64 cap, u32 K, u32 limit, char **d_out,
                       u64 *out_bytes, u64 *ncontigs, u64 *n_nodes);
+
+// ---- graph.cu, fused fast path
+// pair scan over l-mer table slots: base = distinct both-strand l-mer index, eoff = edge offset;
+// *d_total_packed = (E << 32) | U_l
+int graph_lt_scan(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, u64 cap, u32 l, u32 *base, u32 *eoff,
+                  u64 *d_total_packed);
+int graph_edges_fused(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, const u32 *base, const u32 *eoff, u64 cap,
+                      u32 l, const VertexTable &vt, u64 *lkeys, u32 *lvals, u32 *loffs, u32 *ev1, u32 *ev2, u32 *lcount,
+                      u32 *ecount);
+int graph_vertices_fused(euler_ctx *ctx, const u32 *lcount, const u32 *ecount, const u64 *vkeys, u64 nv, u32 *lstart,
+                         u32 *estart, euler_vertex *ev);

@@ -19,7 +19,7 @@ struct Pipeline {
     DevArr<u32> start_bits;
     // canonical l-mer table (SoA) and canonical k-mer (vertex) table
     DevArr<u64> lt_keys;
-    DevArr<u32> lt_cnt, lt_base;
+    DevArr<u32> lt_cnt, lt_base, lt_eoff;
     u64 lt_cap = 0;
     DevArr<u64> vt_keys;
     DevArr<u32> vt_id0, vt_id1;
@@ -46,7 +46,7 @@ void pipeline_destroy(Pipeline *p)
 {
     if (!p) return;
     p->in_buf.free(); p->in_off.free(); p->start_bits.free();
-    p->lt_keys.free(); p->lt_cnt.free(); p->lt_base.free();
+    p->lt_keys.free(); p->lt_cnt.free(); p->lt_base.free(); p->lt_eoff.free();
     p->vt_keys.free(); p->vt_id0.free(); p->vt_id1.free(); p->stats.free();
     p->lkeys.free(); p->vkeys.free(); p->lvals.free(); p->loffs.free(); p->ev1.free(); p->ev2.free();
     p->lcount.free(); p->ecount.free(); p->lstart.free(); p->estart.free(); p->ev.free(); p->ee.free();
@@ -97,6 +97,7 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
         EULER_TRY(P->lt_keys.reserve(ctx, lt_cap));
         EULER_TRY(P->lt_cnt.reserve(ctx, lt_cap));
         EULER_TRY(P->lt_base.reserve(ctx, lt_cap));
+        EULER_TRY(P->lt_eoff.reserve(ctx, lt_cap));
         EULER_TRY(P->vt_keys.reserve(ctx, vt_cap));
         EULER_TRY(P->vt_id0.reserve(ctx, vt_cap));
         CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 16 * sizeof(u64), s));
@@ -106,8 +107,9 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
         EULER_TRY(enc_count_canonical(ctx, P->d_buf, B, P->start_bits.ptr(), l, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap,
                                       P->stats.ptr()));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
-        launches += 4;  // count, slot scan, vertex insert, slot scan
-        EULER_TRY(graph_slot_scan(ctx, P->lt_keys.ptr(), lt_cap, l, P->lt_base.ptr(), P->stats.ptr() + 3));
+        launches += 4;  // count, l-mer pair scan, vertex insert, vertex slot scan
+        EULER_TRY(graph_lt_scan(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap, l, P->lt_base.ptr(), P->lt_eoff.ptr(),
+                                P->stats.ptr() + 3));
         EULER_TRY(graph_vertex_insert(ctx, P->lt_keys.ptr(), lt_cap, l, P->vt_keys.ptr(), vt_cap, P->stats.ptr() + 2));
         EULER_TRY(graph_slot_scan(ctx, P->vt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(), P->stats.ptr() + 4));
         EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 6));
@@ -116,11 +118,12 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
         if (h[2] & 1) lt_cap *= 2;
         if (h[2] & 2) vt_cap *= 2;
     }
-    const u64 N_l = h[0], N_k = h[1], U_l = h[3], V = h[4];
+    const u64 N_l = h[0], N_k = h[1], U_l = h[3] & 0xffffffffull, V = h[4];
     const u64 E = 2 * N_l;
     P->U_l = U_l; P->V = V; P->E = E;
-    if (V >= 0x3fffffffull || U_l >= 0xffffffffull || E >= 0xffffffffull)
+    if (V >= 0x3fffffffull || N_l >= 0x7fffffffull)
         return euler_fail(ctx, EULER_ERR_RANGE, "graph exceeds u32 ids (U_l=%llu V=%llu E=%llu)", U_l, V, E);
+    if ((h[3] >> 32) != E) return euler_fail(ctx, EULER_ERR_STATE, "internal: edge total %llu != 2 N_l %llu", h[3] >> 32, E);
 
     EULER_TRY(P->lkeys.reserve(ctx, U_l)); EULER_TRY(P->lvals.reserve(ctx, U_l)); EULER_TRY(P->loffs.reserve(ctx, U_l));
     EULER_TRY(P->ev1.reserve(ctx, U_l)); EULER_TRY(P->ev2.reserve(ctx, U_l));
@@ -129,34 +132,40 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
     EULER_TRY(P->lstart.reserve(ctx, 4 * V + 4)); EULER_TRY(P->estart.reserve(ctx, 4 * V + 4));
     EULER_TRY(P->ev.reserve(ctx, V));
 
-    EULER_TRY(graph_compact_lmers(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), P->lt_base.ptr(), lt_cap, l, P->lkeys.ptr(),
-                                  P->lvals.ptr()));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->lcount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
     EULER_TRY(graph_compact_vertices(ctx, P->vt_keys.ptr(), P->vt_id0.ptr(), vt_cap, k, P->vkeys.ptr()));
     VertexTable vt = {P->vt_keys.ptr(), P->vt_id0.ptr(), nullptr, vt_cap, k};
     if (flags & EULER_RUN_CANONICAL_IDS) {
+        // ids = rank in ascending key order (B14): sort both-strand l-mers and vertices, then D1 over the arrays
         const u64 nmax = U_l > V ? U_l : V;
         const u32 nblocks = (u32)((nmax + RS_TILE - 1) / RS_TILE);
         EULER_TRY(P->sort_k.reserve(ctx, nmax)); EULER_TRY(P->sort_v.reserve(ctx, nmax));
         EULER_TRY(P->sort_hist.reserve(ctx, (u64)256 * nblocks));
         EULER_TRY(P->vt_id1.reserve(ctx, vt_cap));
+        EULER_TRY(graph_compact_lmers(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), P->lt_base.ptr(), lt_cap, l, P->lkeys.ptr(),
+                                      P->lvals.ptr()));
         EULER_TRY(radix_sort_pairs(ctx, P->lkeys.ptr(), P->lvals.ptr(), U_l, 2 * (int)l, P->sort_k.ptr(), P->sort_v.ptr(),
                                    P->sort_hist.ptr()));
         EULER_TRY(radix_sort_pairs(ctx, P->vkeys.ptr(), nullptr, V, 2 * (int)k, P->sort_k.ptr(), nullptr, P->sort_hist.ptr()));
         EULER_TRY(graph_assign_sorted_ids(ctx, P->vkeys.ptr(), V, P->vt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(),
                                           P->vt_id1.ptr()));
         vt.id1 = P->vt_id1.ptr();
-        launches += 3 * ((2 * l + 7) / 8) + 3 * ((2 * k + 7) / 8) + 1;
+        EULER_TRY(graph_degree_slots(ctx, P->lkeys.ptr(), P->lvals.ptr(), U_l, l, vt, P->lcount.ptr(), P->ecount.ptr(),
+                                     P->ev1.ptr(), P->ev2.ptr()));
+        EULER_TRY(scan_exclusive(ctx, ScanInU32{P->lvals.ptr()}, U_l, P->loffs.ptr(), (u64 *)nullptr));
+        launches += 3 * ((2 * l + 7) / 8) + 3 * ((2 * k + 7) / 8) + 5;
+    } else {
+        // fast path: ids in table-slot order, one fused pass over the l-mer table
+        EULER_TRY(graph_edges_fused(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), P->lt_base.ptr(), P->lt_eoff.ptr(), lt_cap, l, vt,
+                                    P->lkeys.ptr(), P->lvals.ptr(), P->loffs.ptr(), P->ev1.ptr(), P->ev2.ptr(),
+                                    P->lcount.ptr(), P->ecount.ptr()));
+        launches += 2;
     }
-    CUDA_TRY(ctx, cudaMemsetAsync(P->lcount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
-    CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
-    EULER_TRY(graph_degree_slots(ctx, P->lkeys.ptr(), P->lvals.ptr(), U_l, l, vt, P->lcount.ptr(), P->ecount.ptr(),
-                                 P->ev1.ptr(), P->ev2.ptr()));
-    EULER_TRY(scan_exclusive(ctx, ScanInU32{P->lcount.ptr()}, 4 * V, P->lstart.ptr(), (u64 *)nullptr));
-    EULER_TRY(scan_exclusive(ctx, ScanInU32{P->ecount.ptr()}, 4 * V, P->estart.ptr(), (u64 *)nullptr));
-    EULER_TRY(scan_exclusive(ctx, ScanInU32{P->lvals.ptr()}, U_l, P->loffs.ptr(), P->stats.ptr() + 5));
-    EULER_TRY(graph_setup_vertices(ctx, P->vkeys.ptr(), V, P->lcount.ptr(), P->lstart.ptr(), P->ecount.ptr(),
-                                   P->estart.ptr(), P->ev.ptr()));
-    launches += 7;  // 2 compactions, degree slots, 3 scans, vertices
+    // scans of the degree slots + EulerVertex records in one pass
+    EULER_TRY(graph_vertices_fused(ctx, P->lcount.ptr(), P->ecount.ptr(), P->vkeys.ptr(), V, P->lstart.ptr(), P->estart.ptr(),
+                                   P->ev.ptr()));
+    launches += 1;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
     if (flags & EULER_RUN_EXPAND_EDGES) {
         launches += 1;

@@ -1,96 +1,110 @@
-// scan.cuh -- single-pass exclusive prefix sum (decoupled look-back), u32 items -> u32 prefix,
-// u64 grand total.  Replaces the pycuda.scan.ExclusiveScanKernel call sites of the reference
-// (pygpuhash.py:290, pydebruijn.py:560-573, pyeulertour.py:748,774).
+// scan.cuh -- single-pass exclusive prefix sum (decoupled look-back).  Replaces the
+// pycuda.scan.ExclusiveScanKernel call sites of the reference (pygpuhash.py:290,
+// pydebruijn.py:560-573, pyeulertour.py:748,774).
 //
-// The input is a functor so per-slot weights (table occupancy, palindrome-aware strand counts)
-// are computed on the fly instead of being materialised: one read of the source, one write of
-// the prefix.
+// Layout: a tile is 8 warps x 16 rows x 32 lanes.  Lane i of a warp owns items row*32 + i of the
+// warp's 512-item segment, so every load and store is a fully coalesced 128 B (or 256 B) row; the
+// in-warp scan is a shuffle scan per row with the row total carried forward.
+//
+// A Policy supplies the items and receives the prefixes, so weights are computed on the fly
+// (table occupancy, strand multiplicity) and results can be written in any fused form:
+//   typedef T                                    u32 (one sum per tile < 2^32) or u64 (two u32 sums packed hi|lo)
+//   __device__ T    load(u64 idx) const          value of item idx
+//   __device__ void store(u64 idx, u64 excl, u64 value, bool valid) const
+// store() is called by all 32 lanes of a row together (valid == false past the end), so it may use
+// warp shuffles.
 #pragma once
 #include "common.cuh"
 
 #define SCAN_THREADS 256
-#define SCAN_ITEMS 16
-#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+#define SCAN_WARPS (SCAN_THREADS / 32)
+#define SCAN_ROWS 16
+#define SCAN_TILE (SCAN_THREADS * SCAN_ROWS)
 
-#define SCAN_FLAG_AGG (1ull << 62)
-#define SCAN_FLAG_INC (2ull << 62)
-#define SCAN_VAL_MASK ((1ull << 62) - 1)
+#define SCAN_ST_AGG 1ull
+#define SCAN_ST_INC 2ull
 
-struct ScanInU32 {
-    const u32 *p;
-    __device__ __forceinline__ u32 operator()(u64 i) const { return p[i]; }
+struct __align__(16) ScanState {
+    u64 flag;
+    u64 value;
 };
 
-__device__ __forceinline__ u64 ld_volatile_u64(const u64 *p)
+__device__ __forceinline__ ScanState ld_state(const ScanState *p)
 {
-    u64 v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
+    ScanState s;
+    asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(s.flag), "=l"(s.value) : "l"(p));
+    return s;
 }
-__device__ __forceinline__ void st_volatile_u64(u64 *p, u64 v)
+__device__ __forceinline__ void st_state(ScanState *p, u64 flag, u64 value)
 {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(flag), "l"(value) : "memory");
 }
 
-// state[0..ntiles) tile descriptors, state[ntiles] dynamic tile counter; all zero on entry.
-template <typename InFn>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_exclusive_kernel(InFn in, u64 n, u32 *out, u64 *state,
+// state[0..ntiles): tile descriptors; counter: dynamic tile index; all zero on entry.
+template <typename P>
+__global__ void __launch_bounds__(SCAN_THREADS, 4) scan_exclusive_kernel(P p, u64 n, ScanState *state, u64 *counter,
                                                                         u64 ntiles, u64 *total)
 {
     __shared__ u64 s_tile;
-    __shared__ u64 s_warp[SCAN_THREADS / 32];
+    __shared__ u64 s_warp[SCAN_WARPS];
     __shared__ u64 s_prefix;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    if (tid == 0) s_tile = atomicAdd(state + ntiles, 1ull);
+    if (tid == 0) s_tile = atomicAdd(counter, 1ull);
     __syncthreads();
     const u64 tile = s_tile;
-    const u64 base = tile * SCAN_TILE + (u64)tid * SCAN_ITEMS;
+    const u64 base = tile * SCAN_TILE + (u64)warp * (32 * SCAN_ROWS) + lane;
 
-    u32 v[SCAN_ITEMS];
-    u64 tsum = 0;
+    typedef typename P::T T;  // u32 for plain sums, u64 for packed pairs: halves the register footprint
+    T v[SCAN_ROWS];
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        const u64 idx = base + i;
-        v[i] = idx < n ? in(idx) : 0u;
-        tsum += v[i];
+    for (int r = 0; r < SCAN_ROWS; r++) {
+        const u64 idx = base + (u64)r * 32;
+        v[r] = idx < n ? p.load(idx) : (T)0;
     }
-    // block exclusive scan of per-thread sums
-    u64 incl = tsum;
+    // per-row inclusive shuffle scan, row totals carried forward: ex[r] = exclusive prefix in the warp segment
+    T ex[SCAN_ROWS];
+    T carry = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const u64 t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
+    for (int r = 0; r < SCAN_ROWS; r++) {
+        T inc = v[r];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const T t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        ex[r] = carry + inc - v[r];
+        carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_warp[warp] = carry;
     __syncthreads();
     u64 warp_off = 0, block_sum = 0;
 #pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+    for (int w = 0; w < SCAN_WARPS; w++) {
         const u64 t = s_warp[w];
         if (w < warp) warp_off += t;
         block_sum += t;
     }
-    const u64 thread_excl = warp_off + incl - tsum;
 
     // decoupled look-back by warp 0
     if (warp == 0) {
         u64 prefix = 0;
         if (tile == 0) {
-            if (lane == 0) st_volatile_u64(state + 0, SCAN_FLAG_INC | block_sum);
+            if (lane == 0) st_state(state, SCAN_ST_INC, block_sum);
         } else {
-            if (lane == 0) st_volatile_u64(state + tile, SCAN_FLAG_AGG | block_sum);
+            if (lane == 0) st_state(state + tile, SCAN_ST_AGG, block_sum);
             long long look = (long long)tile - 1;
             while (true) {
                 const long long idx = look - lane;
-                u64 s;
+                ScanState s;
                 if (idx >= 0) {
-                    do { s = ld_volatile_u64(state + idx); } while ((s >> 62) == 0);
+                    do { s = ld_state(state + idx); } while (s.flag == 0);
                 } else {
-                    s = SCAN_FLAG_INC;  // virtual tile before tile 0: inclusive 0
+                    s.flag = SCAN_ST_INC;  // virtual tile before tile 0
+                    s.value = 0;
                 }
-                const unsigned inc_mask = __ballot_sync(0xffffffffu, (s >> 62) == 2);
-                u64 val = s & SCAN_VAL_MASK;
+                const unsigned inc_mask = __ballot_sync(0xffffffffu, s.flag == SCAN_ST_INC);
+                u64 val = s.value;
                 if (inc_mask) {
                     const int first = __ffs(inc_mask) - 1;
                     if (lane > first) val = 0;
@@ -101,7 +115,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_exclusive_kernel(InFn in, u
                 if (inc_mask) break;
                 look -= 32;
             }
-            if (lane == 0) st_volatile_u64(state + tile, SCAN_FLAG_INC | ((prefix + block_sum) & SCAN_VAL_MASK));
+            if (lane == 0) st_state(state + tile, SCAN_ST_INC, prefix + block_sum);
         }
         if (lane == 0) {
             s_prefix = prefix;
@@ -109,30 +123,66 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_exclusive_kernel(InFn in, u
         }
     }
     __syncthreads();
-    u64 run = s_prefix + thread_excl;
+    const u64 off = s_prefix + warp_off;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        const u64 idx = base + i;
-        if (idx < n) out[idx] = (u32)run;
-        run += v[i];
+    for (int r = 0; r < SCAN_ROWS; r++) {
+        const u64 idx = base + (u64)r * 32;
+        p.store(idx, off + ex[r], v[r], idx < n);
     }
 }
 
-// host launcher: d_total (device u64) receives the grand total; state scratch is managed by ctx.
-int scan_state_reserve(euler_ctx *ctx, u64 ntiles, u64 **state);
+// ---- stock policies ----------------------------------------------------------------------------
+// u32 array in -> u32 exclusive prefix out (the ExclusiveScanKernel(uintc,"a+b",0) call sites)
+struct ScanU32 {
+    typedef u32 T;
+    const u32 *in;
+    u32 *out;
+    __device__ __forceinline__ u32 load(u64 i) const { return in[i]; }
+    __device__ __forceinline__ void store(u64 i, u64 ex, u64, bool valid) const
+    {
+        if (valid) out[i] = (u32)ex;
+    }
+};
+// weight functor in -> u32 prefix out
+template <typename F>
+struct ScanFn {
+    typedef u32 T;
+    F f;
+    u32 *out;
+    __device__ __forceinline__ u32 load(u64 i) const { return f(i); }
+    __device__ __forceinline__ void store(u64 i, u64 ex, u64, bool valid) const
+    {
+        if (valid) out[i] = (u32)ex;
+    }
+};
 
-template <typename InFn>
-static int scan_exclusive(euler_ctx *ctx, InFn in, u64 n, u32 *d_out, u64 *d_total)
+int scan_state_reserve(euler_ctx *ctx, u64 ntiles, ScanState **state, u64 **counter);
+
+// `total` (device u64, may be NULL) receives the grand total.
+template <typename P>
+static int scan_run(euler_ctx *ctx, P p, u64 n, u64 *d_total)
 {
     if (n == 0) {
         if (d_total) CUDA_TRY(ctx, cudaMemsetAsync(d_total, 0, sizeof(u64), ctx->stream));
         return EULER_OK;
     }
     const u64 ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    u64 *state = nullptr;
-    EULER_TRY(scan_state_reserve(ctx, ntiles, &state));
-    CUDA_TRY(ctx, cudaMemsetAsync(state, 0, (ntiles + 1) * sizeof(u64), ctx->stream));
-    scan_exclusive_kernel<InFn><<<(unsigned)ntiles, SCAN_THREADS, 0, ctx->stream>>>(in, n, d_out, state, ntiles, d_total);
+    ScanState *state = nullptr;
+    u64 *counter = nullptr;
+    EULER_TRY(scan_state_reserve(ctx, ntiles, &state, &counter));
+    CUDA_TRY(ctx, cudaMemsetAsync(state, 0, (ntiles + 1) * sizeof(ScanState), ctx->stream));
+    scan_exclusive_kernel<P><<<(unsigned)ntiles, SCAN_THREADS, 0, ctx->stream>>>(p, n, state, counter, ntiles, d_total);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
+}
+
+// compatibility helpers used across the library
+struct ScanInU32 {
+    const u32 *p;
+    __device__ __forceinline__ u32 operator()(u64 i) const { return p[i]; }
+};
+template <typename F>
+static int scan_exclusive(euler_ctx *ctx, F f, u64 n, u32 *d_out, u64 *d_total)
+{
+    return scan_run(ctx, ScanFn<F>{f, d_out}, n, d_total);
 }
