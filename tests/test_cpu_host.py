@@ -1,0 +1,126 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/euler_b200.h
+declares, the product path fails loudly without a device, and the pure-host pieces of the
+drop-in modules behave like the reference's."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "pycuda-euler_b200")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    if not os.path.exists(ge.LIB):
+        ge.build()
+    header = open(os.path.join(ROOT, "include", "euler_b200.h")).read()
+    declared = set(re.findall(r"\b(euler_[a-z0-9_]+)\s*\(", header))
+    declared -= {"euler_ctx", "euler_stats", "euler_vertex", "euler_edge", "euler_succ_vertex", "euler_circuit_edge"}
+    assert len(declared) >= 35
+    lib = ctypes.CDLL(ge.LIB)
+    missing = [name for name in sorted(declared) if not hasattr(lib, name)]
+    assert not missing, missing
+    assert lib.euler_version() >= 100
+
+
+def test_no_cpu_fallback_without_a_device():
+    if _has_gpu():
+        pytest.skip("a GPU is present")
+    import _native
+    with pytest.raises(_native.EulerError):
+        _native.Context(0)
+    import eulercuda.eulercuda as ec
+    with pytest.raises(_native.EulerError):
+        ec.assemble2(9, buffer=["ACGTACGTACGTACGT"])
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "euler_oracle" not in src, f
+
+
+def test_struct_layouts_match_the_reference_dtypes():
+    import _native as N
+    assert N.EV_DTYPE.itemsize == 24 and N.EE_DTYPE.itemsize == 24
+    assert N.SV_DTYPE.itemsize == 12 and N.CE_DTYPE.itemsize == 20
+    assert N.EV_DTYPE.names == ("vid", "ep", "ecount", "lp", "lcount")
+    assert N.EE_DTYPE.names == ("eid", "v1", "v2", "s", "pad")
+    assert N.CE_DTYPE.names == ("ceid", "e1", "e2", "c1", "c2")
+
+
+def test_import_layouts():
+    """all three import layouts of the reference resolve to the same functions."""
+    import eulercuda
+    import eulercuda.eulercuda as ec
+    import eulercuda.pyencode as a
+    import encoder.pyencode as b
+    import pyencode as c
+    assert a.encode_lmer_device is b.encode_lmer_device is c.encode_lmer_device
+    import gpuhash.pygpuhash, debruijn.pydebruijn, eulertour.pyeulertour, component.pycomponent  # noqa: E401,F401
+    import pygpuhash, pydebruijn, pyeulertour, pycomponent  # noqa: E401,F401
+    assert eulercuda.assemble2 is ec.assemble2 and eulercuda.assemble is ec.assemble2
+    assert pyeulertour.findEulerDevice is eulertour.pyeulertour.findEulerDevice
+
+
+def test_host_helpers():
+    import eulercuda.eulercuda as ec
+    import eulercuda.pyencode as enc
+    import eulercuda.pygpuhash as gh
+    assert ec.getString(4, 27) == "ACGT" and ec.getString(10, 959244) == "TGGGATAATA"
+    assert ec.dna_translate(2) == "G" and ec.dna_translate(7) == "."
+    assert ec.doErrorCorrection(None, 17, 0, 0) == 17
+    assert enc.getOptimalLaunchConfiguration(100000, 512) == ((512, 1, 1), (1, 196, 1))
+    assert enc.getOptimalLaunchConfiguration(70000 * 1024, 1024) == ((1024, 1, 1), (2, 65535, 1))
+    assert [gh.hash_h(959244, b) for b in (1, 7, 409, 1000003)] == [0, 6, 22, 209841]
+    off = enc._offsets(45, 20)
+    assert off.tolist() == [0, 20, 40, 45]
+    assert enc._offsets(40, 20).tolist() == [0, 20, 40] and enc._offsets(10, 0).tolist() == [0, 10]
+    flat = np.array(b"ACGTACGT").astype("S")
+    assert enc._as_bytes(flat).tobytes() == b"ACGTACGT"
+
+
+def test_readers(tmp_path, g200_reads):
+    import eulercuda.eulercuda as ec
+    from fastareader.parse_fasta import Fasta
+    fa = tmp_path / "g.fa"
+    fa.write_text("".join(">r%d\n%s\n" % (i, r) for i, r in enumerate(g200_reads)))
+    assert ec.read_fasta(str(fa)) == g200_reads
+    with open(fa) as h:
+        recs = list(Fasta(h))
+    assert [r.sequence for r in recs] == g200_reads        # the reference's tests/test_fasta_reader.py
+    assert recs[3].head == "r3" and len(recs[11]) == 3
+    multi = tmp_path / "m.fa"
+    multi.write_text(">a desc\nACGT\nTTGA\n>b\nCC\n")
+    with open(multi) as h:
+        recs = list(Fasta(h))
+    assert [(r.head, r.sequence) for r in recs] == [("a desc", "ACGTTTGA"), ("b", "CC")]
+    fq = tmp_path / "r.fastq"
+    fq.write_text("@x\nACGT\n+\nIIII\n@y\nTTGN\n+\nIIII\n")
+    assert ec.read_fastq(str(fq)) == ["ACGT", "TTGN"]
+    assert ec.parse_fastq(str(fq)) == {"@x": "ACGT", "@y": "TTGN"}
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the oracle port on host cores) prints one JSON line."""
+    import json
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                                   "--warmup", "0", "--workload", "small_smoke"], text=True)
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
