@@ -206,6 +206,26 @@ int euler_pipeline_device_ptr(euler_ctx *ctx, int which, void **dptr);
 int euler_pipeline_contigs(euler_ctx *ctx, char *out, uint64_t *out_bytes, uint64_t *ncontigs);
 
 /* =========================================================================================
+ * k-mer-space partition across the GPUs of one box (one process per GPU; the caller owns the
+ * collective, e.g. torch.distributed all_to_all_single over NCCL).  The reference has no analogue:
+ * its only parallelism is Spark mapPartitions over read partitions (src/cli_spark_gpu.py:37).
+ *   1. euler_dist_count    per-destination key counts of this rank's reads
+ *   2. euler_dist_scatter  write the canonical l-mer keys, grouped by destination rank
+ *   3. (all-to-all of the u64 keys)
+ *   4. euler_dist_build    count the received keys and build this rank's part of the graph; the
+ *                          artefacts are read with euler_pipeline_download (local ids; v2 of an edge
+ *                          whose suffix vertex lives on another rank is 0xffffffff)
+ * ======================================================================================= */
+/* counts: nranks + 2 entries: keys for rank 0..nranks-1, then this rank's forward l-mer and k-mer windows */
+int euler_dist_count(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads,
+                     uint64_t n_bases, uint32_t l, uint32_t nranks, uint64_t *counts);
+/* d_send: u64[sum counts]; send_off[r] = first index of rank r's keys (exclusive scan of counts) */
+int euler_dist_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads,
+                       uint64_t n_bases, uint32_t l, uint32_t nranks, void *d_send, const uint64_t *send_off);
+int euler_dist_build(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_t l, uint32_t rank,
+                     uint32_t nranks, uint64_t distinct_hint, euler_stats *stats);
+
+/* =========================================================================================
  * Step-level entry points of the reference's fine-grained wrappers (kept for callers; the
  * product path uses the open-addressing table and union-find components instead)
  * ======================================================================================= */

@@ -94,6 +94,9 @@ def load():
         "euler_pipeline_device_ptr": [vp, i32, vp],
         "euler_pipeline_contigs": [vp, vp, vp, vp],
         "euler_synth_reads_dev": [vp, u64, u32, u32, u64, u64, vp],
+        "euler_dist_count": [vp, vp, vp, u64, u64, u32, u32, vp],
+        "euler_dist_scatter": [vp, vp, vp, u64, u64, u32, u32, vp, vp],
+        "euler_dist_build": [vp, vp, u64, u32, u32, u32, u64, vp],
         "euler_compat_phase1": [vp, vp, u64, u32, vp, vp],
         "euler_compat_copy_to_bucket": [vp, vp, vp, vp, u64, vp, u32, vp, vp],
         "euler_compat_bucket_sort": [vp, vp, vp, u64, vp, vp, u32, vp, vp],
@@ -450,6 +453,24 @@ class Context:
         cap = C.c_uint64(nb.value)
         self.check(self.lib.euler_pipeline_contigs(self.h, _p(out), C.byref(cap), C.byref(nc)))
         return out.tobytes().decode("ascii").split("\n")[:-1]
+
+    # ------------------------------------------------------------------ k-mer-space partition
+    def dist_count(self, d_buf, d_off, nreads, n_bases, l, nranks):
+        counts = np.zeros(nranks + 2, np.uint64)
+        self.check(self.lib.euler_dist_count(self.h, C.c_void_p(int(d_buf)), C.c_void_p(int(d_off)), int(nreads),
+                                             int(n_bases), int(l), int(nranks), _p(counts)))
+        return counts
+
+    def dist_scatter(self, d_buf, d_off, nreads, n_bases, l, nranks, d_send, send_off):
+        send_off = _arr(send_off, np.uint64)
+        self.check(self.lib.euler_dist_scatter(self.h, C.c_void_p(int(d_buf)), C.c_void_p(int(d_off)), int(nreads),
+                                               int(n_bases), int(l), int(nranks), C.c_void_p(int(d_send)), _p(send_off)))
+
+    def dist_build(self, d_keys, nkeys, l, rank, nranks, distinct_hint=0):
+        st = Stats()
+        self.check(self.lib.euler_dist_build(self.h, C.c_void_p(int(d_keys)), int(nkeys), int(l), int(rank), int(nranks),
+                                             int(distinct_hint), C.byref(st)))
+        return st
 
     def synth_reads_dev(self, d_out, G, L, err_ppm, first, nreads):
         self.check(self.lib.euler_synth_reads_dev(self.h, int(G), int(L), int(err_ppm), int(first), int(nreads),

@@ -342,6 +342,123 @@ int euler_pipeline_contigs(euler_ctx *ctx, char *out, uint64_t *out_bytes, uint6
     return EULER_OK;
 }
 
+// ---- multi-GPU: partition, (all-to-all by the caller), build ------------------------------------
+int euler_dist_count(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads, uint64_t n_bases, uint32_t l,
+                     uint32_t nranks, uint64_t *counts)
+{
+    if (!ctx || !counts) return EULER_ERR_ARG;
+    if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
+    if (nranks < 1 || nranks > 16) return euler_fail(ctx, EULER_ERR_ARG, "nranks %u out of range [1,16]", nranks);
+    if (((uintptr_t)d_buf & 15) != 0) return euler_fail(ctx, EULER_ERR_ARG, "d_buf must be 16-byte aligned");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Pipeline *P = get_pipe(ctx);
+    EULER_TRY(P->stats.reserve(ctx, 64));
+    EULER_TRY(P->start_bits.reserve(ctx, n_bases / 32 + 2));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 64 * sizeof(u64), ctx->stream));
+    EULER_TRY(enc_mark_starts(ctx, (const u64 *)d_read_off, nreads, n_bases, P->start_bits.ptr()));
+    EULER_TRY(dist_partition(ctx, false, d_buf, n_bases, P->start_bits.ptr(), l, nranks, P->stats.ptr() + 32, nullptr, nullptr));
+    u64 h[18];
+    EULER_TRY(read_u64s(ctx, P->stats.ptr() + 32, h, 18));
+    for (u32 d = 0; d < nranks; d++) counts[d] = h[d];
+    counts[nranks] = h[16];       // forward l-mer windows of this rank's reads
+    counts[nranks + 1] = h[17];   // forward k-mer windows
+    return EULER_OK;
+}
+
+int euler_dist_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads, uint64_t n_bases,
+                       uint32_t l, uint32_t nranks, void *d_send, const uint64_t *send_off)
+{
+    (void)d_read_off; (void)nreads;
+    if (!ctx || !send_off || (!d_send && n_bases)) return EULER_ERR_ARG;
+    if (nranks < 1 || nranks > 16) return euler_fail(ctx, EULER_ERR_ARG, "nranks %u out of range [1,16]", nranks);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Pipeline *P = get_pipe(ctx);
+    if (!P->start_bits.ptr()) return euler_fail(ctx, EULER_ERR_STATE, "euler_dist_scatter must follow euler_dist_count");
+    // cursors start at the per-destination offsets of the send buffer
+    CUDA_TRY(ctx, cudaMemcpyAsync(P->stats.ptr() + 8, send_off, nranks * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    EULER_TRY(dist_partition(ctx, true, d_buf, n_bases, P->start_bits.ptr(), l, nranks, nullptr, P->stats.ptr() + 8,
+                             (u64 *)d_send));
+    return EULER_OK;
+}
+
+int euler_dist_build(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_t l, uint32_t rank, uint32_t nranks,
+                     uint64_t distinct_hint, euler_stats *stats)
+{
+    if (!ctx) return EULER_ERR_ARG;
+    if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
+    if (nranks < 1 || nranks > 16 || rank >= nranks) return euler_fail(ctx, EULER_ERR_ARG, "bad rank %u / %u", rank, nranks);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Pipeline *P = get_pipe(ctx);
+    cudaStream_t s = ctx->stream;
+    const u32 k = l - 1;
+    P->l = l; P->flags = 0; P->have_graph = false; P->expanded = false;
+    memset(&P->st, 0, sizeof(P->st));
+    EULER_TRY(P->stats.reserve(ctx, 64));
+    u64 est = distinct_hint ? distinct_hint : ((P->learned_bases == nkeys && P->learned_lc) ? P->learned_lc + P->learned_lc / 32
+                                                                                            : (nkeys ? nkeys : 1));
+    u64 lt_cap = cap_for(est), vt_cap = cap_for(est);
+    u64 h[8] = {0};
+    u32 retries = 0, launches = 0;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    while (true) {
+        P->lt_cap = lt_cap; P->vt_cap = vt_cap;
+        EULER_TRY(P->lt_keys.reserve(ctx, lt_cap)); EULER_TRY(P->lt_cnt.reserve(ctx, lt_cap));
+        EULER_TRY(P->lt_base.reserve(ctx, lt_cap)); EULER_TRY(P->lt_eoff.reserve(ctx, lt_cap));
+        EULER_TRY(P->vt_keys.reserve(ctx, vt_cap)); EULER_TRY(P->vt_id0.reserve(ctx, vt_cap));
+        CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 8 * sizeof(u64), s));
+        EULER_TRY(graph_table_clear(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap));
+        EULER_TRY(graph_table_clear(ctx, P->vt_keys.ptr(), nullptr, vt_cap));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
+        EULER_TRY(dist_count_keys(ctx, (const u64 *)d_keys, nkeys, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap, P->stats.ptr()));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+        EULER_TRY(dist_lt_scan(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap, l, rank, nranks, P->lt_base.ptr(),
+                               P->lt_eoff.ptr(), P->stats.ptr() + 3));
+        EULER_TRY(dist_vertex_insert(ctx, P->lt_keys.ptr(), lt_cap, l, P->vt_keys.ptr(), vt_cap, rank, nranks, P->stats.ptr() + 2));
+        EULER_TRY(graph_slot_scan(ctx, P->vt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(), P->stats.ptr() + 4));
+        launches += 4;
+        EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 6));
+        if ((h[2] & 3) == 0) break;
+        if (++retries > 8) return euler_fail(ctx, EULER_ERR_OVERFLOW, "hash table overflow after %u regrows", retries);
+        if (h[2] & 1) lt_cap *= 2;
+        if (h[2] & 2) vt_cap *= 2;
+    }
+    const u64 U_l = h[3] & 0xffffffffull, E = h[3] >> 32, V = h[4];
+    P->U_l = U_l; P->V = V; P->E = E;
+    if (V >= 0x3fffffffull) return euler_fail(ctx, EULER_ERR_RANGE, "vertex count exceeds u32 ids");
+    EULER_TRY(P->lkeys.reserve(ctx, U_l)); EULER_TRY(P->lvals.reserve(ctx, U_l)); EULER_TRY(P->loffs.reserve(ctx, U_l));
+    EULER_TRY(P->ev1.reserve(ctx, U_l)); EULER_TRY(P->ev2.reserve(ctx, U_l)); EULER_TRY(P->vkeys.reserve(ctx, V));
+    EULER_TRY(P->lcount.reserve(ctx, 4 * V + 4)); EULER_TRY(P->ecount.reserve(ctx, 4 * V + 4));
+    EULER_TRY(P->lstart.reserve(ctx, 4 * V + 4)); EULER_TRY(P->estart.reserve(ctx, 4 * V + 4));
+    EULER_TRY(P->ev.reserve(ctx, V));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->lcount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+    EULER_TRY(graph_compact_vertices(ctx, P->vt_keys.ptr(), P->vt_id0.ptr(), vt_cap, k, P->vkeys.ptr()));
+    VertexTable vt = {P->vt_keys.ptr(), P->vt_id0.ptr(), nullptr, vt_cap, k};
+    EULER_TRY(dist_edges(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), P->lt_base.ptr(), P->lt_eoff.ptr(), lt_cap, l, vt, rank, nranks,
+                         P->lkeys.ptr(), P->lvals.ptr(), P->loffs.ptr(), P->ev1.ptr(), P->ev2.ptr(), P->lcount.ptr(),
+                         P->ecount.ptr()));
+    EULER_TRY(graph_vertices_fused(ctx, P->lcount.ptr(), P->ecount.ptr(), P->vkeys.ptr(), V, P->lstart.ptr(), P->estart.ptr(),
+                                   P->ev.ptr()));
+    launches += 3;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    P->have_graph = true;
+    P->learned_bases = nkeys;
+    // distinct canonical l-mers held by this rank (homed or not): occupied slots are not counted
+    // separately, the homed both-strand count is a safe size for the next run of the same input
+    P->learned_lc = U_l + 16;
+    euler_stats &st = P->st;
+    st.n_bases = 0; st.n_reads = 0; st.n_lmer_windows = nkeys; st.distinct_lmers = U_l; st.distinct_kmers = V; st.edge_count = E;
+    st.lmer_table_capacity = lt_cap; st.kmer_table_capacity = vt_cap; st.retries = retries;
+    cudaEventElapsedTime(&st.ms_count, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&st.ms_graph, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[2]);
+    cudaEventElapsedTime(&st.ms_count_kernel, ctx->ev[4], ctx->ev[1]);
+    st.kernel_launches = launches;
+    if (stats) *stats = st;
+    return EULER_OK;
+}
+
 int euler_synth_reads_dev(euler_ctx *ctx, uint64_t genome_len, uint32_t read_len, uint32_t err_ppm, uint64_t first_read,
                           uint64_t nreads, void *d_out)
 {

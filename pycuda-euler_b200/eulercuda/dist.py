@@ -1,0 +1,112 @@
+"""k-mer-space partition across the GPUs of one box: one process per GPU, one all-to-all.
+
+The reference distributes by Spark ``mapPartitions(assemble2)`` over independent read partitions
+with no exchange and no merge (src/cli_spark_gpu.py:37), which breaks the graph at partition
+boundaries.  Here every vertex (k-mer) has one owning rank; each rank encodes its shard of the
+reads, sends every canonical l-mer to the owner(s) of its prefix / suffix k-mer in ONE
+``all_to_all_single`` over NCCL, and builds its part of the graph from what it receives (see
+csrc/dist.cu).  torch.distributed is plumbing only; all compute is in libeuler_b200.so.
+"""
+import numpy as np
+
+
+def plan_exchange(send_counts, all_to_all_counts):
+    """Host logic of the exchange: offsets of the send buffer and the receive split sizes.
+
+    send_counts: int sequence [world] (keys this rank sends to each rank);
+    all_to_all_counts: callable taking that list and returning what every rank sends to us.
+    Returns (send_off uint64[world], recv_counts list[int])."""
+    send_counts = [int(x) for x in send_counts]
+    send_off = np.zeros(len(send_counts), dtype=np.uint64)
+    if len(send_counts) > 1:
+        send_off[1:] = np.cumsum(send_counts[:-1], dtype=np.uint64)
+    recv_counts = [int(x) for x in all_to_all_counts(send_counts)]
+    return send_off, recv_counts
+
+
+def torch_count_exchange(group=None, device="cuda"):
+    """all_to_all of the per-destination counts with torch.distributed (NCCL on GPU, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+
+    def fn(send_counts):
+        world = dist.get_world_size(group)
+        t_in = torch.tensor(send_counts, dtype=torch.int64, device=device)
+        t_out = torch.empty(world, dtype=torch.int64, device=device)
+        if dist.get_backend(group) == "gloo":
+            # gloo has no all_to_all_single on every build: gather + pick our column
+            rows = [torch.empty(world, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(rows, t_in.cpu(), group=group)
+            me = dist.get_rank(group)
+            return [int(r[me]) for r in rows]
+        dist.all_to_all_single(t_out, t_in, group=group)
+        return t_out.tolist()
+    return fn
+
+
+def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint=0, group=None, stream=None):
+    """Run the partitioned hot path on this rank.  d_reads / d_off are CUDA tensors (uint8 / int64).
+    Returns (stats, info) where info has the window counts and exchange sizes."""
+    import torch
+    import torch.distributed as dist
+    counts = ctx.dist_count(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world)
+    send_counts = counts[:world].astype(np.int64).tolist()
+    n_l, n_k = int(counts[world]), int(counts[world + 1])
+    if world > 1:
+        send_off, recv_counts = plan_exchange(send_counts, torch_count_exchange(group))
+    else:
+        send_off, recv_counts = np.zeros(1, np.uint64), send_counts
+    send = torch.empty(max(int(sum(send_counts)), 1), dtype=torch.int64, device=d_reads.device)
+    ctx.dist_scatter(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world, send.data_ptr(), send_off)
+    ctx.sync()
+    if world > 1:
+        recv = torch.empty(max(int(sum(recv_counts)), 1), dtype=torch.int64, device=d_reads.device)
+        dist.all_to_all_single(recv[:sum(recv_counts)], send[:sum(send_counts)], output_split_sizes=recv_counts,
+                               input_split_sizes=send_counts, group=group)
+        torch.cuda.current_stream().synchronize()
+    else:
+        recv = send
+    nkeys = int(sum(recv_counts))
+    st = ctx.dist_build(recv.data_ptr(), nkeys, l, rank, world, distinct_hint)
+    info = {"n_lmer_windows": n_l, "n_kmer_windows": n_k, "sent_keys": int(sum(send_counts)), "recv_keys": nkeys,
+            "exchange_bytes": 8 * int(sum(send_counts))}
+    return st, info
+
+
+def emulate_partitioned(ctx, shards, l, world):
+    """Single-process emulation of `world` ranks on one GPU (tests): shards = list of
+    (uint8 reads array, uint64 offsets array) per rank.  Returns the per-rank artefact dicts."""
+    import torch
+    import _native as N
+    buckets = [[None] * world for _ in range(world)]
+    windows = []
+    for r, (buf, off) in enumerate(shards):
+        d_buf = torch.from_numpy(np.ascontiguousarray(buf)).cuda() if len(buf) else torch.zeros(16, dtype=torch.uint8, device="cuda")
+        d_off = torch.from_numpy(np.ascontiguousarray(off).astype(np.int64)).cuda()
+        nreads, n_bases = len(off) - 1, int(off[-1])
+        counts = ctx.dist_count(d_buf.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world)
+        sc = counts[:world].astype(np.int64)
+        windows.append((int(counts[world]), int(counts[world + 1])))
+        send_off = np.zeros(world, np.uint64)
+        send_off[1:] = np.cumsum(sc[:-1])
+        send = torch.empty(max(int(sc.sum()), 1), dtype=torch.int64, device="cuda")
+        ctx.dist_scatter(d_buf.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world, send.data_ptr(), send_off)
+        ctx.sync()
+        for d in range(world):
+            buckets[r][d] = send[int(send_off[d]):int(send_off[d]) + int(sc[d])].clone()
+    out = []
+    for d in range(world):
+        recv = torch.cat([buckets[r][d] for r in range(world)]) if world else None
+        if recv.numel() == 0:
+            recv = torch.zeros(1, dtype=torch.int64, device="cuda")
+            nkeys = 0
+        else:
+            nkeys = recv.numel()
+        st = ctx.dist_build(recv.data_ptr(), nkeys, l, d, world, 0)
+        art = {name: ctx.download(getattr(N, "ART_" + name)) for name in
+               ("LMER_KEYS", "LMER_VALUES", "LMER_OFFSETS", "KMER_KEYS", "LCOUNT", "ECOUNT", "LSTART", "ESTART", "EV",
+                "EDGE_V1", "EDGE_V2")}
+        art["stats"] = st.as_dict()
+        art["recv_keys"] = nkeys
+        out.append(art)
+    return out, windows

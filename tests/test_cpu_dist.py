@@ -1,0 +1,98 @@
+"""CPU test of the N > 1 host logic with a real 2-rank gloo group: exchange planning, count
+exchange and the ownership rule.  The device kernels are replaced by numpy here (the oracle supplies
+the encodings), so this covers the plumbing around libeuler_b200's dist entry points."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _owner_np(canon, world):
+    c = np.asarray(canon, dtype=np.uint64)
+    h = (c ^ (c >> np.uint64(31))) * np.uint64(0xD6E8FEB86659FD93)
+    return (((h >> np.uint64(32)) * np.uint64(world)) >> np.uint64(32)).astype(np.int64)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "pycuda-euler_b200"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from util import random_reads
+    from eulercuda.dist import plan_exchange, torch_count_exchange
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        l, k = 14, 13
+        reads = random_reads(9, 200, genome_len=2000)
+        buf, off = oracle.pack_reads(reads[rank::world])
+        f, r, v = oracle.encode_positions(buf, off, l)
+        fw, rc = f[v == 1], r[v == 1]
+        canon = np.minimum(fw, rc)
+        kmask = np.uint64((1 << (2 * k)) - 1)
+        pre, suf = fw >> np.uint64(2), fw & kmask
+        cp = np.array([min(int(x), oracle.revcomp(int(x), k)) for x in pre], np.uint64)
+        cs = np.array([min(int(x), oracle.revcomp(int(x), k)) for x in suf], np.uint64)
+        o1, o2 = _owner_np(cp, world), _owner_np(cs, world)
+        buckets = [np.concatenate([canon[o1 == d], canon[(o2 == d) & (o2 != o1)]]) for d in range(world)]
+        send_counts = [int(b.size) for b in buckets]
+        send_off, recv_counts = plan_exchange(send_counts, torch_count_exchange(device="cpu"))
+        assert send_off.tolist() == np.concatenate([[0], np.cumsum(send_counts)[:-1]]).tolist()
+        # the exchange itself (gloo: gather everything, keep our column)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [b.tolist() for b in buckets])
+        mine = np.array(sum((gathered[src][rank] for src in range(world)), []), dtype=np.uint64)
+        assert [len(gathered[src][rank]) for src in range(world)] == recv_counts
+        keys, cnt = np.unique(mine, return_counts=True)
+        q.put((rank, keys.tolist(), cnt.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_partition_over_gloo():
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    import oracle
+    from util import random_reads
+    world, port = 2, 29611
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # every canonical l-mer ends up, with its full multiplicity, on the owner(s) of its end k-mers
+    l, k = 14, 13
+    reads = random_reads(9, 200, genome_len=2000)
+    buf, off = oracle.pack_reads(reads)
+    lo, hi, vals = oracle.count_mers(buf, off, l)
+    canon = {}
+    for key, c in zip(lo.tolist(), vals.tolist()):
+        ck = min(key, oracle.revcomp(key, l))
+        canon[ck] = c if key != oracle.revcomp(key, l) else c // 2
+    seen = {}
+    for rank, keys, cnt in results:
+        for kk, c in zip(keys, cnt):
+            assert canon[kk] == c
+            seen.setdefault(kk, set()).add(rank)
+    kmask = (1 << (2 * k)) - 1
+    for ck in canon:
+        p, s = ck >> 2, ck & kmask
+        owners = {int(_owner_np([min(p, oracle.revcomp(p, k))], world)[0]), int(_owner_np([min(s, oracle.revcomp(s, k))], world)[0])}
+        assert seen[ck] == owners
+
+
+def test_plan_exchange_pure():
+    sys.path.insert(0, os.path.join(ROOT, "pycuda-euler_b200"))
+    from eulercuda.dist import plan_exchange
+    off, recv = plan_exchange([3, 0, 5], lambda s: [7, 8, 9])
+    assert off.tolist() == [0, 3, 3] and recv == [7, 8, 9]

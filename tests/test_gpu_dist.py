@@ -1,0 +1,110 @@
+"""GPU test of the k-mer-space partition: `world` ranks emulated in one process on one
+GPU (partition -> exchange -> per-rank build), checked against the single-graph oracle."""
+import numpy as np
+import pytest
+
+import oracle
+from util import random_reads
+
+pytestmark = pytest.mark.gpu
+NO_ID = 0xFFFFFFFF
+
+
+def owner_np(canon, world):
+    c = np.asarray(canon, dtype=np.uint64)
+    h = (c ^ (c >> np.uint64(31))) * np.uint64(0xD6E8FEB86659FD93)
+    return (((h >> np.uint64(32)) * np.uint64(world)) >> np.uint64(32)).astype(np.int64)
+
+
+def canon_np(x, k):
+    return np.array([min(int(v), oracle.revcomp(int(v), k)) for v in x], dtype=np.uint64)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("l", [12, 32])
+def test_partitioned_graph_equals_oracle(ctx, world, l):
+    from eulercuda.dist import emulate_partitioned
+    reads = random_reads(21, 600, genome_len=5000) + ["A" * 70, "ACGT" * 12]
+    k = l - 1
+    shards = []
+    for r in range(world):
+        shards.append(oracle.pack_reads(reads[r::world]))
+    parts, windows = emulate_partitioned(ctx, shards, l, world)
+    buf, off = oracle.pack_reads(reads)
+    g = oracle.graph_build(buf, off, l, expand=False)
+    assert sum(w[0] for w in windows) * 2 == g.ne
+
+    # vertices: every vertex on exactly one rank, the one its canonical k-mer hashes to
+    all_v = np.concatenate([p["KMER_KEYS"] for p in parts])
+    assert np.array_equal(np.sort(all_v), g.vk_lo)
+    okey = {int(kk): i for i, kk in enumerate(g.vk_lo)}
+    for r, p in enumerate(parts):
+        vk = p["KMER_KEYS"]
+        if vk.size:
+            assert (owner_np(canon_np(vk, k), world) == r).all()
+        ids = np.array([okey[int(x)] for x in vk], dtype=np.int64)
+        lc, ec = p["LCOUNT"].reshape(-1, 4), p["ECOUNT"].reshape(-1, 4)
+        assert np.array_equal(lc, g.lcount.reshape(-1, 4)[ids]) and np.array_equal(ec, g.ecount.reshape(-1, 4)[ids])
+        ev = p["EV"]
+        assert np.array_equal(ev["vid"], vk)
+        assert np.array_equal(ev["lcount"], lc.sum(1)) and np.array_equal(ev["ecount"], ec.sum(1))
+        ls = np.concatenate([[0], np.cumsum(lc.ravel())[:-1]]).astype(np.uint32) if vk.size else p["LSTART"]
+        es = np.concatenate([[0], np.cumsum(ec.ravel())[:-1]]).astype(np.uint32) if vk.size else p["ESTART"]
+        assert np.array_equal(p["LSTART"], ls) and np.array_equal(p["ESTART"], es)
+        assert np.array_equal(ev["lp"], ls[::4]) and np.array_equal(ev["ep"], es[::4])
+
+    # edges: every both-strand l-mer homed exactly once, on the owner of its prefix
+    all_l = np.concatenate([p["LMER_KEYS"] for p in parts])
+    all_m = np.concatenate([p["LMER_VALUES"] for p in parts])
+    o = np.argsort(all_l, kind="stable")
+    assert np.array_equal(all_l[o], g.lk_lo) and np.array_equal(all_m[o], g.lvals)
+    kmask = (1 << (2 * k)) - 1
+    total_e = 0
+    for r, p in enumerate(parts):
+        lk, lv, lo = p["LMER_KEYS"], p["LMER_VALUES"], p["LMER_OFFSETS"]
+        total_e += int(lv.sum())
+        assert p["stats"]["edge_count"] == int(lv.sum())
+        if lk.size == 0:
+            continue
+        assert np.array_equal(lo, np.concatenate([[0], np.cumsum(lv)[:-1]]).astype(np.uint32))
+        vk = p["KMER_KEYS"]
+        pre = lk >> np.uint64(2)
+        suf = lk & np.uint64(kmask)
+        assert np.array_equal(vk[p["EDGE_V1"]], pre)          # v1 always local
+        v2 = p["EDGE_V2"]
+        local = v2 != NO_ID
+        assert np.array_equal(vk[v2[local]], suf[local])
+        assert (owner_np(canon_np(suf[~local], k), world) != r).all()
+        assert (owner_np(canon_np(suf[local], k), world) == r).all()
+    assert total_e == g.ne
+
+
+def test_partition_counts_are_exact(ctx):
+    """per-destination counts from the count pass equal what the scatter pass writes"""
+    import torch
+    reads = random_reads(3, 400, genome_len=3000)
+    buf, off = oracle.pack_reads(reads)
+    d_buf = torch.from_numpy(buf).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    l, world = 20, 4
+    counts = ctx.dist_count(d_buf.data_ptr(), d_off.data_ptr(), len(reads), buf.size, l, world)
+    sc = counts[:world].astype(np.int64)
+    f, r, v = oracle.encode_positions(buf, off, l)
+    fw = f[v == 1]
+    assert counts[world] == fw.size
+    k = l - 1
+    pre, suf = fw >> np.uint64(2), fw & np.uint64((1 << (2 * k)) - 1)
+    o1, o2 = owner_np(canon_np(pre, k), world), owner_np(canon_np(suf, k), world)
+    exp = np.bincount(o1, minlength=world) + np.bincount(o2[o2 != o1], minlength=world)
+    assert np.array_equal(sc, exp)
+    send_off = np.zeros(world, np.uint64)
+    send_off[1:] = np.cumsum(sc[:-1])
+    send = torch.full((int(sc.sum()),), -1, dtype=torch.int64, device="cuda")
+    ctx.dist_scatter(d_buf.data_ptr(), d_off.data_ptr(), len(reads), buf.size, l, world, send.data_ptr(), send_off)
+    ctx.sync()
+    keys = send.cpu().numpy().view(np.uint64)
+    canon = canon_np(fw, l)
+    for d in range(world):
+        seg = np.sort(keys[int(send_off[d]):int(send_off[d]) + int(sc[d])])
+        want = np.sort(np.concatenate([canon[o1 == d], canon[(o2 == d) & (o2 != o1)]]))
+        assert np.array_equal(seg, want)
