@@ -121,7 +121,7 @@ int euler_count_mers(euler_ctx *ctx, const char *buf, const uint64_t *read_off, 
     TMP_CHECK(ctx, tk); TMP_CHECK(ctx, tc); TMP_CHECK(ctx, base);
     CUDA_TRY(ctx, cudaMemsetAsync(d_stats, 0, 8 * sizeof(u64), ctx->stream));
     EULER_TRY(graph_table_clear(ctx, tk, tc, cap));
-    EULER_TRY(enc_count_canonical(ctx, d_buf, B, d_bits, len, tk, tc, cap, d_stats));
+    EULER_TRY(enc_count_canonical(ctx, d_buf, B, d_bits, len, tk, tc, cap, TableHash{0, 0}, d_stats));
     EULER_TRY(graph_slot_scan(ctx, tk, cap, len, base, d_stats.get() + 3));
     u64 h[4];
     EULER_TRY(read_u64s(ctx, d_stats, h, 4));
@@ -170,7 +170,7 @@ int euler_unitigs(euler_ctx *ctx, const char *buf, const uint64_t *read_off, uin
     TMP_CHECK(ctx, tk); TMP_CHECK(ctx, tc);
     CUDA_TRY(ctx, cudaMemsetAsync(d_stats, 0, 8 * sizeof(u64), ctx->stream));
     EULER_TRY(graph_table_clear(ctx, tk, tc, cap));
-    EULER_TRY(enc_count_canonical(ctx, d_buf, B, d_bits, K, tk, tc, cap, d_stats));
+    EULER_TRY(enc_count_canonical(ctx, d_buf, B, d_bits, K, tk, tc, cap, TableHash{0, 0}, d_stats));
     u64 h[3];
     EULER_TRY(read_u64s(ctx, d_stats, h, 3));
     if (h[2]) return euler_fail(ctx, EULER_ERR_OVERFLOW, "count table overflow");

@@ -165,11 +165,67 @@ __device__ __forceinline__ int bucket_claim(u64 *bucket_keys, const K4 &q, u64 k
     return -1;
 }
 
+// ---- minimizer-ordered homes -------------------------------------------------------------------
+// With a plain hash the ~70 l-mers of a read touch ~70 random sectors of a table far larger than
+// L2.  Ordering the table by the key's minimizer (smallest scrambled canonical m-mer) sends the
+// ~(l-m+1)/2 consecutive l-mers that share a minimizer to the same EULER_SPAN buckets (256 B), and
+// sends an l-mer and its prefix / suffix k-mers to corresponding regions of the l-mer and vertex
+// tables, so the graph stage walks both tables almost sequentially.  The minimizer is strand
+// symmetric (canonical m-mers), so it can be taken from either orientation of the key.
+#define EULER_SPAN 8
+struct TableHash {
+    u32 span_nb;  // nbuckets - EULER_SPAN when minimizer ordering is on, 0 = plain hash
+    u32 m;        // minimizer length (<= 16, <= key length)
+};
+__device__ __forceinline__ u32 mmer_score(u32 canon_m)
+{
+    const u32 s = canon_m * 2654435761u;
+    return s ^ (s >> 15);
+}
+// scores of the m-mers of `key` (len bases): min over all of them, over all but the last
+// (= the prefix (len-1)-mer's minimizer) and over all but the first (= the suffix's)
+__device__ __forceinline__ void min_scores(u64 key, u32 len, u32 m, u32 &all, u32 &but_last, u32 &but_first)
+{
+    const u64 r = revcomp64(key, len);
+    const u32 mmask = m >= 16 ? 0xffffffffu : ((1u << (2 * m)) - 1u);
+    const u32 n = len - m + 1;
+    all = but_last = but_first = 0xffffffffu;
+    for (u32 j = 0; j < n; j++) {
+        const u32 w = (u32)(key >> (2 * (len - m - j))) & mmask;
+        const u32 rw = (u32)(r >> (2 * j)) & mmask;
+        const u32 sc = mmer_score(w < rw ? w : rw);
+        all = sc < all ? sc : all;
+        if (j + 1 < n) but_last = sc < but_last ? sc : but_last;
+        if (j > 0) but_first = sc < but_first ? sc : but_first;
+    }
+}
+__device__ __forceinline__ u64 home_from_score(u64 key, u32 score, u32 nb, TableHash th)
+{
+    if (!th.span_nb) return hash_bucket(key, nb);
+    // the minimum of many scores is far from uniform (it hugs 0); the score is a bijection of the
+    // m-mer, so re-mixing it (murmur3 fmix32) gives a uniform region that still depends only on the
+    // minimizer's identity
+    u32 h = score;
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return (((u64)h * th.span_nb) >> 32) + ((key * 0x9E3779B97F4A7C15ull) >> 61);
+}
+__device__ __forceinline__ u64 table_home(u64 key, u32 len, u32 nb, TableHash th)
+{
+    if (!th.span_nb) return hash_bucket(key, nb);
+    u32 a, b, c;
+    min_scores(key, len, th.m, a, b, c);
+    return home_from_score(key, a, nb, th);
+}
+
 // returns slot of `key` after inserting it if absent; EULER_NO_SLOT on overflow. cap % 4 == 0.
-__device__ __forceinline__ u64 table_insert(u64 *keys, u64 cap, u64 key, u64 max_probe)
+__device__ __forceinline__ u64 table_insert_at(u64 *keys, u64 cap, u64 key, u64 home, u64 max_probe)
 {
     const u32 nb = (u32)(cap / EULER_BUCKET);
-    u64 b = hash_bucket(key, nb);
+    u64 b = home;
     for (u64 probe = 0; probe < max_probe; probe++) {
         u64 *bk = keys + b * EULER_BUCKET;
         const K4 q = ld_bucket_cg(bk);
@@ -180,10 +236,10 @@ __device__ __forceinline__ u64 table_insert(u64 *keys, u64 cap, u64 key, u64 max
     return EULER_NO_SLOT;
 }
 
-__device__ __forceinline__ u64 table_find(const u64 *keys, u64 cap, u64 key)
+__device__ __forceinline__ u64 table_find_at(const u64 *keys, u64 cap, u64 key, u64 home)
 {
     const u32 nb = (u32)(cap / EULER_BUCKET);
-    u64 b = hash_bucket(key, nb);
+    u64 b = home;
     for (u64 probe = 0; probe < nb; probe++) {
         const K4 q = ld_bucket_nc(keys + b * EULER_BUCKET);
 #pragma unroll
@@ -194,6 +250,16 @@ __device__ __forceinline__ u64 table_find(const u64 *keys, u64 cap, u64 key)
         if (++b == nb) b = 0;
     }
     return EULER_NO_SLOT;
+}
+
+// plain-hash forms (module-level gpuhash API, partitioned path)
+__device__ __forceinline__ u64 table_insert(u64 *keys, u64 cap, u64 key, u64 max_probe)
+{
+    return table_insert_at(keys, cap, key, hash_bucket(key, (u32)(cap / EULER_BUCKET)), max_probe);
+}
+__device__ __forceinline__ u64 table_find(const u64 *keys, u64 cap, u64 key)
+{
+    return table_find_at(keys, cap, key, hash_bucket(key, (u32)(cap / EULER_BUCKET)));
 }
 
 #endif  // __CUDACC__

@@ -84,17 +84,48 @@ int enc_compute_kmers(euler_ctx *ctx, const u64 *d_lmers, u64 n, u64 mask, u64 *
 // Table: SoA keys u64[cap] / counts u32[cap], linear probing, EMPTY = all-ones (never canonical).
 #define CNT_BLOCK 256
 
-// Rolling formulation: each lane walks the 16 bases of its chunk once, keeping the forward and
+// Sliding-window minimum of the m-mer scores: s[t], t = position + NPREV, holds the scores of the
+// W-1 positions before the chunk followed by the chunk's 16.  win[i] = min s over the W m-mers of
+// the l-mer ending at chunk position i.  Log-doubling min tree, all indices compile-time.
+template <int W>
+struct WinMin {
+    static constexpr int NPREV = W - 1;
+    static constexpr int N = NPREV + 16;
+    static constexpr int E = (W >= 16) ? 4 : (W >= 8) ? 3 : (W >= 4) ? 2 : (W >= 2) ? 1 : 0;
+    static constexpr int P = 1 << E;
+    __device__ __forceinline__ static void run(u32 (&s)[N], u32 (&win)[16])
+    {
+        // after step e, s[t] = min of the original s[t .. t + 2^e - 1]
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const int h = 1 << e;
+#pragma unroll
+            for (int t = 0; t + h < N; t++) s[t] = s[t] < s[t + h] ? s[t] : s[t + h];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int lo = i + NPREV - (W - 1);  // first m-mer of the window
+            const int hi = i + NPREV - (P - 1);  // start of the last P-block inside the window
+            win[i] = s[lo] < s[hi] ? s[lo] : s[hi];
+        }
+    }
+};
+
+// Rolling formulation: each lane walks the 16 bases of its chunk, keeping the forward and
 // reverse-complement l-mers in two 64-bit registers (shift in / shift out), plus two run lengths
 // (valid bases, bases since the last read start) that decide whether the window ending here is a
 // whole l-mer / k-mer of one read.  Keys are produced four at a time and probed right away, so the
 // live state is ~60 registers and the loop body stays inside the instruction cache.
+// W > 0: minimizer-ordered table (W = l - m + 1 m-mers per l-mer); W == 0: plain hash;
+// W < 0: minimizer-ordered with a per-window brute-force minimum (any l).
+template <int W>
 __global__ void __launch_bounds__(CNT_BLOCK, 4) count_canonical_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
                                                                         const u32 *__restrict__ start_bits, u32 l,
                                                                         u64 *__restrict__ tab_keys, u32 *__restrict__ tab_cnt,
-                                                                        u64 cap, u64 ntiles, u64 *__restrict__ stats,
+                                                                        u64 cap, TableHash th, u64 ntiles, u64 *__restrict__ stats,
                                                                         u64 part_lo, u64 part_hi, int count_windows)
 {
+    __shared__ u32 s_win[W > 0 ? 16 * CNT_BLOCK : 1];
     const int lane = threadIdx.x & 31;
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
@@ -115,6 +146,43 @@ __global__ void __launch_bounds__(CNT_BLOCK, 4) count_canonical_kernel(const uin
         // state after the base just before this chunk
         u64 f = ((u64)p2 << 32) | p1;
         u64 rc = revcomp64(f & kmask, l);
+
+        if constexpr (W > 0) {
+            // minimizer of every l-mer ending in this chunk: scores of the chunk's 16 m-mers, the
+            // W-1 before them from the two lanes below, sliding minimum, parked in shared memory
+            constexpr int NP = W - 1;
+            const u32 m = th.m;
+            const u32 mmask = m >= 16 ? 0xffffffffu : ((1u << (2 * m)) - 1u);
+            const u32 rsh = 2 * (l - m);
+            u32 sc[16];
+            {
+                u64 f2 = f, r2 = rc;
+                u32 cd = c.codes;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const u32 cc = cd >> 30;
+                    cd <<= 2;
+                    f2 = (f2 << 2) | cc;
+                    r2 = (r2 >> 2) | ((u64)(3u - cc) << top);
+                    const u32 w = (u32)f2 & mmask, rw = (u32)(r2 >> rsh) & mmask;
+                    sc[i] = mmer_score(w < rw ? w : rw);
+                }
+            }
+            u32 sv[NP + 16];
+#pragma unroll
+            for (int j = 0; j < NP; j++) {
+                const int pos = j - NP;  // chunk-relative position, negative
+                sv[j] = (pos >= -16) ? __shfl_up_sync(0xffffffffu, sc[(pos + 16) & 15], 1)
+                                     : __shfl_up_sync(0xffffffffu, sc[(pos + 32) & 15], 2);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) sv[NP + i] = sc[i];
+            u32 win[16];
+            WinMin<W>::run(sv, win);
+#pragma unroll
+            for (int i = 0; i < 16; i++) s_win[i * CNT_BLOCK + threadIdx.x] = win[i];
+        }
+
         const u32 pv = (v2 << 16) | v1, ps = (s2 << 16) | s1;   // bit 0 = the most recent base
         u32 vrun = (pv == 0xffffffffu) ? 32u : (u32)__ffs(~pv) - 1u;
         u32 srun = ps ? (u32)__ffs(ps) - 1u : 32u;
@@ -152,7 +220,9 @@ __global__ void __launch_bounds__(CNT_BLOCK, 4) count_canonical_kernel(const uin
             K4 q[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                bucket[i] = (u32)hash_bucket(key[i], nbuckets);
+                if constexpr (W > 0) bucket[i] = (u32)home_from_score(key[i], s_win[(b * 4 + i) * CNT_BLOCK + threadIdx.x], nbuckets, th);
+                else if constexpr (W < 0) bucket[i] = (pend & (1u << i)) ? (u32)table_home(key[i], l, nbuckets, th) : 0u;
+                else bucket[i] = (u32)hash_bucket(key[i], nbuckets);
                 // L2 blocking knob: this launch only owns home buckets in [part_lo, part_hi)
                 if (bucket[i] < part_lo || bucket[i] >= part_hi) pend &= ~(1u << i);
             }
@@ -191,7 +261,7 @@ __global__ void __launch_bounds__(CNT_BLOCK, 4) count_canonical_kernel(const uin
 }
 
 int enc_count_canonical(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u64 *tab_keys,
-                        u32 *tab_cnt, u64 cap, u64 *d_stats)
+                        u32 *tab_cnt, u64 cap, TableHash th, u64 *d_stats)
 {
     if (!n_bases) return EULER_OK;
     const u64 nchunks = (n_bases + 15) / 16;
@@ -200,23 +270,25 @@ int enc_count_canonical(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u3
     u64 grid = (u64)ctx->num_sms * 4;
     const u64 need = (ntiles + warps_per_block - 1) / warps_per_block;
     if (grid > need) grid = need;
-    // L2 blocking: split the table into `parts` contiguous slot ranges small enough to stay
-    // resident in L2 and make one pass over the reads per range (re-encoding is cheaper than
-    // missing L2 on every probe).
+    // L2-blocking knob (EULER_B200_COUNT_PARTS): one pass over the reads per contiguous bucket range.
+    // Measured: re-encoding costs more than the misses it saves, so the default is a single pass.
     u64 parts = 1;
     const char *env = getenv("EULER_B200_COUNT_PARTS");
     if (env && atoi(env) > 0) parts = (u64)atoi(env);
-    else {
-        const u64 table_bytes = cap * 12;
-        const u64 budget = ctx->l2_part_budget ? ctx->l2_part_budget : (48ull << 20);
-        parts = 1;  // re-encoding costs more than the misses it saves (measured); kept as a knob
-        (void)table_bytes; (void)budget;
-    }
+    const int W = th.span_nb ? (int)(l - th.m + 1) : 0;
     for (u64 p = 0; p < parts; p++) {
         const u64 nb = cap / EULER_BUCKET;
         const u64 lo = nb * p / parts, hi = nb * (p + 1) / parts;
-        count_canonical_kernel<<<(unsigned)(grid ? grid : 1), CNT_BLOCK, 0, ctx->stream>>>(
-            (const uint4 *)d_buf, n_bases, d_bits, l, tab_keys, tab_cnt, cap, ntiles, d_stats, lo, hi, p == 0 ? 1 : 0);
+        const unsigned g = (unsigned)(grid ? grid : 1);
+        const int cw = p == 0 ? 1 : 0;
+#define LAUNCH_CNT(WW)                                                                                          \
+    count_canonical_kernel<WW><<<g, CNT_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, tab_keys, \
+                                                                 tab_cnt, cap, th, ntiles, d_stats, lo, hi, cw)
+        if (W == 0) LAUNCH_CNT(0);
+        else if (W == 21) LAUNCH_CNT(21);   // l = 32 (k = 31), m = 12
+        else if (W == 11) LAUNCH_CNT(11);   // l = 22 (k = 21), m = 12
+        else LAUNCH_CNT(-1);                // any other l: per-window brute-force minimizer
+#undef LAUNCH_CNT
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;

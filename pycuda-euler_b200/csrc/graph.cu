@@ -20,7 +20,7 @@ __device__ __forceinline__ u64 canon64(u64 x, u32 len)
 
 // ---- vertex table build ------------------------------------------------------------------------
 __global__ void __launch_bounds__(GB) vertex_insert_kernel(const u64 *__restrict__ lt_keys, u64 lt_cap, u32 l,
-                                                            u64 *__restrict__ vt_keys, u64 vt_cap, u64 *flags)
+                                                            u64 *__restrict__ vt_keys, u64 vt_cap, TableHash vth, u64 *flags)
 {
     const u64 slot = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= lt_cap) return;
@@ -29,14 +29,19 @@ __global__ void __launch_bounds__(GB) vertex_insert_kernel(const u64 *__restrict
     const u32 k = l - 1;
     const u64 kmask = key_mask_d(k);
     const u64 max_probe = vt_cap / EULER_BUCKET < 4096 ? vt_cap / EULER_BUCKET : 4096;
-    const u64 a = table_insert(vt_keys, vt_cap, canon64(key >> 2, k), max_probe);
-    const u64 b = table_insert(vt_keys, vt_cap, canon64(key & kmask, k), max_probe);
+    const u32 nb = (u32)(vt_cap / EULER_BUCKET);
+    const u64 cp = canon64(key >> 2, k), cs = canon64(key & kmask, k);
+    u32 sa = 0, sp = 0, ss = 0;
+    if (vth.span_nb) min_scores(key, l, vth.m, sa, sp, ss);   // prefix / suffix minimizers from one pass over the l-mer
+    const u64 a = table_insert_at(vt_keys, vt_cap, cp, home_from_score(cp, sp, nb, vth), max_probe);
+    const u64 b = table_insert_at(vt_keys, vt_cap, cs, home_from_score(cs, ss, nb, vth), max_probe);
     if (a == EULER_NO_SLOT || b == EULER_NO_SLOT) atomicOr((unsigned long long *)flags, 2ull);
 }
 
-int graph_vertex_insert(euler_ctx *ctx, const u64 *lt_keys, u64 lt_cap, u32 l, u64 *vt_keys, u64 vt_cap, u64 *d_flags)
+int graph_vertex_insert(euler_ctx *ctx, const u64 *lt_keys, u64 lt_cap, u32 l, u64 *vt_keys, u64 vt_cap, TableHash vth,
+                        u64 *d_flags)
 {
-    vertex_insert_kernel<<<grid_for(lt_cap, GB), GB, 0, ctx->stream>>>(lt_keys, lt_cap, l, vt_keys, vt_cap, d_flags);
+    vertex_insert_kernel<<<grid_for(lt_cap, GB), GB, 0, ctx->stream>>>(lt_keys, lt_cap, l, vt_keys, vt_cap, vth, d_flags);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
@@ -110,24 +115,24 @@ int graph_compact_vertices(euler_ctx *ctx, const u64 *vt_keys, const u32 *vt_bas
 
 __global__ void __launch_bounds__(GB) assign_sorted_ids_kernel(const u64 *__restrict__ vkeys, u64 nv,
                                                                 const u64 *__restrict__ vt_keys, u64 vt_cap, u32 k,
-                                                                u32 *__restrict__ id0, u32 *__restrict__ id1)
+                                                                TableHash vth, u32 *__restrict__ id0, u32 *__restrict__ id1)
 {
     const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nv) return;
     const u64 x = vkeys[r];
     const u64 rc = revcomp64(x, k);
     const u64 c = x < rc ? x : rc;
-    const u64 slot = table_find(vt_keys, vt_cap, c);
+    const u64 slot = table_find_at(vt_keys, vt_cap, c, table_home(c, k, (u32)(vt_cap / EULER_BUCKET), vth));
     if (slot == EULER_NO_SLOT) return;
     if (x == c) id0[slot] = (u32)r;
     if (x == rc || x != c) id1[slot] = (u32)r;
 }
 
-int graph_assign_sorted_ids(euler_ctx *ctx, const u64 *vkeys, u64 nv, const u64 *vt_keys, u64 vt_cap, u32 k, u32 *id0,
-                            u32 *id1)
+int graph_assign_sorted_ids(euler_ctx *ctx, const u64 *vkeys, u64 nv, const u64 *vt_keys, u64 vt_cap, u32 k, TableHash vth,
+                            u32 *id0, u32 *id1)
 {
     if (!nv) return EULER_OK;
-    assign_sorted_ids_kernel<<<grid_for(nv, GB), GB, 0, ctx->stream>>>(vkeys, nv, vt_keys, vt_cap, k, id0, id1);
+    assign_sorted_ids_kernel<<<grid_for(nv, GB), GB, 0, ctx->stream>>>(vkeys, nv, vt_keys, vt_cap, k, vth, id0, id1);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
@@ -137,7 +142,7 @@ __device__ __forceinline__ u32 vt_lookup(const VertexTable &vt, u64 v)
 {
     const u64 r = revcomp64(v, vt.k);
     const u64 c = v < r ? v : r;
-    const u64 slot = table_find(vt.keys, vt.cap, c);
+    const u64 slot = table_find_at(vt.keys, vt.cap, c, table_home(c, vt.k, (u32)(vt.cap / EULER_BUCKET), vt.th));
     if (slot == EULER_NO_SLOT) return EULER_NO_ID;
     if (v == c) return vt.id0[slot];
     return vt.id1 ? vt.id1[slot] : vt.id0[slot] + 1u;
@@ -451,7 +456,11 @@ __global__ void __launch_bounds__(GB) edges_fused_kernel(const u64 *__restrict__
     const u64 p = c >> 2, s = c & kmask;
     const u64 rp = revcomp64(p, k), rs = revcomp64(s, k);
     const u64 cp = p < rp ? p : rp, cs = s < rs ? s : rs;
-    const u64 sp = table_find(vt.keys, vt.cap, cp), ss = table_find(vt.keys, vt.cap, cs);
+    const u32 vnb = (u32)(vt.cap / EULER_BUCKET);
+    u32 sca = 0, scp = 0, scs = 0;
+    if (vt.th.span_nb) min_scores(c, l, vt.th.m, sca, scp, scs);
+    const u64 sp = table_find_at(vt.keys, vt.cap, cp, home_from_score(cp, scp, vnb, vt.th));
+    const u64 ss = table_find_at(vt.keys, vt.cap, cs, home_from_score(cs, scs, vnb, vt.th));
     if (sp == EULER_NO_SLOT || ss == EULER_NO_SLOT) return;  // cannot happen: both were inserted from this slot
     const u32 p0 = vt.id0[sp], s0 = vt.id0[ss];
     const u32 p1 = vt.id1 ? vt.id1[sp] : (p == rp ? p0 : p0 + 1u);

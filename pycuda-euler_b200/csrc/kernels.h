@@ -9,7 +9,7 @@ int enc_positions(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_b
 int enc_compute_kmers(euler_ctx *ctx, const u64 *d_lmers, u64 n, u64 mask, u64 *d_pk, u64 *d_sk);
 // d_stats: [0] += forward l-windows, [1] += forward (l-1)-windows, [2] |= 1 on table overflow
 int enc_count_canonical(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u64 *tab_keys,
-                        u32 *tab_cnt, u64 cap, u64 *d_stats);
+                        u32 *tab_cnt, u64 cap, TableHash th, u64 *d_stats);
 
 // ---- graph.cu
 // vertex-id lookup over the canonical k-mer table: id of strand 0 (canonical orientation) in id0,
@@ -20,6 +20,7 @@ struct VertexTable {
     const u32 *id1;
     u64 cap;
     u32 k;
+    TableHash th;  // home rule of this table (plain or minimizer-ordered)
 };
 // plain key -> value table of the module-level API (pygpuhash TK/TV)
 struct PlainTable {
@@ -30,7 +31,8 @@ struct PlainTable {
 
 int graph_table_clear(euler_ctx *ctx, u64 *keys, u32 *vals, u64 cap);
 // insert canon(prefix) and canon(suffix) of every key of the canonical l-mer table
-int graph_vertex_insert(euler_ctx *ctx, const u64 *lt_keys, u64 lt_cap, u32 l, u64 *vt_keys, u64 vt_cap, u64 *d_flags);
+int graph_vertex_insert(euler_ctx *ctx, const u64 *lt_keys, u64 lt_cap, u32 l, u64 *vt_keys, u64 vt_cap, TableHash vth,
+                        u64 *d_flags);
 // exclusive scan of strand weights (0 empty / 1 palindrome / 2) over table slots
 int graph_slot_scan(euler_ctx *ctx, const u64 *keys, u64 cap, u32 len, u32 *d_base, u64 *d_total);
 // both-strand (key, multiplicity) pairs in slot order
@@ -39,8 +41,8 @@ int graph_compact_lmers(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, c
 // both-strand vertex keys in slot order
 int graph_compact_vertices(euler_ctx *ctx, const u64 *vt_keys, const u32 *vt_base, u64 vt_cap, u32 k, u64 *vkeys);
 // id0/id1 of the table slot of each (sorted) vertex key: id = index in vkeys
-int graph_assign_sorted_ids(euler_ctx *ctx, const u64 *vkeys, u64 nv, const u64 *vt_keys, u64 vt_cap, u32 k, u32 *id0,
-                            u32 *id1);
+int graph_assign_sorted_ids(euler_ctx *ctx, const u64 *vkeys, u64 nv, const u64 *vt_keys, u64 vt_cap, u32 k, TableHash vth,
+                            u32 *id0, u32 *id1);
 // D1 debruijnCount (+ compressed edges ev1/ev2) over explicit l-mer arrays
 int graph_degree_slots(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, u64 nl, u32 l, const VertexTable &vt,
                        u32 *lcount, u32 *ecount, u32 *ev1, u32 *ev2);

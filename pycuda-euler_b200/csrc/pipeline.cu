@@ -66,6 +66,23 @@ static double table_load()
     }
     return lf;
 }
+// Minimizer-ordered homes (common.cuh) for tables that are big enough to matter; vertices are the
+// shortest keys, so the minimizer length is bounded by k.  EULER_B200_MINHASH=0 turns it off.
+static TableHash table_hash_for(u64 cap, u32 k)
+{
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("EULER_B200_MINHASH");
+        on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    const u64 nb = cap / EULER_BUCKET;
+    TableHash th = {0, 0};
+    if (on && k >= 8 && nb > 64 * EULER_SPAN) {
+        th.span_nb = (u32)(nb - EULER_SPAN);
+        th.m = k < 12 ? k : 12;
+    }
+    return th;
+}
 static u64 cap_for(u64 n) { return round_up((u64)((double)(n < 64 ? 64 : n) / table_load()) + 1, 1024); }
 
 static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 distinct_hint, euler_stats *stats)
@@ -89,6 +106,7 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
     u64 lt_cap = cap_for(est_l), vt_cap = cap_for(est_v);
 
     u64 h[8] = {0};
+    TableHash lth = {0, 0}, vth = {0, 0};
     u32 retries = 0, launches = 1;  // mark_starts
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
     EULER_TRY(enc_mark_starts(ctx, P->d_off, P->nreads, B, P->start_bits.ptr()));
@@ -104,13 +122,15 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
         EULER_TRY(graph_table_clear(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap));
         EULER_TRY(graph_table_clear(ctx, P->vt_keys.ptr(), nullptr, vt_cap));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
+        lth = table_hash_for(lt_cap, k);
+        vth = table_hash_for(vt_cap, k);
         EULER_TRY(enc_count_canonical(ctx, P->d_buf, B, P->start_bits.ptr(), l, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap,
-                                      P->stats.ptr()));
+                                      lth, P->stats.ptr()));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
         launches += 4;  // count, l-mer pair scan, vertex insert, vertex slot scan
         EULER_TRY(graph_lt_scan(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap, l, P->lt_base.ptr(), P->lt_eoff.ptr(),
                                 P->stats.ptr() + 3));
-        EULER_TRY(graph_vertex_insert(ctx, P->lt_keys.ptr(), lt_cap, l, P->vt_keys.ptr(), vt_cap, P->stats.ptr() + 2));
+        EULER_TRY(graph_vertex_insert(ctx, P->lt_keys.ptr(), lt_cap, l, P->vt_keys.ptr(), vt_cap, vth, P->stats.ptr() + 2));
         EULER_TRY(graph_slot_scan(ctx, P->vt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(), P->stats.ptr() + 4));
         EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 6));
         if ((h[2] & 3) == 0) break;
@@ -135,7 +155,7 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
     CUDA_TRY(ctx, cudaMemsetAsync(P->lcount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
     CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
     EULER_TRY(graph_compact_vertices(ctx, P->vt_keys.ptr(), P->vt_id0.ptr(), vt_cap, k, P->vkeys.ptr()));
-    VertexTable vt = {P->vt_keys.ptr(), P->vt_id0.ptr(), nullptr, vt_cap, k};
+    VertexTable vt = {P->vt_keys.ptr(), P->vt_id0.ptr(), nullptr, vt_cap, k, vth};
     if (flags & EULER_RUN_CANONICAL_IDS) {
         // ids = rank in ascending key order (B14): sort both-strand l-mers and vertices, then D1 over the arrays
         const u64 nmax = U_l > V ? U_l : V;
@@ -148,7 +168,7 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
         EULER_TRY(radix_sort_pairs(ctx, P->lkeys.ptr(), P->lvals.ptr(), U_l, 2 * (int)l, P->sort_k.ptr(), P->sort_v.ptr(),
                                    P->sort_hist.ptr()));
         EULER_TRY(radix_sort_pairs(ctx, P->vkeys.ptr(), nullptr, V, 2 * (int)k, P->sort_k.ptr(), nullptr, P->sort_hist.ptr()));
-        EULER_TRY(graph_assign_sorted_ids(ctx, P->vkeys.ptr(), V, P->vt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(),
+        EULER_TRY(graph_assign_sorted_ids(ctx, P->vkeys.ptr(), V, P->vt_keys.ptr(), vt_cap, k, vth, P->vt_id0.ptr(),
                                           P->vt_id1.ptr()));
         vt.id1 = P->vt_id1.ptr();
         EULER_TRY(graph_degree_slots(ctx, P->lkeys.ptr(), P->lvals.ptr(), U_l, l, vt, P->lcount.ptr(), P->ecount.ptr(),
@@ -433,7 +453,7 @@ int euler_dist_build(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_
     CUDA_TRY(ctx, cudaMemsetAsync(P->lcount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
     CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
     EULER_TRY(graph_compact_vertices(ctx, P->vt_keys.ptr(), P->vt_id0.ptr(), vt_cap, k, P->vkeys.ptr()));
-    VertexTable vt = {P->vt_keys.ptr(), P->vt_id0.ptr(), nullptr, vt_cap, k};
+    VertexTable vt = {P->vt_keys.ptr(), P->vt_id0.ptr(), nullptr, vt_cap, k, TableHash{0, 0}};
     EULER_TRY(dist_edges(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), P->lt_base.ptr(), P->lt_eoff.ptr(), lt_cap, l, vt, rank, nranks,
                          P->lkeys.ptr(), P->lvals.ptr(), P->loffs.ptr(), P->ev1.ptr(), P->ev2.ptr(), P->lcount.ptr(),
                          P->ecount.ptr()));
