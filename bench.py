@@ -189,7 +189,7 @@ def main():
     torch.cuda.synchronize()
     # a user knows the genome size; per rank ~2/world of the canonical l-mers are incident to owned vertices
     if wl["err_ppm"] == 0:
-        hint = wl["G"] if world == 1 else int(wl["G"] * (2.0 - 1.0 / world) * 1.02)
+        hint = wl["G"] if world == 1 else int(wl["G"] * 1.15)   # ~1.05 copies with minimizer ownership
     else:
         hint = 0
 
@@ -316,6 +316,8 @@ def main():
             "clocks": clocks,
             "gpu_launches": int(launches_total),
         }
+        if world > 1 and info:
+            line["dist"] = {k: info[k] for k in ("sent_keys", "recv_keys", "exchange_bytes", "exact_fallback", "phase_ms")}
         if e2e:
             line["e2e"] = {"value": nk_total / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],

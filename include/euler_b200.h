@@ -222,6 +222,11 @@ int euler_dist_count(euler_ctx *ctx, const void *d_buf, const void *d_read_off, 
 /* d_send: u64[sum counts]; send_off[r] = first index of rank r's keys (exclusive scan of counts) */
 int euler_dist_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads,
                        uint64_t n_bases, uint32_t l, uint32_t nranks, void *d_send, const uint64_t *send_off);
+/* single-pass form of count + scatter: segment d of d_send starts at d * seg_cap keys; counts has
+ * nranks + 2 entries as above; counts[d] > seg_cap means that segment overflowed (redo with exact sizes) */
+int euler_dist_scatter_segments(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads,
+                                uint64_t n_bases, uint32_t l, uint32_t nranks, void *d_send, uint64_t seg_cap,
+                                uint64_t *counts);
 int euler_dist_build(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_t l, uint32_t rank,
                      uint32_t nranks, uint64_t distinct_hint, euler_stats *stats);
 

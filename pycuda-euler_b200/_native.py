@@ -96,6 +96,7 @@ def load():
         "euler_synth_reads_dev": [vp, u64, u32, u32, u64, u64, vp],
         "euler_dist_count": [vp, vp, vp, u64, u64, u32, u32, vp],
         "euler_dist_scatter": [vp, vp, vp, u64, u64, u32, u32, vp, vp],
+        "euler_dist_scatter_segments": [vp, vp, vp, u64, u64, u32, u32, vp, u64, vp],
         "euler_dist_build": [vp, vp, u64, u32, u32, u32, u64, vp],
         "euler_compat_phase1": [vp, vp, u64, u32, vp, vp],
         "euler_compat_copy_to_bucket": [vp, vp, vp, vp, u64, vp, u32, vp, vp],
@@ -465,6 +466,13 @@ class Context:
         send_off = _arr(send_off, np.uint64)
         self.check(self.lib.euler_dist_scatter(self.h, C.c_void_p(int(d_buf)), C.c_void_p(int(d_off)), int(nreads),
                                                int(n_bases), int(l), int(nranks), C.c_void_p(int(d_send)), _p(send_off)))
+
+    def dist_scatter_segments(self, d_buf, d_off, nreads, n_bases, l, nranks, d_send, seg_cap):
+        counts = np.zeros(nranks + 2, np.uint64)
+        self.check(self.lib.euler_dist_scatter_segments(self.h, C.c_void_p(int(d_buf)), C.c_void_p(int(d_off)), int(nreads),
+                                                        int(n_bases), int(l), int(nranks), C.c_void_p(int(d_send)),
+                                                        int(seg_cap), _p(counts)))
+        return counts
 
     def dist_build(self, d_keys, nkeys, l, rank, nranks, distinct_hint=0):
         st = Stats()

@@ -18,34 +18,74 @@
 
 #define DB 256
 
-__device__ __forceinline__ u32 owner_of(u64 canon_kmer, u32 nranks)
+// Owner of a vertex = re-mixed score of its minimizer (smallest scrambled canonical m-mer), scaled
+// to the rank count.  Adjacent k-mers almost always share their minimizer, so the prefix and suffix
+// vertex of an l-mer have the same owner ~(1 - 2/(k-m+2)) of the time: ~1.1 copies of every l-mer
+// cross the fabric instead of ~(2 - 1/N) with a per-k-mer hash.
+#define DIST_M 12
+__device__ __forceinline__ u32 dist_m(u32 k) { return k < DIST_M ? k : DIST_M; }
+__device__ __forceinline__ u32 owner_from_score(u32 score, u32 nranks)
 {
-    const u64 h = (canon_kmer ^ (canon_kmer >> 31)) * 0xD6E8FEB86659FD93ull;
-    return (u32)(((h >> 32) * (u64)nranks) >> 32);
+    u32 h = score;
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return (u32)(((u64)h * nranks) >> 32);
 }
-__device__ __forceinline__ u32 owner_kmer(u64 v, u32 k, u32 nranks)
+// owners of the prefix and suffix k-mer of an l-mer (either orientation: the minimizer is strand symmetric)
+__device__ __forceinline__ void owners_of_lmer(u64 x, u32 l, u32 nranks, u32 &own_prefix, u32 &own_suffix)
 {
-    const u64 r = revcomp64(v, k);
-    return owner_of(v < r ? v : r, nranks);
+    u32 all, but_last, but_first;
+    min_scores(x, l, dist_m(l - 1), all, but_last, but_first);
+    own_prefix = owner_from_score(but_last, nranks);
+    own_suffix = owner_from_score(but_first, nranks);
 }
 
+// sliding minima for the partition kernel: s[t], t = position + WK, holds the m-mer scores of the
+// WK positions before the chunk and the chunk's 16; for the l-mer ending at chunk position i the
+// prefix k-mer owns m-mers ending at positions i-WK .. i-1 and the suffix k-mer i-WK+1 .. i.
+template <int WK>
+struct WinMin2 {
+    static constexpr int N = WK + 16;
+    static constexpr int E = (WK >= 16) ? 4 : (WK >= 8) ? 3 : (WK >= 4) ? 2 : (WK >= 2) ? 1 : 0;
+    static constexpr int P = 1 << E;
+    __device__ __forceinline__ static void run(u32 (&s)[N], u32 (&wp)[16], u32 (&ws)[16])
+    {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const int h = 1 << e;
+#pragma unroll
+            for (int t = 0; t + h < N; t++) s[t] = s[t] < s[t + h] ? s[t] : s[t + h];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const u32 a = s[i], b = s[i + WK - P], c = s[i + 1], d = s[i + 1 + WK - P];
+            wp[i] = a < b ? a : b;
+            ws[i] = c < d ? c : d;
+        }
+    }
+};
+
 // ---- pass over the reads: per-destination counts (SCATTER=false) or key scatter (SCATTER=true) --
-template <bool SCATTER>
-__global__ void __launch_bounds__(DB, 4) dist_partition_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
+// SCATTER writes into fixed-capacity per-destination segments (seg_cap keys each); a cursor that
+// runs past its segment only counts (the caller then falls back to exact sizes).
+template <bool SCATTER, int WK>
+__global__ void __launch_bounds__(DB, 3) dist_partition_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
                                                                 const u32 *__restrict__ start_bits, u32 l, u32 nranks, u64 ntiles,
-                                                                u64 *__restrict__ counts /* [nranks] + N_l + N_k */,
-                                                                u64 *__restrict__ cursors, u64 *__restrict__ send)
+                                                                u64 *__restrict__ counts /* [16] per dest, [16] N_l, [17] N_k */,
+                                                                u64 *__restrict__ cursors, u64 *__restrict__ send,
+                                                                const u64 *__restrict__ seg_off, u64 seg_cap)
 {
+    __shared__ u32 s_own[16 * DB];
     const int lane = threadIdx.x & 31;
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
     const u32 k = l - 1, top = 2 * (l - 1);
-    const u64 lmask = key_mask_d(l), kmask = key_mask_d(k);
-    const unsigned lt = (1u << lane) - 1u;
+    const u64 lmask = key_mask_d(l);
+    const u32 m = dist_m(k);
     u32 nl_tot = 0, nk_tot = 0;
-    u32 cnt_local[16];
-#pragma unroll
-    for (int d = 0; d < 16; d++) cnt_local[d] = 0;
 
     for (u64 tile = warp; tile < ntiles; tile += nwarps) {
         const long long chunk = (long long)(tile * ENC_ADV) - ENC_HALO + lane;
@@ -55,90 +95,191 @@ __global__ void __launch_bounds__(DB, 4) dist_partition_kernel(const uint4 *__re
         const u32 s1 = __shfl_up_sync(0xffffffffu, c.smask, 1), s2 = __shfl_up_sync(0xffffffffu, c.smask, 2);
         u64 f = ((u64)p2 << 32) | p1;
         u64 rc = revcomp64(f & lmask, l);
+        if constexpr (WK > 0) {
+            const u32 mmask = m >= 16 ? 0xffffffffu : ((1u << (2 * m)) - 1u);
+            const u32 rsh = 2 * (l - m);
+            u32 sc[16];
+            {
+                u64 f2 = f, r2 = rc;
+                u32 cd = c.codes;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const u32 cc = cd >> 30;
+                    cd <<= 2;
+                    f2 = (f2 << 2) | cc;
+                    r2 = (r2 >> 2) | ((u64)(3u - cc) << top);
+                    const u32 w = (u32)f2 & mmask, rw = (u32)(r2 >> rsh) & mmask;
+                    sc[i] = mmer_score(w < rw ? w : rw);
+                }
+            }
+            u32 sv[WK + 16];
+#pragma unroll
+            for (int j = 0; j < WK; j++) {
+                const int pos = j - WK;
+                sv[j] = (pos >= -16) ? __shfl_up_sync(0xffffffffu, sc[(pos + 16) & 15], 1)
+                                     : __shfl_up_sync(0xffffffffu, sc[(pos + 32) & 15], 2);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) sv[WK + i] = sc[i];
+            u32 wp[16], ws[16];
+            WinMin2<WK>::run(sv, wp, ws);
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                s_own[i * DB + threadIdx.x] = owner_from_score(wp[i], nranks) | (owner_from_score(ws[i], nranks) << 8);
+        }
         const u32 pv = (v2 << 16) | v1, ps = (s2 << 16) | s1;
-        u32 vrun = (pv == 0xffffffffu) ? 32u : (u32)__ffs(~pv) - 1u;
-        u32 srun = ps ? (u32)__ffs(ps) - 1u : 32u;
-        u32 codes = c.codes;
-        u32 vm = (lane < ENC_HALO) ? 0u : (c.vmask << 16);
-        u32 sm = c.smask << 16;
-        if (lane < ENC_HALO) vrun = 0;
+        const u32 vrun0 = (lane < ENC_HALO) ? 0u : ((pv == 0xffffffffu) ? 32u : (u32)__ffs(~pv) - 1u);
+        const u32 srun0 = ps ? (u32)__ffs(ps) - 1u : 32u;
+        const u32 vm0 = (lane < ENC_HALO) ? 0u : (c.vmask << 16);   // halo lanes own no windows
+        const u32 sm0 = c.smask << 16;
+        const u64 f0 = f, rc0 = rc;
+
+        // pass 1: classify the 16 windows of this lane; per-destination counts in packed 16-bit fields
+        // (4 destinations per u64; a warp sends at most 32 * 32 keys to one destination per tile)
+        u64 cnt[4] = {0, 0, 0, 0};
+        u32 okmask = 0;
+        {
+            u32 vrun = vrun0, srun = srun0, codes = c.codes, vm = vm0, sm = sm0;
 #pragma unroll 1
-        for (int i = 0; i < 16; i++) {
-            const u32 cc = codes >> 30;
-            codes <<= 2;
-            const bool valid = (vm >> 31) != 0, start = (sm >> 31) != 0;
-            vm <<= 1;
-            sm <<= 1;
-            f = (f << 2) | cc;
-            rc = (rc >> 2) | ((u64)(3u - cc) << top);
-            vrun = valid ? vrun + 1u : 0u;
-            srun = start ? 0u : srun + 1u;
-            nk_tot += (vrun >= k && srun + 1u >= k) ? 1u : 0u;
-            const bool ok = vrun >= l && srun + 1u >= l;
-            nl_tot += ok ? 1u : 0u;
-            const u64 fm = f & lmask;
-            // rc(prefix x) = suffix(rc x), rc(suffix x) = prefix(rc x): owners come for free
-            const u64 p = fm >> 2, s = fm & kmask, rp = rc & kmask, rs = rc >> 2;
-            const u32 o1 = ok ? owner_of(p < rp ? p : rp, nranks) : 0xffffffffu;
-            u32 o2 = ok ? owner_of(s < rs ? s : rs, nranks) : 0xffffffffu;
-            if (o2 == o1) o2 = 0xffffffffu;
-            const u64 key = fm < rc ? fm : rc;
-#pragma unroll
-            for (int pass = 0; pass < 2; pass++) {
-                const u32 o = pass ? o2 : o1;
-                const unsigned peers = __match_any_sync(0xffffffffu, o);
-                if (o == 0xffffffffu) continue;
-                const int leader = __ffs(peers) - 1;
-                if (!SCATTER) {
-                    if (lane == leader) {
-#pragma unroll
-                        for (int d = 0; d < 16; d++)
-                            if ((u32)d == o) cnt_local[d] += __popc(peers);
-                    }
+            for (int i = 0; i < 16; i++) {
+                const u32 cc = codes >> 30;
+                codes <<= 2;
+                const bool valid = (vm >> 31) != 0, start = (sm >> 31) != 0;
+                vm <<= 1;
+                sm <<= 1;
+                f = (f << 2) | cc;
+                rc = (rc >> 2) | ((u64)(3u - cc) << top);
+                vrun = valid ? vrun + 1u : 0u;
+                srun = start ? 0u : srun + 1u;
+                nk_tot += (vrun >= k && srun + 1u >= k) ? 1u : 0u;
+                const bool ok = vrun >= l && srun + 1u >= l;
+                if (!ok) continue;
+                nl_tot++;
+                okmask |= 1u << i;
+                u32 o1, o2;
+                if constexpr (WK > 0) {
+                    const u32 o = s_own[i * DB + threadIdx.x];
+                    o1 = o & 0xffu;
+                    o2 = o >> 8;
                 } else {
-                    u64 base = 0;
-                    if (lane == leader) base = atomicAdd(cursors + o, (u64)__popc(peers));
-                    base = __shfl_sync(peers, base, leader);
-                    send[base + __popc(peers & lt)] = key;
+                    owners_of_lmer(f & lmask, l, nranks, o1, o2);
+                    s_own[i * DB + threadIdx.x] = o1 | (o2 << 8);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    if ((o1 >> 2) == (u32)g) cnt[g] += 1ull << (16 * (o1 & 3));
+                    if (o2 != o1 && (o2 >> 2) == (u32)g) cnt[g] += 1ull << (16 * (o2 & 3));
+                }
+            }
+        }
+        const u32 ngroups = (nranks + 3) >> 2;
+        if (!SCATTER) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                if ((u32)g < ngroups) {
+                    u64 t = cnt[g];
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    if ((lane >> 2) == g && (u32)lane < nranks) {
+                        const u64 mine = (t >> (16 * (lane & 3))) & 0xffffull;
+                        if (mine) atomicAdd(counts + lane, mine);
+                    }
+                }
+            }
+            continue;
+        }
+        // warp-exclusive scan of the packed counts; ONE cursor atomic per destination per tile
+        u64 excl[4] = {0, 0, 0, 0};
+        u64 base_reg = 0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            if ((u32)g < ngroups) {
+                u64 inc = cnt[g];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const u64 t = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += t;
+                }
+                excl[g] = inc - cnt[g];
+                const u64 tot = __shfl_sync(0xffffffffu, inc, 31);
+                if ((lane >> 2) == g && (u32)lane < nranks) {
+                    const u64 mine = (tot >> (16 * (lane & 3))) & 0xffffull;
+                    if (mine) base_reg = atomicAdd(cursors + lane, mine);
+                }
+            }
+        }
+        const u64 seg_reg = (u32)lane < nranks ? seg_off[lane] : 0ull;
+        // pass 2: roll again and write every key at base[dest] + keys of lower lanes + own keys so far
+        {
+            u64 f2 = f0, r2 = rc0;
+            u32 codes = c.codes;
+            u64 run[4] = {0, 0, 0, 0};
+#pragma unroll 1
+            for (int i = 0; i < 16; i++) {
+                const u32 cc = codes >> 30;
+                codes <<= 2;
+                f2 = (f2 << 2) | cc;
+                r2 = (r2 >> 2) | ((u64)(3u - cc) << top);
+                const bool ok = (okmask >> i) & 1u;
+                const u32 o = ok ? s_own[i * DB + threadIdx.x] : 0u;
+                const u32 o1 = o & 0xffu, o2 = o >> 8;
+                const u64 fm = f2 & lmask;
+                const u64 key = fm < r2 ? fm : r2;
+#pragma unroll
+                for (int pass = 0; pass < 2; pass++) {
+                    const u32 dst = pass ? o2 : o1;
+                    const u64 base = __shfl_sync(0xffffffffu, base_reg, dst & 31);
+                    const u64 seg = __shfl_sync(0xffffffffu, seg_reg, dst & 31);
+                    if (!ok || (pass && o2 == o1)) continue;
+                    u64 e = 0, r = 0;
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        if ((dst >> 2) == (u32)g) { e = excl[g]; r = run[g]; run[g] += 1ull << (16 * (dst & 3)); }
+                    }
+                    const u32 sh = 16 * (dst & 3);
+                    const u64 at = base + ((e >> sh) & 0xffffull) + ((r >> sh) & 0xffffull);
+                    if (at < seg_cap) send[seg + at] = key;
                 }
             }
         }
     }
-    if (!SCATTER) {
 #pragma unroll
-        for (int d = 0; d < 16; d++) {
-            u32 t = cnt_local[d];
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == 0 && t && (u32)d < nranks) atomicAdd(counts + d, (u64)t);
-        }
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-            nl_tot += __shfl_xor_sync(0xffffffffu, nl_tot, o);
-            nk_tot += __shfl_xor_sync(0xffffffffu, nk_tot, o);
-        }
-        if (lane == 0) {
-            if (nl_tot) atomicAdd(counts + 16, (u64)nl_tot);
-            if (nk_tot) atomicAdd(counts + 17, (u64)nk_tot);
-        }
+    for (int o = 16; o >= 1; o >>= 1) {
+        nl_tot += __shfl_xor_sync(0xffffffffu, nl_tot, o);
+        nk_tot += __shfl_xor_sync(0xffffffffu, nk_tot, o);
+    }
+    if (lane == 0) {
+        if (nl_tot) atomicAdd(counts + 16, (u64)nl_tot);
+        if (nk_tot) atomicAdd(counts + 17, (u64)nk_tot);
     }
 }
 
 int dist_partition(euler_ctx *ctx, bool scatter, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u32 nranks,
-                   u64 *d_counts, u64 *d_cursors, u64 *d_send)
+                   u64 *d_counts, u64 *d_cursors, u64 *d_send, const u64 *d_seg_off, u64 seg_cap)
 {
     if (!n_bases) return EULER_OK;
     const u64 nchunks = (n_bases + 15) / 16;
     const u64 ntiles = (nchunks + ENC_ADV - 1) / ENC_ADV;
-    u64 grid = (u64)ctx->num_sms * 4;
+    u64 grid = (u64)ctx->num_sms * 3;
     const u64 need = (ntiles + DB / 32 - 1) / (DB / 32);
     if (grid > need) grid = need;
-    if (!scatter)
-        dist_partition_kernel<false><<<(unsigned)grid, DB, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, nranks,
-                                                                              ntiles, d_counts, nullptr, nullptr);
-    else
-        dist_partition_kernel<true><<<(unsigned)grid, DB, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, nranks,
-                                                                             ntiles, nullptr, d_cursors, d_send);
+    const u32 k = l - 1;
+    const int WK = (int)(l - (k < DIST_M ? k : DIST_M));
+    const uint4 *b16 = (const uint4 *)d_buf;
+    const unsigned g = (unsigned)grid;
+#define LAUNCH_PART(S, WW)                                                                                              \
+    dist_partition_kernel<S, WW><<<g, DB, 0, ctx->stream>>>(b16, n_bases, d_bits, l, nranks, ntiles, d_counts, d_cursors, \
+                                                            d_send, d_seg_off, seg_cap)
+    if (!scatter) {
+        if (WK == 20) LAUNCH_PART(false, 20);
+        else if (WK == 10) LAUNCH_PART(false, 10);
+        else LAUNCH_PART(false, -1);
+    } else {
+        if (WK == 20) LAUNCH_PART(true, 20);
+        else if (WK == 10) LAUNCH_PART(true, 10);
+        else LAUNCH_PART(true, -1);
+    }
+#undef LAUNCH_PART
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
@@ -202,8 +343,8 @@ int dist_count_keys(euler_ctx *ctx, const u64 *d_keys, u64 n, u64 *tab_keys, u32
 
 // ---- ownership-aware graph stage ----------------------------------------------------------------
 __global__ void __launch_bounds__(DB) dist_vertex_insert_kernel(const u64 *__restrict__ lt_keys, u64 lt_cap, u32 l,
-                                                                 u64 *__restrict__ vt_keys, u64 vt_cap, u32 rank, u32 nranks,
-                                                                 u64 *flags)
+                                                                 u64 *__restrict__ vt_keys, u64 vt_cap,
+                                                                 const unsigned char *__restrict__ own_flags, u64 *flags)
 {
     const u64 slot = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= lt_cap) return;
@@ -216,46 +357,42 @@ __global__ void __launch_bounds__(DB) dist_vertex_insert_kernel(const u64 *__res
     const u64 rp = revcomp64(p, k), rs = revcomp64(s, k);
     const u64 cp = p < rp ? p : rp, cs = s < rs ? s : rs;
     bool bad = false;
-    if (owner_of(cp, nranks) == rank) bad |= table_insert(vt_keys, vt_cap, cp, max_probe) == EULER_NO_SLOT;
-    if (owner_of(cs, nranks) == rank) bad |= table_insert(vt_keys, vt_cap, cs, max_probe) == EULER_NO_SLOT;
+    const u32 own = own_flags[slot];
+    if (own & 1u) bad |= table_insert(vt_keys, vt_cap, cp, max_probe) == EULER_NO_SLOT;
+    if (own & 2u) bad |= table_insert(vt_keys, vt_cap, cs, max_probe) == EULER_NO_SLOT;
     if (bad) atomicOr((unsigned long long *)flags, 2ull);
 }
 
-int dist_vertex_insert(euler_ctx *ctx, const u64 *lt_keys, u64 lt_cap, u32 l, u64 *vt_keys, u64 vt_cap, u32 rank, u32 nranks,
-                       u64 *d_flags)
+int dist_vertex_insert(euler_ctx *ctx, const u64 *lt_keys, u64 lt_cap, u32 l, u64 *vt_keys, u64 vt_cap,
+                       const unsigned char *own_flags, u64 *d_flags)
 {
-    dist_vertex_insert_kernel<<<grid_for(lt_cap, DB), DB, 0, ctx->stream>>>(lt_keys, lt_cap, l, vt_keys, vt_cap, rank, nranks,
+    dist_vertex_insert_kernel<<<grid_for(lt_cap, DB), DB, 0, ctx->stream>>>(lt_keys, lt_cap, l, vt_keys, vt_cap, own_flags,
                                                                             d_flags);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
 
-// strands of the slot's canonical l-mer that are homed on this rank: bit0 = c (prefix owned),
-// bit1 = rc(c) (suffix owned; same record as bit0 for a palindrome)
-__device__ __forceinline__ u32 homed_strands(u64 c, u32 l, u32 rank, u32 nranks, bool &pal)
-{
-    const u32 k = l - 1;
-    pal = c == revcomp64(c, l);
-    const bool own_p = owner_kmer(c >> 2, k, nranks) == rank;
-    const bool own_s = owner_kmer(c & key_mask_d(k), k, nranks) == rank;
-    return (own_p ? 1u : 0u) | ((own_s && !pal) ? 2u : 0u);
-}
-
+// Ownership of the slot's canonical l-mer c, computed once (one pass over its m-mers) and cached:
+// bit0 = prefix(c) is ours (strand c is homed here), bit1 = suffix(c) is ours (strand rc(c) is homed here)
 struct DistLtScanPolicy {
     typedef u64 T;
     const u64 *keys;
     const u32 *cnt;
     u32 l, rank, nranks;
     u32 *base, *eoff;
+    unsigned char *own_flags;
     __device__ __forceinline__ u64 load(u64 i) const
     {
         const u64 c = keys[i];
-        if (c == EULER_EMPTY_KEY) return 0ull;
-        bool pal;
-        const u32 h = homed_strands(c, l, rank, nranks, pal);
+        if (c == EULER_EMPTY_KEY) { own_flags[i] = 0; return 0ull; }
+        u32 op, os;
+        owners_of_lmer(c, l, nranks, op, os);
+        const bool pal = c == revcomp64(c, l);
+        const u32 own = (op == rank ? 1u : 0u) | (os == rank ? 2u : 0u);
+        own_flags[i] = (unsigned char)own;
         const u64 n = cnt[i];
-        const u64 records = (h & 1u) + ((h >> 1) & 1u);
-        const u64 edges = pal ? ((h & 1u) ? 2 * n : 0) : n * records;
+        const u64 records = pal ? (own & 1u) : ((own & 1u) + ((own >> 1) & 1u));
+        const u64 edges = pal ? ((own & 1u) ? 2 * n : 0) : n * records;
         return (edges << 32) | records;
     }
     __device__ __forceinline__ void store(u64 i, u64 ex, u64, bool valid) const
@@ -265,14 +402,15 @@ struct DistLtScanPolicy {
 };
 
 int dist_lt_scan(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, u64 cap, u32 l, u32 rank, u32 nranks, u32 *base,
-                 u32 *eoff, u64 *d_total_packed)
+                 u32 *eoff, unsigned char *own_flags, u64 *d_total_packed)
 {
-    return scan_run(ctx, DistLtScanPolicy{lt_keys, lt_cnt, l, rank, nranks, base, eoff}, cap, d_total_packed);
+    return scan_run(ctx, DistLtScanPolicy{lt_keys, lt_cnt, l, rank, nranks, base, eoff, own_flags}, cap, d_total_packed);
 }
 
 __global__ void __launch_bounds__(DB) dist_edges_kernel(const u64 *__restrict__ lt_keys, const u32 *__restrict__ lt_cnt,
                                                          const u32 *__restrict__ base, const u32 *__restrict__ eoff, u64 cap, u32 l,
-                                                         VertexTable vt, u32 rank, u32 nranks, u64 *__restrict__ lkeys,
+                                                         VertexTable vt, const unsigned char *__restrict__ own_flags,
+                                                         u64 *__restrict__ lkeys,
                                                          u32 *__restrict__ lvals, u32 *__restrict__ loffs, u32 *__restrict__ ev1,
                                                          u32 *__restrict__ ev2, u32 *__restrict__ lcount, u32 *__restrict__ ecount)
 {
@@ -288,7 +426,8 @@ __global__ void __launch_bounds__(DB) dist_edges_kernel(const u64 *__restrict__ 
     const u64 p = c >> 2, s = c & kmask;
     const u64 rp = revcomp64(p, k), rs = revcomp64(s, k);
     const u64 cp = p < rp ? p : rp, cs = s < rs ? s : rs;
-    const bool own_p = owner_of(cp, nranks) == rank, own_s = owner_of(cs, nranks) == rank;
+    const u32 own = own_flags[slot];
+    const bool own_p = (own & 1u) != 0, own_s = (own & 2u) != 0;
     u32 id_p = EULER_NO_ID, id_rp = EULER_NO_ID, id_s = EULER_NO_ID, id_rs = EULER_NO_ID;
     if (own_p) {
         const u64 sp = table_find(vt.keys, vt.cap, cp);
@@ -323,10 +462,10 @@ __global__ void __launch_bounds__(DB) dist_edges_kernel(const u64 *__restrict__ 
 }
 
 int dist_edges(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, const u32 *base, const u32 *eoff, u64 cap, u32 l,
-               const VertexTable &vt, u32 rank, u32 nranks, u64 *lkeys, u32 *lvals, u32 *loffs, u32 *ev1, u32 *ev2, u32 *lcount,
-               u32 *ecount)
+               const VertexTable &vt, const unsigned char *own_flags, u64 *lkeys, u32 *lvals, u32 *loffs, u32 *ev1, u32 *ev2,
+               u32 *lcount, u32 *ecount)
 {
-    dist_edges_kernel<<<grid_for(cap, DB), DB, 0, ctx->stream>>>(lt_keys, lt_cnt, base, eoff, cap, l, vt, rank, nranks, lkeys, lvals,
+    dist_edges_kernel<<<grid_for(cap, DB), DB, 0, ctx->stream>>>(lt_keys, lt_cnt, base, eoff, cap, l, vt, own_flags, lkeys, lvals,
                                                                  loffs, ev1, ev2, lcount, ecount);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;

@@ -108,13 +108,14 @@ int graph_vertices_fused(euler_ctx *ctx, const u32 *lcount, const u32 *ecount, c
                          u32 *estart, euler_vertex *ev);
 
 // ---- dist.cu (k-mer-space partition across GPUs)
+// d_counts: 18 u64 ([0..15] keys per destination (count pass), [16] N_l, [17] N_k)
 int dist_partition(euler_ctx *ctx, bool scatter, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u32 nranks,
-                   u64 *d_counts, u64 *d_cursors, u64 *d_send);
+                   u64 *d_counts, u64 *d_cursors, u64 *d_send, const u64 *d_seg_off, u64 seg_cap);
 int dist_count_keys(euler_ctx *ctx, const u64 *d_keys, u64 n, u64 *tab_keys, u32 *tab_cnt, u64 cap, u64 *d_stats);
-int dist_vertex_insert(euler_ctx *ctx, const u64 *lt_keys, u64 lt_cap, u32 l, u64 *vt_keys, u64 vt_cap, u32 rank, u32 nranks,
-                       u64 *d_flags);
+int dist_vertex_insert(euler_ctx *ctx, const u64 *lt_keys, u64 lt_cap, u32 l, u64 *vt_keys, u64 vt_cap,
+                       const unsigned char *own_flags, u64 *d_flags);
 int dist_lt_scan(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, u64 cap, u32 l, u32 rank, u32 nranks, u32 *base,
-                 u32 *eoff, u64 *d_total_packed);
+                 u32 *eoff, unsigned char *own_flags, u64 *d_total_packed);
 int dist_edges(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, const u32 *base, const u32 *eoff, u64 cap, u32 l,
-               const VertexTable &vt, u32 rank, u32 nranks, u64 *lkeys, u32 *lvals, u32 *loffs, u32 *ev1, u32 *ev2, u32 *lcount,
-               u32 *ecount);
+               const VertexTable &vt, const unsigned char *own_flags, u64 *lkeys, u32 *lvals, u32 *loffs, u32 *ev1, u32 *ev2,
+               u32 *lcount, u32 *ecount);

@@ -20,6 +20,7 @@ struct Pipeline {
     // canonical l-mer table (SoA) and canonical k-mer (vertex) table
     DevArr<u64> lt_keys;
     DevArr<u32> lt_cnt, lt_base, lt_eoff;
+    DevArr<unsigned char> lt_own;  // partitioned path: ownership bits per slot
     u64 lt_cap = 0;
     DevArr<u64> vt_keys;
     DevArr<u32> vt_id0, vt_id1;
@@ -46,7 +47,7 @@ void pipeline_destroy(Pipeline *p)
 {
     if (!p) return;
     p->in_buf.free(); p->in_off.free(); p->start_bits.free();
-    p->lt_keys.free(); p->lt_cnt.free(); p->lt_base.free(); p->lt_eoff.free();
+    p->lt_keys.free(); p->lt_cnt.free(); p->lt_base.free(); p->lt_eoff.free(); p->lt_own.free();
     p->vt_keys.free(); p->vt_id0.free(); p->vt_id1.free(); p->stats.free();
     p->lkeys.free(); p->vkeys.free(); p->lvals.free(); p->loffs.free(); p->ev1.free(); p->ev2.free();
     p->lcount.free(); p->ecount.free(); p->lstart.free(); p->estart.free(); p->ev.free(); p->ee.free();
@@ -73,7 +74,7 @@ static TableHash table_hash_for(u64 cap, u32 k)
     static int on = -1;
     if (on < 0) {
         const char *e = getenv("EULER_B200_MINHASH");
-        on = (e && atoi(e) == 0) ? 0 : 1;
+        on = (e && atoi(e) != 0) ? 1 : 0;   // measured slower than the plain hash (bucket-load variance): opt-in
     }
     const u64 nb = cap / EULER_BUCKET;
     TableHash th = {0, 0};
@@ -376,7 +377,8 @@ int euler_dist_count(euler_ctx *ctx, const void *d_buf, const void *d_read_off, 
     EULER_TRY(P->start_bits.reserve(ctx, n_bases / 32 + 2));
     CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 64 * sizeof(u64), ctx->stream));
     EULER_TRY(enc_mark_starts(ctx, (const u64 *)d_read_off, nreads, n_bases, P->start_bits.ptr()));
-    EULER_TRY(dist_partition(ctx, false, d_buf, n_bases, P->start_bits.ptr(), l, nranks, P->stats.ptr() + 32, nullptr, nullptr));
+    EULER_TRY(dist_partition(ctx, false, d_buf, n_bases, P->start_bits.ptr(), l, nranks, P->stats.ptr() + 32, nullptr, nullptr,
+                             nullptr, 0));
     u64 h[18];
     EULER_TRY(read_u64s(ctx, P->stats.ptr() + 32, h, 18));
     for (u32 d = 0; d < nranks; d++) counts[d] = h[d];
@@ -394,10 +396,40 @@ int euler_dist_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     Pipeline *P = get_pipe(ctx);
     if (!P->start_bits.ptr()) return euler_fail(ctx, EULER_ERR_STATE, "euler_dist_scatter must follow euler_dist_count");
-    // cursors start at the per-destination offsets of the send buffer
-    CUDA_TRY(ctx, cudaMemcpyAsync(P->stats.ptr() + 8, send_off, nranks * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-    EULER_TRY(dist_partition(ctx, true, d_buf, n_bases, P->start_bits.ptr(), l, nranks, nullptr, P->stats.ptr() + 8,
-                             (u64 *)d_send));
+    // cursors count from 0 inside each destination's segment, which starts at send_off[d]
+    CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr() + 8, 0, 16 * sizeof(u64), ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(P->stats.ptr() + 24, send_off, nranks * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    EULER_TRY(dist_partition(ctx, true, d_buf, n_bases, P->start_bits.ptr(), l, nranks, P->stats.ptr() + 32, P->stats.ptr() + 8,
+                             (u64 *)d_send, P->stats.ptr() + 24, ~0ull));
+    return EULER_OK;
+}
+
+// single pass: scatter into nranks fixed-capacity segments of d_send (segment d starts at d * seg_cap);
+// counts[d] may exceed seg_cap, in which case the caller must redo the exchange with exact sizes
+int euler_dist_scatter_segments(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads, uint64_t n_bases,
+                                uint32_t l, uint32_t nranks, void *d_send, uint64_t seg_cap, uint64_t *counts)
+{
+    if (!ctx || !counts || (!d_send && n_bases)) return EULER_ERR_ARG;
+    if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
+    if (nranks < 1 || nranks > 16) return euler_fail(ctx, EULER_ERR_ARG, "nranks %u out of range [1,16]", nranks);
+    if (((uintptr_t)d_buf & 15) != 0) return euler_fail(ctx, EULER_ERR_ARG, "d_buf must be 16-byte aligned");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Pipeline *P = get_pipe(ctx);
+    EULER_TRY(P->stats.reserve(ctx, 64));
+    EULER_TRY(P->start_bits.reserve(ctx, n_bases / 32 + 2));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 64 * sizeof(u64), ctx->stream));
+    u64 seg_off[16];
+    for (u32 d = 0; d < 16; d++) seg_off[d] = (u64)d * seg_cap;
+    CUDA_TRY(ctx, cudaMemcpyAsync(P->stats.ptr() + 24, seg_off, nranks * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    EULER_TRY(enc_mark_starts(ctx, (const u64 *)d_read_off, nreads, n_bases, P->start_bits.ptr()));
+    EULER_TRY(dist_partition(ctx, true, d_buf, n_bases, P->start_bits.ptr(), l, nranks, P->stats.ptr() + 32, P->stats.ptr() + 8,
+                             (u64 *)d_send, P->stats.ptr() + 24, seg_cap));
+    u64 h[16], w[2];
+    EULER_TRY(read_u64s(ctx, P->stats.ptr() + 8, h, 16));
+    EULER_TRY(read_u64s(ctx, P->stats.ptr() + 48, w, 2));
+    for (u32 d = 0; d < nranks; d++) counts[d] = h[d];
+    counts[nranks] = w[0];
+    counts[nranks + 1] = w[1];
     return EULER_OK;
 }
 
@@ -424,6 +456,7 @@ int euler_dist_build(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_
         P->lt_cap = lt_cap; P->vt_cap = vt_cap;
         EULER_TRY(P->lt_keys.reserve(ctx, lt_cap)); EULER_TRY(P->lt_cnt.reserve(ctx, lt_cap));
         EULER_TRY(P->lt_base.reserve(ctx, lt_cap)); EULER_TRY(P->lt_eoff.reserve(ctx, lt_cap));
+        EULER_TRY(P->lt_own.reserve(ctx, lt_cap));
         EULER_TRY(P->vt_keys.reserve(ctx, vt_cap)); EULER_TRY(P->vt_id0.reserve(ctx, vt_cap));
         CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 8 * sizeof(u64), s));
         EULER_TRY(graph_table_clear(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap));
@@ -432,8 +465,9 @@ int euler_dist_build(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_
         EULER_TRY(dist_count_keys(ctx, (const u64 *)d_keys, nkeys, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap, P->stats.ptr()));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
         EULER_TRY(dist_lt_scan(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap, l, rank, nranks, P->lt_base.ptr(),
-                               P->lt_eoff.ptr(), P->stats.ptr() + 3));
-        EULER_TRY(dist_vertex_insert(ctx, P->lt_keys.ptr(), lt_cap, l, P->vt_keys.ptr(), vt_cap, rank, nranks, P->stats.ptr() + 2));
+                               P->lt_eoff.ptr(), P->lt_own.ptr(), P->stats.ptr() + 3));
+        EULER_TRY(dist_vertex_insert(ctx, P->lt_keys.ptr(), lt_cap, l, P->vt_keys.ptr(), vt_cap, P->lt_own.ptr(),
+                                     P->stats.ptr() + 2));
         EULER_TRY(graph_slot_scan(ctx, P->vt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(), P->stats.ptr() + 4));
         launches += 4;
         EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 6));
@@ -454,7 +488,7 @@ int euler_dist_build(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_
     CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
     EULER_TRY(graph_compact_vertices(ctx, P->vt_keys.ptr(), P->vt_id0.ptr(), vt_cap, k, P->vkeys.ptr()));
     VertexTable vt = {P->vt_keys.ptr(), P->vt_id0.ptr(), nullptr, vt_cap, k, TableHash{0, 0}};
-    EULER_TRY(dist_edges(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), P->lt_base.ptr(), P->lt_eoff.ptr(), lt_cap, l, vt, rank, nranks,
+    EULER_TRY(dist_edges(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), P->lt_base.ptr(), P->lt_eoff.ptr(), lt_cap, l, vt, P->lt_own.ptr(),
                          P->lkeys.ptr(), P->lvals.ptr(), P->loffs.ptr(), P->ev1.ptr(), P->ev2.ptr(), P->lcount.ptr(),
                          P->ecount.ptr()));
     EULER_TRY(graph_vertices_fused(ctx, P->lcount.ptr(), P->ecount.ptr(), P->vkeys.ptr(), V, P->lstart.ptr(), P->estart.ptr(),

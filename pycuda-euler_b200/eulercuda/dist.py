@@ -44,32 +44,79 @@ def torch_count_exchange(group=None, device="cuda"):
     return fn
 
 
-def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint=0, group=None, stream=None):
+_BUFFERS = {}
+
+
+def _buffer(name, n, device):
+    """grow-only cached int64 CUDA buffers (no allocation in steady state)"""
+    import torch
+    t = _BUFFERS.get((name, str(device)))
+    if t is None or t.numel() < n:
+        t = torch.empty(int(n * 1.1) + 1024, dtype=torch.int64, device=device)
+        _BUFFERS[(name, str(device))] = t
+    return t
+
+
+def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint=0, group=None, slack=1.25):
     """Run the partitioned hot path on this rank.  d_reads / d_off are CUDA tensors (uint8 / int64).
-    Returns (stats, info) where info has the window counts and exchange sizes."""
+
+    One pass over the reads scatters the canonical l-mer keys into `world` fixed-capacity segments
+    (expected size x `slack`); if a segment overflows (skewed minimizers) the exchange is redone
+    with exact sizes.  Returns (stats, info)."""
+    import time
     import torch
     import torch.distributed as dist
-    counts = ctx.dist_count(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world)
+    dev = d_reads.device
+    t0 = time.perf_counter()
+    if world == 1:
+        counts = ctx.dist_count(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, 1)
+        send = _buffer("send", int(counts[0]), dev)
+        ctx.dist_scatter(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, 1, send.data_ptr(), np.zeros(1, np.uint64))
+        ctx.sync()
+        st = ctx.dist_build(send.data_ptr(), int(counts[0]), l, 0, 1, distinct_hint)
+        return st, {"n_lmer_windows": int(counts[1]), "n_kmer_windows": int(counts[2]), "sent_keys": int(counts[0]),
+                    "recv_keys": int(counts[0]), "exchange_bytes": 0, "exact_fallback": False}
+    # upper bound of windows; ~1.1 copies of each go out with minimizer ownership, allow for the worst case of 2
+    windows_ub = max(n_bases - nreads * (l - 1), 1)
+    seg_cap = int(windows_ub * slack * 1.15 / world) + 4096
+    send = _buffer("send", seg_cap * world, dev)
+    counts = ctx.dist_scatter_segments(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world, send.data_ptr(), seg_cap)
     send_counts = counts[:world].astype(np.int64).tolist()
     n_l, n_k = int(counts[world]), int(counts[world + 1])
-    if world > 1:
-        send_off, recv_counts = plan_exchange(send_counts, torch_count_exchange(group))
+    t1 = time.perf_counter()
+    overflow = torch.tensor([1 if max(send_counts) > seg_cap else 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(overflow, op=dist.ReduceOp.MAX, group=group)
+    exact = bool(overflow.item())
+    if exact:   # rare: redo with exact sizes on every rank
+        counts = ctx.dist_count(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world)
+        send_counts = counts[:world].astype(np.int64).tolist()
+        send_off = np.zeros(world, np.uint64)
+        send_off[1:] = np.cumsum(send_counts[:-1])
+        send = _buffer("send", int(sum(send_counts)), dev)
+        ctx.dist_scatter(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world, send.data_ptr(), send_off)
+        ctx.sync()
+        starts = [int(x) for x in send_off]
     else:
-        send_off, recv_counts = np.zeros(1, np.uint64), send_counts
-    send = torch.empty(max(int(sum(send_counts)), 1), dtype=torch.int64, device=d_reads.device)
-    ctx.dist_scatter(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world, send.data_ptr(), send_off)
-    ctx.sync()
-    if world > 1:
-        recv = torch.empty(max(int(sum(recv_counts)), 1), dtype=torch.int64, device=d_reads.device)
-        dist.all_to_all_single(recv[:sum(recv_counts)], send[:sum(send_counts)], output_split_sizes=recv_counts,
-                               input_split_sizes=send_counts, group=group)
-        torch.cuda.current_stream().synchronize()
-    else:
-        recv = send
+        starts = [d * seg_cap for d in range(world)]
+    recv_counts = torch_count_exchange(group)(send_counts)
+    recv = _buffer("recv", int(sum(recv_counts)), dev)
+    out_list, in_list, pos = [], [], 0
+    for src in range(world):
+        out_list.append(recv[pos:pos + recv_counts[src]])
+        pos += recv_counts[src]
+    for d in range(world):
+        in_list.append(send[starts[d]:starts[d] + send_counts[d]])
+    t2 = time.perf_counter()
+    dist.all_to_all(out_list, in_list, group=group)
+    torch.cuda.current_stream().synchronize()
+    t3 = time.perf_counter()
     nkeys = int(sum(recv_counts))
     st = ctx.dist_build(recv.data_ptr(), nkeys, l, rank, world, distinct_hint)
+    t4 = time.perf_counter()
     info = {"n_lmer_windows": n_l, "n_kmer_windows": n_k, "sent_keys": int(sum(send_counts)), "recv_keys": nkeys,
-            "exchange_bytes": 8 * int(sum(send_counts))}
+            "exchange_bytes": 8 * (int(sum(send_counts)) - send_counts[rank]), "exact_fallback": exact,
+            "phase_ms": {"partition": 1e3 * (t1 - t0), "count_exchange": 1e3 * (t2 - t1), "all_to_all": 1e3 * (t3 - t2),
+                         "build": 1e3 * (t4 - t3)}}
     return st, info
 
 

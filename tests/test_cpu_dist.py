@@ -10,10 +10,25 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _owner_np(canon, world):
-    c = np.asarray(canon, dtype=np.uint64)
-    h = (c ^ (c >> np.uint64(31))) * np.uint64(0xD6E8FEB86659FD93)
-    return (((h >> np.uint64(32)) * np.uint64(world)) >> np.uint64(32)).astype(np.int64)
+def _fmix32(h):
+    h ^= h >> 16
+    h = (h * 0x85ebca6b) & 0xffffffff
+    h ^= h >> 13
+    h = (h * 0xc2b2ae35) & 0xffffffff
+    return h ^ (h >> 16)
+
+
+def _owner_kmer(v, k, world, revcomp):
+    m = min(12, k)
+    mask = (1 << (2 * m)) - 1
+    best = 0xffffffff
+    for j in range(k - m + 1):
+        w = (int(v) >> (2 * (k - m - j))) & mask
+        c = min(w, revcomp(w, m))
+        s = (c * 2654435761) & 0xffffffff
+        s ^= s >> 15
+        best = min(best, s)
+    return (_fmix32(best) * world) >> 32
 
 
 def _worker(rank, world, port, q):
@@ -37,9 +52,8 @@ def _worker(rank, world, port, q):
         canon = np.minimum(fw, rc)
         kmask = np.uint64((1 << (2 * k)) - 1)
         pre, suf = fw >> np.uint64(2), fw & kmask
-        cp = np.array([min(int(x), oracle.revcomp(int(x), k)) for x in pre], np.uint64)
-        cs = np.array([min(int(x), oracle.revcomp(int(x), k)) for x in suf], np.uint64)
-        o1, o2 = _owner_np(cp, world), _owner_np(cs, world)
+        o1 = np.array([_owner_kmer(x, k, world, oracle.revcomp) for x in pre], np.int64)
+        o2 = np.array([_owner_kmer(x, k, world, oracle.revcomp) for x in suf], np.int64)
         buckets = [np.concatenate([canon[o1 == d], canon[(o2 == d) & (o2 != o1)]]) for d in range(world)]
         send_counts = [int(b.size) for b in buckets]
         send_off, recv_counts = plan_exchange(send_counts, torch_count_exchange(device="cpu"))
@@ -87,7 +101,7 @@ def test_two_rank_partition_over_gloo():
     kmask = (1 << (2 * k)) - 1
     for ck in canon:
         p, s = ck >> 2, ck & kmask
-        owners = {int(_owner_np([min(p, oracle.revcomp(p, k))], world)[0]), int(_owner_np([min(s, oracle.revcomp(s, k))], world)[0])}
+        owners = {_owner_kmer(p, k, world, oracle.revcomp), _owner_kmer(s, k, world, oracle.revcomp)}
         assert seen[ck] == owners
 
 
