@@ -317,7 +317,7 @@ def main():
             "gpu_launches": int(launches_total),
         }
         if world > 1 and info:
-            line["dist"] = {k: info[k] for k in ("sent_keys", "recv_keys", "exchange_bytes", "exact_fallback", "phase_ms")}
+            line["dist"] = {k: info[k] for k in ("sent_keys", "recv_keys", "exchange_bytes", "exact_fallback", "transport", "phase_ms")}
         if e2e:
             line["e2e"] = {"value": nk_total / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],

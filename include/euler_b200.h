@@ -227,6 +227,19 @@ int euler_dist_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off
 int euler_dist_scatter_segments(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads,
                                 uint64_t n_bases, uint32_t l, uint32_t nranks, void *d_send, uint64_t seg_cap,
                                 uint64_t *counts);
+/* Peer-memory exchange (fuses the all-to-all into the scatter pass): every rank allocates a receive
+ * buffer of nranks * seg_cap keys, publishes its CUDA IPC handle (64 bytes), opens the others', and
+ * scatters with dst_ptrs[d] = (rank d's buffer) + my_rank * seg_cap.  After a barrier and an
+ * exchange of the counts, euler_dist_build_regions counts the nranks regions of the local buffer. */
+int euler_dist_recv_alloc(euler_ctx *ctx, uint64_t nkeys, void **dptr, unsigned char *handle64);
+int euler_dist_peer_open(euler_ctx *ctx, const unsigned char *handle64, void **dptr);
+int euler_dist_peer_close(euler_ctx *ctx, void *dptr);
+int euler_dist_scatter_peers(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads,
+                             uint64_t n_bases, uint32_t l, uint32_t nranks, void *const *dst_ptrs,
+                             uint64_t seg_cap, uint64_t *counts);
+int euler_dist_build_regions(euler_ctx *ctx, const void *d_keys, uint64_t region_stride,
+                             const uint64_t *region_counts, uint32_t l, uint32_t rank, uint32_t nranks,
+                             uint64_t distinct_hint, euler_stats *stats);
 int euler_dist_build(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_t l, uint32_t rank,
                      uint32_t nranks, uint64_t distinct_hint, euler_stats *stats);
 

@@ -98,6 +98,11 @@ def load():
         "euler_dist_scatter": [vp, vp, vp, u64, u64, u32, u32, vp, vp],
         "euler_dist_scatter_segments": [vp, vp, vp, u64, u64, u32, u32, vp, u64, vp],
         "euler_dist_build": [vp, vp, u64, u32, u32, u32, u64, vp],
+        "euler_dist_recv_alloc": [vp, u64, vp, vp],
+        "euler_dist_peer_open": [vp, vp, vp],
+        "euler_dist_peer_close": [vp, vp],
+        "euler_dist_scatter_peers": [vp, vp, vp, u64, u64, u32, u32, vp, u64, vp],
+        "euler_dist_build_regions": [vp, vp, u64, vp, u32, u32, u32, u64, vp],
         "euler_compat_phase1": [vp, vp, u64, u32, vp, vp],
         "euler_compat_copy_to_bucket": [vp, vp, vp, vp, u64, vp, u32, vp, vp],
         "euler_compat_bucket_sort": [vp, vp, vp, u64, vp, vp, u32, vp, vp],
@@ -478,6 +483,36 @@ class Context:
         st = Stats()
         self.check(self.lib.euler_dist_build(self.h, C.c_void_p(int(d_keys)), int(nkeys), int(l), int(rank), int(nranks),
                                              int(distinct_hint), C.byref(st)))
+        return st
+
+    def dist_recv_alloc(self, nkeys):
+        """(device pointer, 64-byte CUDA IPC handle) of this rank's peer-visible receive buffer"""
+        p = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        self.check(self.lib.euler_dist_recv_alloc(self.h, int(nkeys), C.byref(p), handle))
+        return p.value, bytes(handle)
+
+    def dist_peer_open(self, handle):
+        p = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self.check(self.lib.euler_dist_peer_open(self.h, buf, C.byref(p)))
+        return p.value
+
+    def dist_peer_close(self, ptr):
+        self.check(self.lib.euler_dist_peer_close(self.h, C.c_void_p(int(ptr))))
+
+    def dist_scatter_peers(self, d_buf, d_off, nreads, n_bases, l, nranks, dst_ptrs, seg_cap):
+        counts = np.zeros(nranks + 2, np.uint64)
+        arr = (C.c_void_p * nranks)(*[C.c_void_p(int(x)) for x in dst_ptrs])
+        self.check(self.lib.euler_dist_scatter_peers(self.h, C.c_void_p(int(d_buf)), C.c_void_p(int(d_off)), int(nreads),
+                                                     int(n_bases), int(l), int(nranks), arr, int(seg_cap), _p(counts)))
+        return counts
+
+    def dist_build_regions(self, d_keys, region_stride, region_counts, l, rank, nranks, distinct_hint=0):
+        st = Stats()
+        rc = _arr(region_counts, np.uint64)
+        self.check(self.lib.euler_dist_build_regions(self.h, C.c_void_p(int(d_keys)), int(region_stride), _p(rc), int(l),
+                                                     int(rank), int(nranks), int(distinct_hint), C.byref(st)))
         return st
 
     def synth_reads_dev(self, d_out, G, L, err_ppm, first, nreads):

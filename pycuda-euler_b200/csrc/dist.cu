@@ -71,14 +71,18 @@ struct WinMin2 {
 // ---- pass over the reads: per-destination counts (SCATTER=false) or key scatter (SCATTER=true) --
 // SCATTER writes into fixed-capacity per-destination segments (seg_cap keys each); a cursor that
 // runs past its segment only counts (the caller then falls back to exact sizes).
+#define PB 128          // partition kernel block: 4 warps, each with an 8 KB staging area
+#define PB_STAGE 1024   // keys per warp staging area (a tile emits at most 30 * 16 * 2 = 960)
 template <bool SCATTER, int WK>
-__global__ void __launch_bounds__(DB, 3) dist_partition_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
+__global__ void __launch_bounds__(PB, 4) dist_partition_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
                                                                 const u32 *__restrict__ start_bits, u32 l, u32 nranks, u64 ntiles,
                                                                 u64 *__restrict__ counts /* [16] per dest, [16] N_l, [17] N_k */,
                                                                 u64 *__restrict__ cursors, u64 *__restrict__ send,
                                                                 const u64 *__restrict__ seg_off, u64 seg_cap)
 {
-    __shared__ u32 s_own[16 * DB];
+    __shared__ u32 s_own[16 * PB];
+    __shared__ u64 s_stage[SCATTER ? (PB / 32) * PB_STAGE : 1];
+    u64 *stage = s_stage + (SCATTER ? (threadIdx.x >> 5) * PB_STAGE : 0);
     const int lane = threadIdx.x & 31;
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(DB, 3) dist_partition_kernel(const uint4 *__re
             WinMin2<WK>::run(sv, wp, ws);
 #pragma unroll
             for (int i = 0; i < 16; i++)
-                s_own[i * DB + threadIdx.x] = owner_from_score(wp[i], nranks) | (owner_from_score(ws[i], nranks) << 8);
+                s_own[i * PB + threadIdx.x] = owner_from_score(wp[i], nranks) | (owner_from_score(ws[i], nranks) << 8);
         }
         const u32 pv = (v2 << 16) | v1, ps = (s2 << 16) | s1;
         const u32 vrun0 = (lane < ENC_HALO) ? 0u : ((pv == 0xffffffffu) ? 32u : (u32)__ffs(~pv) - 1u);
@@ -158,12 +162,12 @@ __global__ void __launch_bounds__(DB, 3) dist_partition_kernel(const uint4 *__re
                 okmask |= 1u << i;
                 u32 o1, o2;
                 if constexpr (WK > 0) {
-                    const u32 o = s_own[i * DB + threadIdx.x];
+                    const u32 o = s_own[i * PB + threadIdx.x];
                     o1 = o & 0xffu;
                     o2 = o >> 8;
                 } else {
                     owners_of_lmer(f & lmask, l, nranks, o1, o2);
-                    s_own[i * DB + threadIdx.x] = o1 | (o2 << 8);
+                    s_own[i * PB + threadIdx.x] = o1 | (o2 << 8);
                 }
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
@@ -191,6 +195,7 @@ __global__ void __launch_bounds__(DB, 3) dist_partition_kernel(const uint4 *__re
         // warp-exclusive scan of the packed counts; ONE cursor atomic per destination per tile
         u64 excl[4] = {0, 0, 0, 0};
         u64 base_reg = 0;
+        u32 mine_reg = 0;   // lane d: keys this warp sends to destination d in this tile
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             if ((u32)g < ngroups) {
@@ -204,12 +209,21 @@ __global__ void __launch_bounds__(DB, 3) dist_partition_kernel(const uint4 *__re
                 const u64 tot = __shfl_sync(0xffffffffu, inc, 31);
                 if ((lane >> 2) == g && (u32)lane < nranks) {
                     const u64 mine = (tot >> (16 * (lane & 3))) & 0xffffull;
+                    mine_reg = (u32)mine;
                     if (mine) base_reg = atomicAdd(cursors + lane, mine);
                 }
             }
         }
         const u64 seg_reg = (u32)lane < nranks ? seg_off[lane] : 0ull;
-        // pass 2: roll again and write every key at base[dest] + keys of lower lanes + own keys so far
+        // warp-local layout of the staging area: destination after destination
+        u32 woff_reg = mine_reg;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, woff_reg, d);
+            if (lane >= d) woff_reg += t;
+        }
+        woff_reg -= mine_reg;
+        // pass 2: roll again and stage every key at woff[dest] + keys of lower lanes + own keys so far
         {
             u64 f2 = f0, r2 = rc0;
             u32 codes = c.codes;
@@ -221,15 +235,14 @@ __global__ void __launch_bounds__(DB, 3) dist_partition_kernel(const uint4 *__re
                 f2 = (f2 << 2) | cc;
                 r2 = (r2 >> 2) | ((u64)(3u - cc) << top);
                 const bool ok = (okmask >> i) & 1u;
-                const u32 o = ok ? s_own[i * DB + threadIdx.x] : 0u;
+                const u32 o = ok ? s_own[i * PB + threadIdx.x] : 0u;
                 const u32 o1 = o & 0xffu, o2 = o >> 8;
                 const u64 fm = f2 & lmask;
                 const u64 key = fm < r2 ? fm : r2;
 #pragma unroll
                 for (int pass = 0; pass < 2; pass++) {
                     const u32 dst = pass ? o2 : o1;
-                    const u64 base = __shfl_sync(0xffffffffu, base_reg, dst & 31);
-                    const u64 seg = __shfl_sync(0xffffffffu, seg_reg, dst & 31);
+                    const u32 wo = __shfl_sync(0xffffffffu, woff_reg, dst & 31);
                     if (!ok || (pass && o2 == o1)) continue;
                     u64 e = 0, r = 0;
 #pragma unroll
@@ -237,11 +250,23 @@ __global__ void __launch_bounds__(DB, 3) dist_partition_kernel(const uint4 *__re
                         if ((dst >> 2) == (u32)g) { e = excl[g]; r = run[g]; run[g] += 1ull << (16 * (dst & 3)); }
                     }
                     const u32 sh = 16 * (dst & 3);
-                    const u64 at = base + ((e >> sh) & 0xffffull) + ((r >> sh) & 0xffffull);
-                    if (at < seg_cap) send[seg + at] = key;
+                    stage[wo + (u32)((e >> sh) & 0xffffull) + (u32)((r >> sh) & 0xffffull)] = key;
                 }
             }
         }
+        __syncwarp();
+        // copy-out: contiguous, fully coalesced runs per destination (local HBM or a peer's over NVLink)
+        for (u32 d = 0; d < nranks; d++) {
+            const u32 tot = __shfl_sync(0xffffffffu, mine_reg, d);
+            const u64 base = __shfl_sync(0xffffffffu, base_reg, d);
+            const u64 seg = __shfl_sync(0xffffffffu, seg_reg, d);
+            const u32 wo = __shfl_sync(0xffffffffu, woff_reg, d);
+            for (u32 j = lane; j < tot; j += 32) {
+                const u64 at = base + j;
+                if (at < seg_cap) send[seg + at] = stage[wo + j];
+            }
+        }
+        __syncwarp();
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
@@ -260,15 +285,15 @@ int dist_partition(euler_ctx *ctx, bool scatter, const void *d_buf, u64 n_bases,
     if (!n_bases) return EULER_OK;
     const u64 nchunks = (n_bases + 15) / 16;
     const u64 ntiles = (nchunks + ENC_ADV - 1) / ENC_ADV;
-    u64 grid = (u64)ctx->num_sms * 3;
-    const u64 need = (ntiles + DB / 32 - 1) / (DB / 32);
+    u64 grid = (u64)ctx->num_sms * 4;
+    const u64 need = (ntiles + PB / 32 - 1) / (PB / 32);
     if (grid > need) grid = need;
     const u32 k = l - 1;
     const int WK = (int)(l - (k < DIST_M ? k : DIST_M));
     const uint4 *b16 = (const uint4 *)d_buf;
     const unsigned g = (unsigned)grid;
 #define LAUNCH_PART(S, WW)                                                                                              \
-    dist_partition_kernel<S, WW><<<g, DB, 0, ctx->stream>>>(b16, n_bases, d_bits, l, nranks, ntiles, d_counts, d_cursors, \
+    dist_partition_kernel<S, WW><<<g, PB, 0, ctx->stream>>>(b16, n_bases, d_bits, l, nranks, ntiles, d_counts, d_cursors, \
                                                             d_send, d_seg_off, seg_cap)
     if (!scatter) {
         if (WK == 20) LAUNCH_PART(false, 20);

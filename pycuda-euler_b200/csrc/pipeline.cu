@@ -40,6 +40,8 @@ struct Pipeline {
     // capacity memory: distinct canonical l-mers / k-mers seen on the last run of this input size
     u64 learned_bases = 0, learned_lc = 0, learned_vc = 0;
     u64 text_bytes = 0, text_n = 0;
+    void *recv_buf = nullptr;  // peer-visible receive buffer of the partitioned path (plain cudaMalloc)
+    u64 recv_cap = 0;
     euler_stats st = {};
 };
 
@@ -51,6 +53,7 @@ void pipeline_destroy(Pipeline *p)
     p->vt_keys.free(); p->vt_id0.free(); p->vt_id1.free(); p->stats.free();
     p->lkeys.free(); p->vkeys.free(); p->lvals.free(); p->loffs.free(); p->ev1.free(); p->ev2.free();
     p->lcount.free(); p->ecount.free(); p->lstart.free(); p->estart.free(); p->ev.free(); p->ee.free();
+    if (p->recv_buf) cudaFree(p->recv_buf);
     p->lev.free(); p->ent.free(); p->sort_k.free(); p->sort_v.free(); p->sort_hist.free();
     delete p;
 }
@@ -433,8 +436,106 @@ int euler_dist_scatter_segments(euler_ctx *ctx, const void *d_buf, const void *d
     return EULER_OK;
 }
 
+// ---- peer-memory exchange: the scatter kernel stores straight into the destination ranks' receive
+// buffers over NVLink (CUDA IPC mappings), so the all-to-all is fused into the partition pass.
+int euler_dist_recv_alloc(euler_ctx *ctx, uint64_t nkeys, void **dptr, unsigned char *handle64)
+{
+    if (!ctx || !dptr || !handle64) return EULER_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Pipeline *P = get_pipe(ctx);
+    if (P->recv_buf && P->recv_cap < nkeys) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(P->recv_buf);
+        P->recv_buf = nullptr;
+        P->recv_cap = 0;
+    }
+    if (!P->recv_buf) {
+        // plain cudaMalloc: IPC handles cannot be taken from stream-ordered pool memory
+        cudaError_t e = cudaMalloc(&P->recv_buf, (nkeys ? nkeys : 1) * sizeof(u64));
+        if (e != cudaSuccess) return euler_fail(ctx, EULER_ERR_NOMEM, "cudaMalloc(recv %llu keys): %s", (u64)nkeys, cudaGetErrorString(e));
+        P->recv_cap = nkeys;
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, P->recv_buf));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    *dptr = P->recv_buf;
+    return EULER_OK;
+}
+
+int euler_dist_peer_open(euler_ctx *ctx, const unsigned char *handle64, void **dptr)
+{
+    if (!ctx || !dptr || !handle64) return EULER_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CUDA_TRY(ctx, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return EULER_OK;
+}
+
+int euler_dist_peer_close(euler_ctx *ctx, void *dptr)
+{
+    if (!ctx) return EULER_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaIpcCloseMemHandle(dptr));
+    return EULER_OK;
+}
+
+// scatter with one destination pointer per rank (local or peer-mapped): region d receives at most
+// seg_cap keys; counts as in euler_dist_scatter_segments
+int euler_dist_scatter_peers(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads, uint64_t n_bases,
+                             uint32_t l, uint32_t nranks, void *const *dst_ptrs, uint64_t seg_cap, uint64_t *counts)
+{
+    if (!ctx || !counts || !dst_ptrs) return EULER_ERR_ARG;
+    if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
+    if (nranks < 1 || nranks > 16) return euler_fail(ctx, EULER_ERR_ARG, "nranks %u out of range [1,16]", nranks);
+    if (((uintptr_t)d_buf & 15) != 0) return euler_fail(ctx, EULER_ERR_ARG, "d_buf must be 16-byte aligned");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Pipeline *P = get_pipe(ctx);
+    EULER_TRY(P->stats.reserve(ctx, 64));
+    EULER_TRY(P->start_bits.reserve(ctx, n_bases / 32 + 2));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 64 * sizeof(u64), ctx->stream));
+    u64 seg_off[16];
+    for (u32 d = 0; d < nranks; d++) {
+        if (((uintptr_t)dst_ptrs[d] & 7) != 0) return euler_fail(ctx, EULER_ERR_ARG, "destination pointer %u not 8-byte aligned", d);
+        seg_off[d] = (u64)(uintptr_t)dst_ptrs[d] / sizeof(u64);   // the kernel indexes u64 words from address 0
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(P->stats.ptr() + 24, seg_off, nranks * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    EULER_TRY(enc_mark_starts(ctx, (const u64 *)d_read_off, nreads, n_bases, P->start_bits.ptr()));
+    EULER_TRY(dist_partition(ctx, true, d_buf, n_bases, P->start_bits.ptr(), l, nranks, P->stats.ptr() + 32, P->stats.ptr() + 8,
+                             (u64 *)nullptr, P->stats.ptr() + 24, seg_cap));
+    u64 h[16], w[2];
+    EULER_TRY(read_u64s(ctx, P->stats.ptr() + 8, h, 16));
+    EULER_TRY(read_u64s(ctx, P->stats.ptr() + 48, w, 2));
+    for (u32 d = 0; d < nranks; d++) counts[d] = h[d];
+    counts[nranks] = w[0];
+    counts[nranks + 1] = w[1];
+    return EULER_OK;
+}
+
+static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_t nregions, uint64_t region_stride,
+                           const uint64_t *region_counts, uint32_t l, uint32_t rank, uint32_t nranks, uint64_t distinct_hint,
+                           euler_stats *stats);
+
 int euler_dist_build(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_t l, uint32_t rank, uint32_t nranks,
                      uint64_t distinct_hint, euler_stats *stats)
+{
+    return dist_build_impl(ctx, d_keys, nkeys, 1, 0, &nkeys, l, rank, nranks, distinct_hint, stats);
+}
+
+// keys arrive in `nranks` regions of d_keys (region r starts at r * region_stride keys and holds region_counts[r] keys)
+int euler_dist_build_regions(euler_ctx *ctx, const void *d_keys, uint64_t region_stride, const uint64_t *region_counts,
+                             uint32_t l, uint32_t rank, uint32_t nranks, uint64_t distinct_hint, euler_stats *stats)
+{
+    if (!ctx || !region_counts) return EULER_ERR_ARG;
+    u64 total = 0;
+    for (u32 r = 0; r < nranks; r++) total += region_counts[r];
+    return dist_build_impl(ctx, d_keys, total, nranks, region_stride, region_counts, l, rank, nranks, distinct_hint, stats);
+}
+
+static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_t nregions, uint64_t region_stride,
+                           const uint64_t *region_counts, uint32_t l, uint32_t rank, uint32_t nranks, uint64_t distinct_hint,
+                           euler_stats *stats)
 {
     if (!ctx) return EULER_ERR_ARG;
     if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
@@ -462,7 +563,9 @@ int euler_dist_build(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_
         EULER_TRY(graph_table_clear(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap));
         EULER_TRY(graph_table_clear(ctx, P->vt_keys.ptr(), nullptr, vt_cap));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
-        EULER_TRY(dist_count_keys(ctx, (const u64 *)d_keys, nkeys, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap, P->stats.ptr()));
+        for (u32 r = 0; r < nregions; r++)
+            EULER_TRY(dist_count_keys(ctx, (const u64 *)d_keys + (u64)r * region_stride, region_counts[r], P->lt_keys.ptr(),
+                                      P->lt_cnt.ptr(), lt_cap, P->stats.ptr()));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
         EULER_TRY(dist_lt_scan(ctx, P->lt_keys.ptr(), P->lt_cnt.ptr(), lt_cap, l, rank, nranks, P->lt_base.ptr(),
                                P->lt_eoff.ptr(), P->lt_own.ptr(), P->stats.ptr() + 3));

@@ -57,12 +57,58 @@ def _buffer(name, n, device):
     return t
 
 
-def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint=0, group=None, slack=1.25):
+class PeerExchange:
+    """Peer-mapped receive buffers: rank r's scatter kernel stores the keys for rank d straight into
+    region r of d's buffer over NVLink (CUDA IPC), so the all-to-all is fused into the partition pass."""
+
+    def __init__(self, ctx, rank, world, seg_cap, group=None):
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world, self.seg_cap, self.group = ctx, rank, world, int(seg_cap), group
+        self.local_ptr, handle = ctx.dist_recv_alloc(self.seg_cap * world)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        self.bases = []
+        for d in range(world):
+            self.bases.append(self.local_ptr if d == rank else ctx.dist_peer_open(handles[d]))
+        # my region inside every destination's buffer
+        self.dst_ptrs = [b + 8 * self.seg_cap * rank for b in self.bases]
+
+    def close(self):
+        for d, b in enumerate(self.bases):
+            if d != self.rank:
+                try:
+                    self.ctx.dist_peer_close(b)
+                except Exception:
+                    pass
+        self.bases = []
+
+
+_PEER = {}
+
+
+def _peer_exchange(ctx, rank, world, seg_cap, group):
+    key = (id(ctx), world)
+    px = _PEER.get(key)
+    if px is None or px.seg_cap < seg_cap:
+        if px is not None:
+            px.close()
+        try:
+            px = PeerExchange(ctx, rank, world, seg_cap, group)
+        except Exception as e:          # no peer access on this box: fall back to NCCL all_to_all
+            px = e
+        _PEER[key] = px
+    return None if isinstance(px, Exception) else px
+
+
+def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint=0, group=None, slack=1.25,
+                      use_peer=True):
     """Run the partitioned hot path on this rank.  d_reads / d_off are CUDA tensors (uint8 / int64).
 
     One pass over the reads scatters the canonical l-mer keys into `world` fixed-capacity segments
-    (expected size x `slack`); if a segment overflows (skewed minimizers) the exchange is redone
-    with exact sizes.  Returns (stats, info)."""
+    (expected size x `slack`): with peer access straight into the owners' receive buffers over
+    NVLink, otherwise into a local send buffer followed by an NCCL all_to_all.  If a segment
+    overflows (skewed minimizers) the exchange is redone with exact sizes over NCCL.
+    Returns (stats, info)."""
     import time
     import torch
     import torch.distributed as dist
@@ -75,19 +121,31 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
         ctx.sync()
         st = ctx.dist_build(send.data_ptr(), int(counts[0]), l, 0, 1, distinct_hint)
         return st, {"n_lmer_windows": int(counts[1]), "n_kmer_windows": int(counts[2]), "sent_keys": int(counts[0]),
-                    "recv_keys": int(counts[0]), "exchange_bytes": 0, "exact_fallback": False}
-    # upper bound of windows; ~1.1 copies of each go out with minimizer ownership, allow for the worst case of 2
+                    "recv_keys": int(counts[0]), "exchange_bytes": 0, "exact_fallback": False, "transport": "none"}
+    # upper bound of windows; ~1.05 copies of each go out with minimizer ownership
     windows_ub = max(n_bases - nreads * (l - 1), 1)
     seg_cap = int(windows_ub * slack * 1.15 / world) + 4096
-    send = _buffer("send", seg_cap * world, dev)
-    counts = ctx.dist_scatter_segments(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world, send.data_ptr(), seg_cap)
+    px = _peer_exchange(ctx, rank, world, seg_cap, group) if use_peer else None
+    if px is not None:
+        seg_cap = px.seg_cap
+        counts = ctx.dist_scatter_peers(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world, px.dst_ptrs, seg_cap)
+    else:
+        send = _buffer("send", seg_cap * world, dev)
+        counts = ctx.dist_scatter_segments(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world, send.data_ptr(),
+                                           seg_cap)
     send_counts = counts[:world].astype(np.int64).tolist()
     n_l, n_k = int(counts[world]), int(counts[world + 1])
     t1 = time.perf_counter()
-    overflow = torch.tensor([1 if max(send_counts) > seg_cap else 0], dtype=torch.int64, device=dev)
-    dist.all_reduce(overflow, op=dist.ReduceOp.MAX, group=group)
-    exact = bool(overflow.item())
-    if exact:   # rare: redo with exact sizes on every rank
+    # the count exchange doubles as the barrier that makes every rank's peer stores visible
+    msg = send_counts + [1 if max(send_counts) > seg_cap else 0]
+    table = torch.tensor(msg, dtype=torch.int64, device=dev)
+    gathered = torch.empty((world, world + 1), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, table, group=group)
+    gathered = gathered.cpu().numpy()
+    recv_counts = [int(gathered[src, rank]) for src in range(world)]
+    exact = bool(gathered[:, world].max())
+    t2 = time.perf_counter()
+    if exact:   # rare: redo with exact sizes on every rank, over NCCL
         counts = ctx.dist_count(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world)
         send_counts = counts[:world].astype(np.int64).tolist()
         send_off = np.zeros(world, np.uint64)
@@ -95,26 +153,32 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
         send = _buffer("send", int(sum(send_counts)), dev)
         ctx.dist_scatter(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world, send.data_ptr(), send_off)
         ctx.sync()
+        recv_counts = torch_count_exchange(group)(send_counts)
         starts = [int(x) for x in send_off]
+        px = None
     else:
         starts = [d * seg_cap for d in range(world)]
-    recv_counts = torch_count_exchange(group)(send_counts)
-    recv = _buffer("recv", int(sum(recv_counts)), dev)
-    out_list, in_list, pos = [], [], 0
-    for src in range(world):
-        out_list.append(recv[pos:pos + recv_counts[src]])
-        pos += recv_counts[src]
-    for d in range(world):
-        in_list.append(send[starts[d]:starts[d] + send_counts[d]])
-    t2 = time.perf_counter()
-    dist.all_to_all(out_list, in_list, group=group)
-    torch.cuda.current_stream().synchronize()
-    t3 = time.perf_counter()
     nkeys = int(sum(recv_counts))
-    st = ctx.dist_build(recv.data_ptr(), nkeys, l, rank, world, distinct_hint)
+    if px is not None:
+        t3 = time.perf_counter()
+        st = ctx.dist_build_regions(px.local_ptr, seg_cap, recv_counts, l, rank, world, distinct_hint)
+        transport = "peer stores over NVLink (CUDA IPC), fused into the scatter kernel"
+    else:
+        recv = _buffer("recv", nkeys, dev)
+        out_list, in_list, pos = [], [], 0
+        for src in range(world):
+            out_list.append(recv[pos:pos + recv_counts[src]])
+            pos += recv_counts[src]
+        for d in range(world):
+            in_list.append(send[starts[d]:starts[d] + send_counts[d]])
+        dist.all_to_all(out_list, in_list, group=group)
+        torch.cuda.current_stream().synchronize()
+        t3 = time.perf_counter()
+        st = ctx.dist_build(recv.data_ptr(), nkeys, l, rank, world, distinct_hint)
+        transport = "NCCL all_to_all"
     t4 = time.perf_counter()
     info = {"n_lmer_windows": n_l, "n_kmer_windows": n_k, "sent_keys": int(sum(send_counts)), "recv_keys": nkeys,
-            "exchange_bytes": 8 * (int(sum(send_counts)) - send_counts[rank]), "exact_fallback": exact,
+            "exchange_bytes": 8 * (int(sum(send_counts)) - send_counts[rank]), "exact_fallback": exact, "transport": transport,
             "phase_ms": {"partition": 1e3 * (t1 - t0), "count_exchange": 1e3 * (t2 - t1), "all_to_all": 1e3 * (t3 - t2),
                          "build": 1e3 * (t4 - t3)}}
     return st, info
