@@ -235,3 +235,35 @@ def test_pipeline_device_resident_synthetic(ctx):
     st3 = ctx.run_dev(d.data_ptr(), offs.data_ptr(), n, n * L, l, N.RUN_CANONICAL_IDS, 64)
     assert st3.retries > 0 and st3.distinct_lmers == g.nl
     assert np.array_equal(ctx.download(N.ART_LMER_VALUES), g.lvals)
+
+
+def test_minimizer_ordered_tables_give_the_same_graph():
+    """EULER_B200_MINHASH=1 (minimizer-ordered homes; rolling-minimum kernels for l = 32 / 22, the
+    brute-force one otherwise) must not change any artefact.  The knob is read once per process, so
+    this runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oracle, _native as N
+from util import random_reads
+ctx = N.Context(0)
+reads = random_reads(4, 1500, genome_len=20000) + ["A" * 90, "ACGT" * 30]
+buf, off = oracle.pack_reads(reads)
+for l in (32, 22, 27, 12):
+    g = oracle.graph_build(buf, off, l, expand=True)
+    st = ctx.run_host(buf, off, l, N.RUN_EXPAND_EDGES | N.RUN_CANONICAL_IDS)
+    assert (st.distinct_lmers, st.distinct_kmers, st.edge_count) == (g.nl, g.nv, g.ne), l
+    assert np.array_equal(ctx.download(N.ART_LMER_KEYS), g.lk_lo) and np.array_equal(ctx.download(N.ART_LMER_VALUES), g.lvals)
+    assert np.array_equal(ctx.download(N.ART_EV), g.ev) and np.array_equal(ctx.download(N.ART_EE), g.ee)
+    st = ctx.run_host(buf, off, l, 0)
+    lk = ctx.download(N.ART_LMER_KEYS); o = np.argsort(lk)
+    assert np.array_equal(lk[o], g.lk_lo) and np.array_equal(ctx.download(N.ART_LMER_VALUES)[o], g.lvals)
+print("ok")
+''' % (root, os.path.join(root, "pycuda-euler_b200"), os.path.join(root, "tests"))
+    env = dict(os.environ, EULER_B200_MINHASH="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]

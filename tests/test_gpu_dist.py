@@ -41,7 +41,7 @@ def canon_np(x, k):
 
 
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
-@pytest.mark.parametrize("l", [12, 32])
+@pytest.mark.parametrize("l", [12, 22, 32])   # 22 and 32 use the rolling-minimizer kernels, 12 the generic one
 def test_partitioned_graph_equals_oracle(ctx, world, l):
     from eulercuda.dist import emulate_partitioned
     reads = random_reads(21, 600, genome_len=5000) + ["A" * 70, "ACGT" * 12]
