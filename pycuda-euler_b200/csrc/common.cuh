@@ -40,7 +40,8 @@ struct euler_ctx {
     cudaEvent_t ev[8] = {};
     int num_sms = EULER_SMS;
     size_t l2_bytes = 0;
-    size_t persist_max = 0;
+    size_t persist_max = 0;   // bytes of L2 that may be set aside for persisting lines
+    size_t window_max = 0;    // largest access-policy window
     size_t l2_part_budget = 0;  // table bytes one count pass may own (0 = default)
 };
 

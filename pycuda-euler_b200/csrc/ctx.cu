@@ -1,5 +1,6 @@
 // ctx.cu -- context, error reporting, grow-only device buffers.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "scan.cuh"
@@ -74,6 +75,12 @@ int euler_ctx_create(int device, euler_ctx **out)
         ctx->num_sms = prop.multiProcessorCount;
         ctx->l2_bytes = (size_t)prop.l2CacheSize;
         ctx->persist_max = (size_t)prop.persistingL2CacheMaxSize;
+        ctx->window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        // the persisting-L2 set-aside is only carved out on request: measured on B200 it slows every
+        // other kernel more than it helps the table (EULER_B200_L2_PERSIST=1 to try it)
+        const char *pe = getenv("EULER_B200_L2_PERSIST");
+        if (pe && atoi(pe) == 1 && ctx->persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->persist_max);
+        else ctx->persist_max = 0;
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return EULER_ERR_CUDA; }
     ctx->own_stream = true;

@@ -53,20 +53,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_exclusive_kernel(P p, u6
     if (tid == 0) s_tile = atomicAdd(counter, 1ull);
     __syncthreads();
     const u64 tile = s_tile;
-    const u64 base = tile * SCAN_TILE + (u64)warp * (32 * SCAN_ROWS) + lane;
-
-    typedef typename P::T T;  // u32 for plain sums, u64 for packed pairs: halves the register footprint
-    T v[SCAN_ROWS];
+    typedef typename P::T T;
+    constexpr int ROWS = sizeof(T) == 8 ? 8 : 16;   // 64-bit items: half the rows, same register budget
+    const u64 base = tile * (u64)(SCAN_THREADS * ROWS) + (u64)warp * (32 * ROWS) + lane;
+  // u32 for plain sums, u64 for packed pairs: halves the register footprint
+    T v[ROWS];
 #pragma unroll
-    for (int r = 0; r < SCAN_ROWS; r++) {
+    for (int r = 0; r < ROWS; r++) {
         const u64 idx = base + (u64)r * 32;
         v[r] = idx < n ? p.load(idx) : (T)0;
     }
     // per-row inclusive shuffle scan, row totals carried forward: ex[r] = exclusive prefix in the warp segment
-    T ex[SCAN_ROWS];
+    T ex[ROWS];
     T carry = 0;
 #pragma unroll
-    for (int r = 0; r < SCAN_ROWS; r++) {
+    for (int r = 0; r < ROWS; r++) {
         T inc = v[r];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_exclusive_kernel(P p, u6
     __syncthreads();
     const u64 off = s_prefix + warp_off;
 #pragma unroll
-    for (int r = 0; r < SCAN_ROWS; r++) {
+    for (int r = 0; r < ROWS; r++) {
         const u64 idx = base + (u64)r * 32;
         p.store(idx, off + ex[r], v[r], idx < n);
     }
@@ -166,7 +167,8 @@ static int scan_run(euler_ctx *ctx, P p, u64 n, u64 *d_total)
         if (d_total) CUDA_TRY(ctx, cudaMemsetAsync(d_total, 0, sizeof(u64), ctx->stream));
         return EULER_OK;
     }
-    const u64 ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    constexpr u64 tile_items = (u64)SCAN_THREADS * (sizeof(typename P::T) == 8 ? 8 : 16);
+    const u64 ntiles = (n + tile_items - 1) / tile_items;
     ScanState *state = nullptr;
     u64 *counter = nullptr;
     EULER_TRY(scan_state_reserve(ctx, ntiles, &state, &counter));
