@@ -144,6 +144,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = genome and reads grow with N (default); strong = the named data set is split over the ranks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -179,8 +181,9 @@ def main():
     L, k, l = wl["L"], wl["k"], wl["k"] + 1
     # Weak scaling: the genome (= the k-mer space) grows with the GPU count, every rank encodes its own
     # R reads of the shared data set and owns 1/world of the k-mer space (hash partition, one all-to-all).
-    G = wl["G"] * world
-    R = wl["R"]
+    strong = args.scaling == "strong" and world > 1
+    G = wl["G"] if strong else wl["G"] * world
+    R = -(-wl["R"] // world) if strong else wl["R"]
     first = rank * R
     d_reads = torch.empty(R * L, dtype=torch.uint8, device="cuda")
     ctx.synth_reads_dev(d_reads.data_ptr(), G, L, wl["err_ppm"], first, R)
@@ -189,7 +192,7 @@ def main():
     torch.cuda.synchronize()
     # a user knows the genome size; per rank ~2/world of the canonical l-mers are incident to owned vertices
     if wl["err_ppm"] == 0:
-        hint = wl["G"] if world == 1 else int(wl["G"] * 1.15)   # ~1.05 copies with minimizer ownership
+        hint = wl["G"] if world == 1 else int((G / world) * 1.15)   # ~1.05 copies with minimizer ownership
     else:
         hint = 0
 
@@ -291,7 +294,7 @@ def main():
                 traffic = None
         line = {
             "metric": METRIC, "value": nk_total / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {
                 "workload": args.workload, "genome_bp": wl["G"], "read_len": L, "coverage": wl["cov"], "err_ppm": wl["err_ppm"],

@@ -119,3 +119,9 @@ int dist_lt_scan(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, u64 cap,
 int dist_edges(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, const u32 *base, const u32 *eoff, u64 cap, u32 l,
                const VertexTable &vt, const unsigned char *own_flags, u64 *lkeys, u32 *lvals, u32 *loffs, u32 *ev1, u32 *ev2,
                u32 *lcount, u32 *ecount);
+
+// ---- packed.cu (L2-sized quotient table for the count kernel)
+int enc_count_packed(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u64 *tab, u32 b,
+                     u64 *side_keys, u32 *side_cnt, u64 side_cap, u64 *d_stats);
+int enc_unpack(euler_ctx *ctx, const u64 *tab, u32 b, const u64 *side_keys, const u32 *side_cnt, u64 side_cap, u64 *d_side_used,
+               u64 *keys, u32 *cnt);

@@ -59,6 +59,8 @@ struct Pipeline {
     // canonical l-mer table (SoA) and canonical k-mer (vertex) table
     LtTable lt;  // keys u64[cap] followed by counts u32[cap] in ONE allocation (one L2 access-policy window covers both)
     DevArr<u32> lt_base, lt_eoff;
+    DevArr<u64> lt_packed, side_keys;  // packed count table (packed.cu) and its wrap side table
+    DevArr<u32> side_cnt;
     DevArr<unsigned char> lt_own;  // partitioned path: ownership bits per slot
     u64 lt_cap = 0;
     DevArr<u64> vt_keys;
@@ -79,6 +81,7 @@ struct Pipeline {
     // capacity memory: distinct canonical l-mers / k-mers seen on the last run of this input size
     u64 learned_bases = 0, learned_lc = 0, learned_vc = 0;
     u64 text_bytes = 0, text_n = 0;
+    bool text_valid = false;  // contig text of the current graph is resident
     void *recv_buf = nullptr;  // peer-visible receive buffer of the partitioned path (plain cudaMalloc)
     u64 recv_cap = 0;
     euler_stats st = {};
@@ -88,7 +91,7 @@ void pipeline_destroy(Pipeline *p)
 {
     if (!p) return;
     p->in_buf.free(); p->in_off.free(); p->start_bits.free();
-    dev_free(p->lt.b); p->lt_base.free(); p->lt_eoff.free(); p->lt_own.free();
+    dev_free(p->lt.b); p->lt_packed.free(); p->side_keys.free(); p->side_cnt.free(); p->lt_base.free(); p->lt_eoff.free(); p->lt_own.free();
     p->vt_keys.free(); p->vt_id0.free(); p->vt_id1.free(); p->stats.free();
     p->lkeys.free(); p->vkeys.free(); p->lvals.free(); p->loffs.free(); p->ev1.free(); p->ev2.free();
     p->lcount.free(); p->ecount.free(); p->lstart.free(); p->estart.free(); p->ev.free(); p->ee.free();
@@ -126,12 +129,24 @@ static TableHash table_hash_for(u64 cap, u32 k)
     }
     return th;
 }
+// EULER_B200_PACKED=1 selects the packed quotient count table (packed.cu).  Measured on B200: it
+// removes the DRAM misses (DRAM read 2.8 GB -> 0.26 GB per launch, L2 hit 55 % -> 71 %) but issues
+// 56 % more instructions, and the kernel is issue/latency bound: 2.3 ms vs 1.5 ms.  Opt-in.
+static bool use_packed_table()
+{
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("EULER_B200_PACKED");
+        on = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    return on != 0;
+}
 static u64 cap_for(u64 n) { return round_up((u64)((double)(n < 64 ? 64 : n) / table_load()) + 1, 1024); }
 
 static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 distinct_hint, euler_stats *stats)
 {
     if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
-    P->l = l; P->flags = flags; P->have_graph = false; P->expanded = false;
+    P->l = l; P->flags = flags; P->have_graph = false; P->expanded = false; P->text_valid = false;
     const u32 k = l - 1;
     const u64 B = P->n_bases;
     cudaStream_t s = ctx->stream;
@@ -147,6 +162,14 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
     else if (P->learned_bases == B && P->learned_lc) { est_l = P->learned_lc + P->learned_lc / 32; est_v = P->learned_vc + P->learned_vc / 32; }
     else { est_l = B ? B : 1; est_v = est_l; }
     u64 lt_cap = cap_for(est_l), vt_cap = cap_for(est_v);
+    // packed count table: power-of-two bucket count, load factor in (0.375, 0.75]
+    bool packed = use_packed_table();
+    u32 pk_b = 8;
+    const u64 side_cap = 16384;
+    if (packed) {
+        while (((u64)EULER_BUCKET << pk_b) * 3 < est_l * 4 && pk_b < 31) pk_b++;
+        lt_cap = (u64)EULER_BUCKET << pk_b;
+    }
 
     u64 h[8] = {0};
     TableHash lth = {0, 0}, vth = {0, 0};
@@ -161,25 +184,40 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
         EULER_TRY(P->vt_keys.reserve(ctx, vt_cap));
         EULER_TRY(P->vt_id0.reserve(ctx, vt_cap));
         CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 16 * sizeof(u64), s));
-        EULER_TRY(graph_table_clear(ctx, P->lt.keys(), P->lt.cnt(), lt_cap));
         EULER_TRY(graph_table_clear(ctx, P->vt_keys.ptr(), nullptr, vt_cap));
-        l2_window(ctx, P->lt.b.p, P->lt.bytes());
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
-        lth = table_hash_for(lt_cap, k);
         vth = table_hash_for(vt_cap, k);
-        EULER_TRY(enc_count_canonical(ctx, P->d_buf, B, P->start_bits.ptr(), l, P->lt.keys(), P->lt.cnt(), lt_cap,
-                                      lth, P->stats.ptr()));
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
-        l2_window(ctx, nullptr, 0);
+        if (packed) {
+            EULER_TRY(P->lt_packed.reserve(ctx, lt_cap));
+            EULER_TRY(P->side_keys.reserve(ctx, side_cap)); EULER_TRY(P->side_cnt.reserve(ctx, side_cap));
+            CUDA_TRY(ctx, cudaMemsetAsync(P->lt_packed.ptr(), 0, lt_cap * sizeof(u64), s));
+            EULER_TRY(graph_table_clear(ctx, P->side_keys.ptr(), P->side_cnt.ptr(), side_cap));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
+            EULER_TRY(enc_count_packed(ctx, P->d_buf, B, P->start_bits.ptr(), l, P->lt_packed.ptr(), pk_b, P->side_keys.ptr(),
+                                       P->side_cnt.ptr(), side_cap, P->stats.ptr()));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+            EULER_TRY(enc_unpack(ctx, P->lt_packed.ptr(), pk_b, P->side_keys.ptr(), P->side_cnt.ptr(), side_cap,
+                                 P->stats.ptr() + 7, P->lt.keys(), P->lt.cnt()));
+            launches += 2;
+        } else {
+            EULER_TRY(graph_table_clear(ctx, P->lt.keys(), P->lt.cnt(), lt_cap));
+            l2_window(ctx, P->lt.b.p, P->lt.bytes());
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
+            lth = table_hash_for(lt_cap, k);
+            EULER_TRY(enc_count_canonical(ctx, P->d_buf, B, P->start_bits.ptr(), l, P->lt.keys(), P->lt.cnt(), lt_cap,
+                                          lth, P->stats.ptr()));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+            l2_window(ctx, nullptr, 0);
+        }
         launches += 4;  // count, l-mer pair scan, vertex insert, vertex slot scan
         EULER_TRY(graph_lt_scan(ctx, P->lt.keys(), P->lt.cnt(), lt_cap, l, P->lt_base.ptr(), P->lt_eoff.ptr(),
                                 P->stats.ptr() + 3));
         EULER_TRY(graph_vertex_insert(ctx, P->lt.keys(), lt_cap, l, P->vt_keys.ptr(), vt_cap, vth, P->stats.ptr() + 2));
         EULER_TRY(graph_slot_scan(ctx, P->vt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(), P->stats.ptr() + 4));
         EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 6));
-        if ((h[2] & 3) == 0) break;
-        if (++retries > 8) return euler_fail(ctx, EULER_ERR_OVERFLOW, "hash table overflow after %u regrows", retries);
-        if (h[2] & 1) lt_cap *= 2;
+        if ((h[2] & 7) == 0) break;
+        if (++retries > 10) return euler_fail(ctx, EULER_ERR_OVERFLOW, "hash table overflow after %u regrows", retries);
+        if (h[2] & 4) packed = false;   // wrap side table full (extreme repeats): use the SoA kernel
+        if (h[2] & 1) { lt_cap *= 2; pk_b++; }
         if (h[2] & 2) vt_cap *= 2;
     }
     const u64 N_l = h[0], N_k = h[1], U_l = h[3] & 0xffffffffull, V = h[4];
@@ -364,7 +402,7 @@ int euler_pipeline_contigs(euler_ctx *ctx, char *out, uint64_t *out_bytes, uint6
     const u32 E = (u32)P->E, V = (u32)P->V;
     *ncontigs = 0;
     if (!E) { *out_bytes = 0; return EULER_OK; }
-    if (!out) {  // sizing call: run the tour now, keep the text resident for the second call
+    if (!out || !P->text_valid) {  // sizing call (or first call): run the tour now, keep the text resident
         DevTmp<euler_succ_vertex> sv(ctx, E);
         DevTmp<u32> D(ctx, E), C(ctx, E), cmap(ctx, E), mark(ctx, E);
         DevTmp<u64> cnt(ctx, 1);
@@ -392,9 +430,11 @@ int euler_pipeline_contigs(euler_ctx *ctx, char *out, uint64_t *out_bytes, uint6
         char *d_text = nullptr;
         u64 bytes = 0, nc = 0;
         EULER_TRY(tour_emit_contigs(ctx, P->ev.ptr(), V, P->ee.ptr(), E, P->l, &d_text, &bytes, &nc));
-        P->text_bytes = bytes; P->text_n = nc;
-        *out_bytes = bytes; *ncontigs = nc;
-        return EULER_OK;
+        P->text_bytes = bytes; P->text_n = nc; P->text_valid = true;
+        if (!out) {
+            *out_bytes = bytes; *ncontigs = nc;
+            return EULER_OK;
+        }
     }
     const u64 bytes = P->text_bytes, nc = P->text_n;
     if (*out_bytes < bytes) return euler_fail(ctx, EULER_ERR_ARG, "contig buffer too small");

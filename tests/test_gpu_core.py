@@ -237,10 +237,12 @@ def test_pipeline_device_resident_synthetic(ctx):
     assert np.array_equal(ctx.download(N.ART_LMER_VALUES), g.lvals)
 
 
-def test_minimizer_ordered_tables_give_the_same_graph():
+@pytest.mark.parametrize("knob", ["EULER_B200_MINHASH", "EULER_B200_PACKED"])
+def test_opt_in_table_variants_give_the_same_graph(knob):
     """EULER_B200_MINHASH=1 (minimizer-ordered homes; rolling-minimum kernels for l = 32 / 22, the
-    brute-force one otherwise) must not change any artefact.  The knob is read once per process, so
-    this runs in a child process."""
+    brute-force one otherwise) and EULER_B200_PACKED=1 (packed quotient count table, count-wrap side
+    table) must not change any artefact.  The knobs are read once per process, so this runs in a
+    child process."""
     import os
     import subprocess
     import sys
@@ -251,7 +253,7 @@ sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
 import oracle, _native as N
 from util import random_reads
 ctx = N.Context(0)
-reads = random_reads(4, 1500, genome_len=20000) + ["A" * 90, "ACGT" * 30]
+reads = random_reads(4, 1500, genome_len=20000) + ["A" * 90, "ACGT" * 30] + ["C" * 100] * 40   # poly-C: wraps the packed count field
 buf, off = oracle.pack_reads(reads)
 for l in (32, 22, 27, 12):
     g = oracle.graph_build(buf, off, l, expand=True)
@@ -264,6 +266,6 @@ for l in (32, 22, 27, 12):
     assert np.array_equal(lk[o], g.lk_lo) and np.array_equal(ctx.download(N.ART_LMER_VALUES)[o], g.lvals)
 print("ok")
 ''' % (root, os.path.join(root, "pycuda-euler_b200"), os.path.join(root, "tests"))
-    env = dict(os.environ, EULER_B200_MINHASH="1")
+    env = dict(os.environ, **{knob: "1"})
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
