@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_exclusive_kernel(P p, u6
     __syncthreads();
     const u64 tile = s_tile;
     typedef typename P::T T;
-    constexpr int ROWS = sizeof(T) == 8 ? 8 : 16;   // 64-bit items: half the rows, same register budget
+    constexpr int ROWS = 16;
     const u64 base = tile * (u64)(SCAN_THREADS * ROWS) + (u64)warp * (32 * ROWS) + lane;
   // u32 for plain sums, u64 for packed pairs: halves the register footprint
     T v[ROWS];
@@ -63,20 +63,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_exclusive_kernel(P p, u6
         const u64 idx = base + (u64)r * 32;
         v[r] = idx < n ? p.load(idx) : (T)0;
     }
-    // per-row inclusive shuffle scan, row totals carried forward: ex[r] = exclusive prefix in the warp segment
-    T ex[ROWS];
+    // warp total of the segment (the per-row prefixes are recomputed in the store pass instead of being
+    // kept: 16 fewer live registers per thread, which buys a whole extra resident block)
     T carry = 0;
 #pragma unroll
-    for (int r = 0; r < ROWS; r++) {
-        T inc = v[r];
+    for (int r = 0; r < ROWS; r++) carry += v[r];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const T t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
-        }
-        ex[r] = carry + inc - v[r];
-        carry += __shfl_sync(0xffffffffu, inc, 31);
-    }
+    for (int d = 16; d >= 1; d >>= 1) carry += __shfl_xor_sync(0xffffffffu, carry, d);
     if (lane == 0) s_warp[warp] = carry;
     __syncthreads();
     u64 warp_off = 0, block_sum = 0;
@@ -124,11 +117,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_exclusive_kernel(P p, u6
         }
     }
     __syncthreads();
-    const u64 off = s_prefix + warp_off;
+    u64 off = s_prefix + warp_off;
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
         const u64 idx = base + (u64)r * 32;
-        p.store(idx, off + ex[r], v[r], idx < n);
+        T inc = v[r];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const T t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        p.store(idx, off + inc - v[r], v[r], idx < n);
+        off += __shfl_sync(0xffffffffu, inc, 31);
     }
 }
 
@@ -167,7 +167,7 @@ static int scan_run(euler_ctx *ctx, P p, u64 n, u64 *d_total)
         if (d_total) CUDA_TRY(ctx, cudaMemsetAsync(d_total, 0, sizeof(u64), ctx->stream));
         return EULER_OK;
     }
-    constexpr u64 tile_items = (u64)SCAN_THREADS * (sizeof(typename P::T) == 8 ? 8 : 16);
+    constexpr u64 tile_items = (u64)SCAN_THREADS * 16;
     const u64 ntiles = (n + tile_items - 1) / tile_items;
     ScanState *state = nullptr;
     u64 *counter = nullptr;

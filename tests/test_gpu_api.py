@@ -267,3 +267,42 @@ def test_errors_are_loud(ctx):
     with pytest.raises(N.EulerError):
         c2.download(N.ART_EE)               # edges were not expanded
     c2.close()
+
+
+def test_full_size_config2_properties_and_parity(ctx):
+    """BASELINE.json configs[1] at full size (4.6 Mbp, 100 bp, 30x, k = 31; 96.6 M k-mer windows), reads
+    generated on device: size-independent properties of the fast path, then full parity of the l-mer
+    and vertex tables with the oracle on the same reads."""
+    import torch
+    import _native as N
+    G, L, cov, l = 4_600_000, 100, 30, 32
+    R = G * cov // L
+    d = torch.empty(R * L, dtype=torch.uint8, device="cuda")
+    ctx.synth_reads_dev(d.data_ptr(), G, L, 0, 0, R)
+    offs = torch.arange(R + 1, dtype=torch.int64, device="cuda") * L
+    ctx.sync()
+    torch.cuda.synchronize()
+    st = ctx.run_dev(d.data_ptr(), offs.data_ptr(), R, R * L, l, 0, G)
+    assert st.n_kmer_windows == R * (L - l + 2) and st.n_lmer_windows == R * (L - l + 1)
+    assert st.edge_count == 2 * st.n_lmer_windows
+    lk, lv = ctx.download(N.ART_LMER_KEYS), ctx.download(N.ART_LMER_VALUES)
+    ev = ctx.download(N.ART_EV)
+    assert int(lv.sum(dtype=np.uint64)) == st.edge_count
+    assert int(ev["lcount"].sum(dtype=np.uint64)) == st.edge_count == int(ev["ecount"].sum(dtype=np.uint64))
+    lo = ctx.download(N.ART_LMER_OFFSETS)
+    assert lo[0] == 0 and int(lo[-1]) + int(lv[-1]) == st.edge_count
+    v1, v2 = ctx.download(N.ART_EDGE_V1), ctx.download(N.ART_EDGE_V2)
+    kmask = np.uint64((1 << 62) - 1)
+    assert np.array_equal(ev["vid"][v1], lk >> np.uint64(2)) and np.array_equal(ev["vid"][v2], lk & kmask)
+    # leaving multiplicity per vertex = sum over its edges (checksum of checksums)
+    assert np.array_equal(np.bincount(v1, weights=lv, minlength=len(ev)).astype(np.uint64), ev["lcount"].astype(np.uint64))
+    assert np.array_equal(np.bincount(v2, weights=lv, minlength=len(ev)).astype(np.uint64), ev["ecount"].astype(np.uint64))
+    # parity with the oracle at full size
+    buf = d.cpu().numpy()
+    g = oracle.graph_build(buf, oracle.fixed_offsets(R, L), l, expand=False)
+    assert (st.distinct_lmers, st.distinct_kmers, st.edge_count) == (g.nl, g.nv, g.ne)
+    o = np.argsort(lk, kind="stable")
+    assert np.array_equal(lk[o], g.lk_lo) and np.array_equal(lv[o], g.lvals)
+    ov = np.argsort(ev["vid"], kind="stable")
+    assert np.array_equal(ev["vid"][ov], g.vk_lo)
+    assert np.array_equal(ev["lcount"][ov], g.ev["lcount"]) and np.array_equal(ev["ecount"][ov], g.ev["ecount"])
