@@ -206,6 +206,21 @@ int euler_pipeline_device_ptr(euler_ctx *ctx, int which, void **dptr);
 int euler_pipeline_contigs(euler_ctx *ctx, char *out, uint64_t *out_bytes, uint64_t *ncontigs);
 
 /* =========================================================================================
+ * FASTA / FASTQ ingestion on device (replaces eulercuda.read_fasta :439-447 / read_fastq :44-56):
+ * the raw file bytes are parsed on the GPU (line split, header / '+' / quality skipping, read
+ * offsets) and the reads stay resident for the calls below.  format: 0 auto, 1 FASTA, 2 FASTQ.
+ * FASTA: every line not starting with '>' is one read; FASTQ: lines with index % 4 == 1.
+ * ======================================================================================= */
+int euler_ingest(euler_ctx *ctx, const char *file_bytes, uint64_t nbytes, int format, uint64_t *nreads,
+                 uint64_t *nbases);
+/* copy the parsed reads back: buf nbases bytes, read_off nreads + 1 entries (either may be NULL) */
+int euler_ingest_download(euler_ctx *ctx, char *buf, uint64_t *read_off);
+int euler_pipeline_run_ingested(euler_ctx *ctx, uint32_t l, uint32_t flags, uint64_t distinct_hint,
+                                euler_stats *stats);
+int euler_unitigs_ingested(euler_ctx *ctx, uint32_t K, uint32_t limit, char *out, uint64_t *out_bytes,
+                           uint64_t *ncontigs);
+
+/* =========================================================================================
  * k-mer-space partition across the GPUs of one box (one process per GPU; the caller owns the
  * collective, e.g. torch.distributed all_to_all_single over NCCL).  The reference has no analogue:
  * its only parallelism is Spark mapPartitions over read partitions (src/cli_spark_gpu.py:37).

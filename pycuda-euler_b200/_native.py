@@ -94,6 +94,10 @@ def load():
         "euler_pipeline_device_ptr": [vp, i32, vp],
         "euler_pipeline_contigs": [vp, vp, vp, vp],
         "euler_synth_reads_dev": [vp, u64, u32, u32, u64, u64, vp],
+        "euler_ingest": [vp, vp, u64, i32, vp, vp],
+        "euler_ingest_download": [vp, vp, vp],
+        "euler_pipeline_run_ingested": [vp, u32, u32, u64, vp],
+        "euler_unitigs_ingested": [vp, u32, u32, vp, vp, vp],
         "euler_dist_count": [vp, vp, vp, u64, u64, u32, u32, vp],
         "euler_dist_scatter": [vp, vp, vp, u64, u64, u32, u32, vp, vp],
         "euler_dist_scatter_segments": [vp, vp, vp, u64, u64, u32, u32, vp, u64, vp],
@@ -458,6 +462,38 @@ class Context:
         out = np.zeros(nb.value, np.uint8)
         cap = C.c_uint64(nb.value)
         self.check(self.lib.euler_pipeline_contigs(self.h, _p(out), C.byref(cap), C.byref(nc)))
+        return out.tobytes().decode("ascii").split("\n")[:-1]
+
+    # ------------------------------------------------------------------ FASTA / FASTQ ingestion on device
+    def ingest(self, data, fmt=0):
+        """Parse raw FASTA (fmt=1) / FASTQ (fmt=2) bytes on the GPU (0 = auto); returns (nreads, nbases).
+        The reads stay resident for run_ingested / unitigs_ingested / ingest_download."""
+        arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else _arr(data, np.uint8)
+        nr, nb = C.c_uint64(0), C.c_uint64(0)
+        self.check(self.lib.euler_ingest(self.h, _p(arr) if arr.size else None, arr.size, int(fmt), C.byref(nr), C.byref(nb)))
+        self._ingested = (nr.value, nb.value)
+        return nr.value, nb.value
+
+    def ingest_download(self):
+        nr, nb = self._ingested
+        buf = np.zeros(nb, np.uint8)
+        off = np.zeros(nr + 1, np.uint64)
+        self.check(self.lib.euler_ingest_download(self.h, _p(buf) if nb else None, _p(off)))
+        return buf, off
+
+    def run_ingested(self, l, flags=0, distinct_hint=0):
+        st = Stats()
+        self.check(self.lib.euler_pipeline_run_ingested(self.h, int(l), int(flags), int(distinct_hint), C.byref(st)))
+        return st
+
+    def unitigs_ingested(self, K, limit=1):
+        nb, nc = C.c_uint64(0), C.c_uint64(0)
+        self.check(self.lib.euler_unitigs_ingested(self.h, int(K), int(limit), None, C.byref(nb), C.byref(nc)))
+        if not nb.value:
+            return []
+        out = np.zeros(nb.value, np.uint8)
+        cap = C.c_uint64(nb.value)
+        self.check(self.lib.euler_unitigs_ingested(self.h, int(K), int(limit), _p(out), C.byref(cap), C.byref(nc)))
         return out.tobytes().decode("ascii").split("\n")[:-1]
 
     # ------------------------------------------------------------------ k-mer-space partition

@@ -147,22 +147,15 @@ int euler_count_mers(euler_ctx *ctx, const char *buf, const uint64_t *read_off, 
     FINISH(ctx);
 }
 
-int euler_unitigs(euler_ctx *ctx, const char *buf, const uint64_t *read_off, uint64_t nreads, uint32_t K, uint32_t limit,
-                  char *out, uint64_t *out_bytes, uint64_t *ncontigs)
+static int unitigs_core(euler_ctx *ctx, const void *d_buf, const u64 *d_off, u64 nreads, u64 B, uint32_t K, uint32_t limit,
+                        char *out, uint64_t *out_bytes, uint64_t *ncontigs)
 {
-    ENTER(ctx);
-    if (!read_off || !out_bytes || !ncontigs) return euler_fail(ctx, EULER_ERR_ARG, "null argument");
-    if (K < 2 || K > 32) return euler_fail(ctx, EULER_ERR_ARG, "K %u out of range [2,32]", K);
     const u64 cap_out = *out_bytes;
     *out_bytes = 0; *ncontigs = 0;
-    const u64 B = read_off[nreads];
     if (!B) return EULER_OK;
-    DevTmp<unsigned char> d_buf(ctx, B + 16);
-    DevTmp<u64> d_off(ctx, nreads + 1), d_stats(ctx, 8);
+    DevTmp<u64> d_stats(ctx, 8);
     DevTmp<u32> d_bits(ctx, B / 32 + 2);
     TMP_CHECK(ctx, d_bits); TMP_CHECK(ctx, d_stats);
-    EULER_TRY(upload(ctx, d_buf, (const unsigned char *)buf, B));
-    EULER_TRY(upload(ctx, d_off, (const u64 *)read_off, nreads + 1));
     EULER_TRY(enc_mark_starts(ctx, d_off, nreads, B, d_bits));
     const u64 cap = euler_hash_capacity(B);
     DevTmp<u64> tk(ctx, cap);
@@ -182,7 +175,33 @@ int euler_unitigs(euler_ctx *ctx, const char *buf, const uint64_t *read_off, uin
         if (cap_out < bytes) return euler_fail(ctx, EULER_ERR_ARG, "output capacity too small");
         EULER_TRY(download(ctx, out, (const char *)d_text, bytes));
     }
-    FINISH(ctx);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return EULER_OK;
+}
+
+int euler_unitigs(euler_ctx *ctx, const char *buf, const uint64_t *read_off, uint64_t nreads, uint32_t K, uint32_t limit,
+                  char *out, uint64_t *out_bytes, uint64_t *ncontigs)
+{
+    ENTER(ctx);
+    if (!read_off || !out_bytes || !ncontigs) return euler_fail(ctx, EULER_ERR_ARG, "null argument");
+    if (K < 2 || K > 32) return euler_fail(ctx, EULER_ERR_ARG, "K %u out of range [2,32]", K);
+    const u64 B = read_off[nreads];
+    DevTmp<unsigned char> d_buf(ctx, B + 16);
+    DevTmp<u64> d_off(ctx, nreads + 1);
+    EULER_TRY(upload(ctx, d_buf, (const unsigned char *)buf, B));
+    EULER_TRY(upload(ctx, d_off, (const u64 *)read_off, nreads + 1));
+    return unitigs_core(ctx, d_buf, d_off, nreads, B, K, limit, out, out_bytes, ncontigs);
+}
+
+// unitigs of the reads left on the device by euler_ingest
+int euler_unitigs_ingested(euler_ctx *ctx, uint32_t K, uint32_t limit, char *out, uint64_t *out_bytes, uint64_t *ncontigs)
+{
+    ENTER(ctx);
+    if (!out_bytes || !ncontigs) return euler_fail(ctx, EULER_ERR_ARG, "null argument");
+    if (K < 2 || K > 32) return euler_fail(ctx, EULER_ERR_ARG, "K %u out of range [2,32]", K);
+    const void *d_buf; const u64 *d_off; u64 nr, nb;
+    EULER_TRY(pipeline_resident_reads(ctx, &d_buf, &d_off, &nr, &nb));
+    return unitigs_core(ctx, d_buf, d_off, nr, nb, K, limit, out, out_bytes, ncontigs);
 }
 
 int euler_hash_build(euler_ctx *ctx, const uint64_t *keys, const uint32_t *values, uint64_t n, uint64_t capacity,

@@ -125,3 +125,9 @@ int enc_count_packed(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *
                      u64 *side_keys, u32 *side_cnt, u64 side_cap, u64 *d_stats);
 int enc_unpack(euler_ctx *ctx, const u64 *tab, u32 b, const u64 *side_keys, const u32 *side_cnt, u64 side_cap, u64 *d_side_used,
                u64 *keys, u32 *cnt);
+
+// ---- ingest.cu (FASTA / FASTQ parsing on device)
+int ingest_parse(euler_ctx *ctx, const unsigned char *d_file, u64 n, int fastq, unsigned char *d_reads, u64 *d_off, u64 off_cap,
+                 u64 *nreads, u64 *nbases);
+// reads left resident by euler_ingest (pipeline.cu)
+int pipeline_resident_reads(euler_ctx *ctx, const void **d_buf, const u64 **d_off, u64 *nreads, u64 *n_bases);

@@ -82,6 +82,7 @@ struct Pipeline {
     u64 learned_bases = 0, learned_lc = 0, learned_vc = 0;
     u64 text_bytes = 0, text_n = 0;
     bool text_valid = false;  // contig text of the current graph is resident
+    bool ingested = false;    // in_buf / in_off hold reads parsed on device by euler_ingest
     void *recv_buf = nullptr;  // peer-visible receive buffer of the partitioned path (plain cudaMalloc)
     u64 recv_cap = 0;
     euler_stats st = {};
@@ -324,6 +325,7 @@ int euler_pipeline_run_host(euler_ctx *ctx, const char *buf, const uint64_t *rea
     Pipeline *P = get_pipe(ctx);
     const u64 B = read_off[nreads];
     if (B && !buf) return euler_fail(ctx, EULER_ERR_ARG, "null buf");
+    P->ingested = false;
     EULER_TRY(P->in_buf.reserve(ctx, B + 16));
     EULER_TRY(P->in_off.reserve(ctx, nreads + 1));
     if (B) CUDA_TRY(ctx, cudaMemcpyAsync(P->in_buf.ptr(), buf, B, cudaMemcpyHostToDevice, ctx->stream));
@@ -444,6 +446,73 @@ int euler_pipeline_contigs(euler_ctx *ctx, char *out, uint64_t *out_bytes, uint6
     }
     *out_bytes = bytes; *ncontigs = nc;
     return EULER_OK;
+}
+
+// ---- FASTA / FASTQ ingestion on device ----------------------------------------------
+int euler_ingest(euler_ctx *ctx, const char *file_bytes, uint64_t nbytes, int format, uint64_t *nreads, uint64_t *nbases)
+{
+    if (!ctx || !nreads || !nbases) return EULER_ERR_ARG;
+    if (nbytes && !file_bytes) return euler_fail(ctx, EULER_ERR_ARG, "null file buffer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Pipeline *P = get_pipe(ctx);
+    P->ingested = false;
+    if (format == 0) {  // '>' opens a FASTA record, '@' a FASTQ record (eulercuda.py:469-476 goes by extension)
+        format = 1;
+        for (u64 i = 0; i < nbytes; i++) {
+            const char c = file_bytes[i];
+            if (c == '\n' || c == '\r' || c == ' ' || c == '\t') continue;
+            format = (c == '@') ? 2 : 1;
+            break;
+        }
+    }
+    if (format != 1 && format != 2) return euler_fail(ctx, EULER_ERR_ARG, "format must be 0 (auto), 1 (FASTA) or 2 (FASTQ)");
+    u64 nlines_ub = 1;
+    for (u64 i = 0; i < nbytes; i++) nlines_ub += file_bytes[i] == '\n';
+    DevTmp<unsigned char> d_file(ctx, nbytes + 16);
+    TMP_CHECK(ctx, d_file);
+    if (nbytes) CUDA_TRY(ctx, cudaMemcpyAsync(d_file.get(), file_bytes, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    EULER_TRY(P->in_buf.reserve(ctx, nbytes + 16));
+    EULER_TRY(P->in_off.reserve(ctx, nlines_ub + 2));
+    u64 nr = 0, nb = 0;
+    EULER_TRY(ingest_parse(ctx, d_file, nbytes, format == 2, P->in_buf.ptr(), P->in_off.ptr(), nlines_ub + 2, &nr, &nb));
+    P->d_buf = P->in_buf.ptr(); P->d_off = P->in_off.ptr(); P->nreads = nr; P->n_bases = nb;
+    P->ingested = true;
+    *nreads = nr; *nbases = nb;
+    return EULER_OK;
+}
+
+}  // extern "C"
+
+int pipeline_resident_reads(euler_ctx *ctx, const void **d_buf, const u64 **d_off, u64 *nreads, u64 *n_bases)
+{
+    Pipeline *P = ctx->pipe;
+    if (!P || !P->ingested) return euler_fail(ctx, EULER_ERR_STATE, "no reads resident: call euler_ingest first");
+    *d_buf = P->in_buf.ptr(); *d_off = P->in_off.ptr(); *nreads = P->nreads; *n_bases = P->n_bases;
+    return EULER_OK;
+}
+
+extern "C" {
+
+int euler_ingest_download(euler_ctx *ctx, char *buf, uint64_t *read_off)
+{
+    if (!ctx) return EULER_ERR_ARG;
+    const void *d_buf; const u64 *d_off; u64 nr, nb;
+    EULER_TRY(pipeline_resident_reads(ctx, &d_buf, &d_off, &nr, &nb));
+    if (buf && nb) CUDA_TRY(ctx, cudaMemcpyAsync(buf, d_buf, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (read_off) CUDA_TRY(ctx, cudaMemcpyAsync(read_off, d_off, (nr + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return EULER_OK;
+}
+
+int euler_pipeline_run_ingested(euler_ctx *ctx, uint32_t l, uint32_t flags, uint64_t distinct_hint, euler_stats *stats)
+{
+    if (!ctx) return EULER_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const void *d_buf; const u64 *d_off; u64 nr, nb;
+    EULER_TRY(pipeline_resident_reads(ctx, &d_buf, &d_off, &nr, &nb));
+    Pipeline *P = ctx->pipe;
+    P->d_buf = d_buf; P->d_off = d_off; P->nreads = nr; P->n_bases = nb;
+    return pipeline_run(ctx, P, l, flags, distinct_hint, stats);
 }
 
 // ---- multi-GPU: partition, (all-to-all by the caller), build ------------------------------------

@@ -158,13 +158,33 @@ def assemble2(lmerLength, buffer='', readLength=0, readCount=0, infile='', outfi
     Euler tour -> partial contigs."""
     logger = logging.getLogger(__name__)
     if infile != '':
+        # the file is parsed on the device (csrc/ingest.cu): the reads never exist on the host
         extension = infile.split('.')[-1]
         if extension in ['fa', 'fasta', 'fsa']:
-            buffer = read_fasta(infile)
+            fmt = 1
         elif extension in ['fq', 'fastq']:
-            buffer = read_fastq(infile)
+            fmt = 2
         else:
             raise ValueError("unknown read file extension: %s" % infile)
+        with open(infile, 'rb') as handle:
+            data = handle.read()
+        ctx = _native.default_context()
+        nreads, nbases = ctx.ingest(data, fmt)
+        logger.info("Got %s reads." % nreads)
+        contigs = []
+        if nbases > 0:
+            if mode == 'unitig':
+                contigs = ctx.unitigs_ingested(int(lmerLength), int(limit))
+            elif mode == 'euler':
+                ctx.run_ingested(int(lmerLength), _native.RUN_CANONICAL_IDS | _native.RUN_EXPAND_EDGES)
+                contigs = ctx.pipeline_contigs()
+            else:
+                raise ValueError("mode must be 'unitig' or 'euler'")
+        if outfile:
+            with open(outfile, 'w') as ofile:
+                for i, c in enumerate(contigs):
+                    ofile.write('>%u\n%s\n' % (i, c))
+        return contigs
     reads = [r.decode('ascii') if isinstance(r, (bytes, bytearray)) else str(r) for r in buffer]
     logger.info("Got %s reads." % len(reads))
     data = b''.join(r.encode('ascii') for r in reads)

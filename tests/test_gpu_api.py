@@ -306,3 +306,35 @@ def test_full_size_config2_properties_and_parity(ctx):
     ov = np.argsort(ev["vid"], kind="stable")
     assert np.array_equal(ev["vid"][ov], g.vk_lo)
     assert np.array_equal(ev["lcount"][ov], g.ev["lcount"]) and np.array_equal(ev["ecount"][ov], g.ev["ecount"])
+
+
+def test_device_ingestion_matches_the_reference_readers(ctx, tmp_path, g200_reads):
+    """FASTA / FASTQ parsed on the GPU == eulercuda.read_fasta / read_fastq (host restatements of the
+    reference readers), including blank lines, CRLF, a missing final newline and multi-line records."""
+    import eulercuda.eulercuda as ec
+    cases = {
+        "g200.fa": "".join(">r%d\n%s\n" % (i, r) for i, r in enumerate(g200_reads)),
+        "odd.fa": ">a desc\nACGT\nTTGA\n\n>b\nCC\r\n>c\nGGNNA",          # multi-line, blank line, CRLF, no final newline
+        "only_headers.fa": ">x\n>y\n",
+        "r.fq": "".join("@q%d\n%s\n+\n%s\n" % (i, r, "I" * len(r)) for i, r in enumerate(g200_reads[:40])),
+        "tail.fastq": "@a\nACGTACGT\n+\nIIIIIIII\n@b\nTTTT\n+\nIIII",
+    }
+    for name, text in cases.items():
+        p = tmp_path / name
+        p.write_bytes(text.encode("ascii"))
+        fq = name.endswith(("fq", "fastq"))
+        want = ec.read_fastq(str(p)) if fq else ec.read_fasta(str(p))
+        nr, nb = ctx.ingest(text.encode("ascii"), 2 if fq else 1)
+        buf, off = ctx.ingest_download()
+        got = [buf[int(off[i]):int(off[i + 1])].tobytes().decode() for i in range(nr)]
+        assert got == want, name
+        assert ctx.ingest(text.encode("ascii"), 0)[0] == nr      # auto-detection
+    # whole path from a file: ingestion on device -> unitigs / Euler contigs
+    fa = tmp_path / "g200.fa"
+    fx = _load("g200.json")
+    gold = {(c["k"], c["limit"]): c for c in fx["cases"]}
+    c = ec.assemble2(11, infile=str(fa))
+    assert oracle.canonical_contigs(c) == oracle.canonical_contigs(gold[(11, 1)]["contigs"])
+    b, o = oracle.pack_reads(g200_reads)
+    ref, _ = oracle.euler_contigs(b, o, 12)
+    assert ec.assemble2(12, infile=str(fa), mode="euler") == ref
