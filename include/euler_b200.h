@@ -172,7 +172,10 @@ typedef struct {
 #define EULER_RUN_CANONICAL_IDS 2u  /* ids = rank in ascending key order (sort), else slot order */
 
 /* reads already resident in device memory (d_buf: n_bases ASCII bytes, 16-byte aligned;
- * d_read_off: nreads+1 u64).  distinct_hint = expected distinct canonical l-mers (0 = estimate). */
+ * d_read_off: nreads+1 u64).  distinct_hint = expected distinct canonical l-mers (0 = estimate).
+ * l in [2,64].  The reference stops at 64-bit keys (KEY_T, pyencode.py:22-33: l <= 32); for
+ * l in 33..64 (k up to 63, BASELINE.json configs[4]) keys are two words: the low words are the
+ * usual artefacts, the high words EULER_ART_*_KEYS_HI, and contigs come out the same way. */
 int euler_pipeline_run_dev(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads,
                            uint64_t n_bases, uint32_t l, uint32_t flags, uint64_t distinct_hint,
                            euler_stats *stats);
@@ -195,7 +198,9 @@ enum {
     EULER_ART_EDGE_V2 = 10,    /* u32[U_l] suffix vertex */
     EULER_ART_EE = 11,         /* euler_edge[E]  (EXPAND_EDGES) */
     EULER_ART_LEV = 12,        /* u32[E] l[]      (EXPAND_EDGES) */
-    EULER_ART_ENT = 13         /* u32[E] e[]      (EXPAND_EDGES) */
+    EULER_ART_ENT = 13,        /* u32[E] e[]      (EXPAND_EDGES) */
+    EULER_ART_LMER_KEYS_HI = 14, /* u64[U_l] bits 64..127 of the l-mer keys; only after a run with l > 32 */
+    EULER_ART_KMER_KEYS_HI = 15  /* u64[U_k] bits 64..127 of the vertex keys; euler_vertex.vid holds the low word */
 };
 int euler_pipeline_artifact_bytes(euler_ctx *ctx, int which, uint64_t *bytes);
 int euler_pipeline_download(euler_ctx *ctx, int which, void *host_dst, uint64_t cap_bytes);

@@ -23,13 +23,14 @@ RUN_EXPAND_EDGES = 1
 RUN_CANONICAL_IDS = 2
 
 (ART_LMER_KEYS, ART_LMER_VALUES, ART_LMER_OFFSETS, ART_KMER_KEYS, ART_LCOUNT, ART_ECOUNT, ART_LSTART,
- ART_ESTART, ART_EV, ART_EDGE_V1, ART_EDGE_V2, ART_EE, ART_LEV, ART_ENT) = range(14)
+ ART_ESTART, ART_EV, ART_EDGE_V1, ART_EDGE_V2, ART_EE, ART_LEV, ART_ENT, ART_LMER_KEYS_HI, ART_KMER_KEYS_HI) = range(16)
 
 _ART_DTYPE = {
     ART_LMER_KEYS: np.uint64, ART_LMER_VALUES: np.uint32, ART_LMER_OFFSETS: np.uint32,
     ART_KMER_KEYS: np.uint64, ART_LCOUNT: np.uint32, ART_ECOUNT: np.uint32, ART_LSTART: np.uint32,
     ART_ESTART: np.uint32, ART_EV: EV_DTYPE, ART_EDGE_V1: np.uint32, ART_EDGE_V2: np.uint32,
     ART_EE: EE_DTYPE, ART_LEV: np.uint32, ART_ENT: np.uint32,
+    ART_LMER_KEYS_HI: np.uint64, ART_KMER_KEYS_HI: np.uint64,
 }
 
 

@@ -7,7 +7,7 @@
 // every cycle, entered at its smallest node id.  A `Model` supplies what a node spells:
 //   n()                       number of nodes
 //   succ(i)                   successor node or >= n
-//   head_key(i)               k-mer (2-bit packed) that opens a contig headed by node i
+//   head_key(i)               k-mer (2-bit packed) that opens a contig headed by node i (head_key_hi: bits 64.. when k > 32)
 //   base(i)                   character appended by node i
 //   emit(D, i)                whether the component (label array D) of head i is written at all
 //   HEAD_APPENDS              1: the head node also appends base(i) (Euler edges)
@@ -121,8 +121,12 @@ __global__ void __launch_bounds__(CH_TB) ch_write_kernel(M m, const u32 *__restr
     const u64 o = off_by_ord[ord];
     if (M::HEAD_APPENDS || t != head) out[o + k + dist - (1 - M::HEAD_APPENDS)] = m.base(t);
     if (t == head) {
-        u64 x = m.head_key(t);  // getString eulercuda.py:315-321
-        for (u32 i = 0; i < k; i++) { out[o + k - 1 - i] = "ACGT"[x & 3]; x >>= 2; }
+        u64 x = m.head_key(t), xh = m.head_key_hi(t);  // getString eulercuda.py:315-321
+        for (u32 i = 0; i < k; i++) {
+            out[o + k - 1 - i] = "ACGT"[x & 3];
+            x = (x >> 2) | (xh << 62);
+            xh >>= 2;
+        }
         out[o + len_by_ord[ord] - 1] = '\n';
     }
 }

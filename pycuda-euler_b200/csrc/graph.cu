@@ -269,15 +269,17 @@ __global__ void __launch_bounds__(GB) setup_edges_kernel(const u64 *__restrict__
                                                           PlainTable pt, const u32 *__restrict__ lstart,
                                                           const u32 *__restrict__ estart, u32 ecount,
                                                           euler_edge *__restrict__ ee, u32 *__restrict__ lev,
-                                                          u32 *__restrict__ ent)
+                                                          u32 *__restrict__ ent, const unsigned char *__restrict__ tf)
 {
+    // tf != NULL (128-bit keys, wide.cu): first / last base codes come precomputed, lkeys is not read
     const int lane = threadIdx.x & 31;
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 i = warp * 32 + lane;
     u32 m = 0, off = 0, pid = EULER_NO_ID, sid = EULER_NO_ID, lo = 0, eo = 0;
     if (i < nl) {
-        const u64 x = lkeys[i];
         const u32 k = l - 1;
+        const u64 x = tf ? 0ull : lkeys[i];
+        const u32 to = tf ? (tf[i] & 3u) : (u32)(x & 3), from = tf ? (tf[i] >> 2) : (u32)((x >> (2 * k)) & 3);
         m = lvals[i];
         off = loffs[i];
         if (PLAIN) {
@@ -289,8 +291,8 @@ __global__ void __launch_bounds__(GB) setup_edges_kernel(const u64 *__restrict__
         }
         if (pid == EULER_NO_ID || sid == EULER_NO_ID) m = 0;
         else {
-            lo = lstart[((u64)pid << 2) + (u32)(x & 3)];
-            eo = estart[((u64)sid << 2) + (u32)((x >> (2 * k)) & 3)];
+            lo = lstart[((u64)pid << 2) + to];
+            eo = estart[((u64)sid << 2) + from];
         }
     }
     for (int src = 0; src < 32; src++) {
@@ -315,12 +317,12 @@ __global__ void __launch_bounds__(GB) setup_edges_kernel(const u64 *__restrict__
 
 int graph_setup_edges(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, const u32 *loffs, u64 nl, u32 l,
                       const u32 *ev1, const u32 *ev2, const u32 *lstart, const u32 *estart, u32 ecount,
-                      euler_edge *ee, u32 *lev, u32 *ent)
+                      euler_edge *ee, u32 *lev, u32 *ent, const unsigned char *tf)
 {
     if (!nl) return EULER_OK;
     PlainTable none = {nullptr, nullptr, 0};
     setup_edges_kernel<false><<<grid_for(nl, GB), GB, 0, ctx->stream>>>(lkeys, lvals, loffs, nl, l, ev1, ev2, none, lstart,
-                                                                        estart, ecount, ee, lev, ent);
+                                                                        estart, ecount, ee, lev, ent, tf);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
@@ -331,7 +333,7 @@ int graph_setup_edges_plain(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, 
 {
     if (!nl) return EULER_OK;
     setup_edges_kernel<true><<<grid_for(nl, GB), GB, 0, ctx->stream>>>(lkeys, lvals, loffs, nl, l, nullptr, nullptr, pt,
-                                                                       lstart, estart, ecount, ee, lev, ent);
+                                                                       lstart, estart, ecount, ee, lev, ent, nullptr);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }

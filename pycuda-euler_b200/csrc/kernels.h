@@ -57,7 +57,7 @@ int graph_setup_vertices_plain(euler_ctx *ctx, const u64 *kmer_keys, u64 nk, con
 // D6 setupEdges (expanded): ee / l[] / e[]
 int graph_setup_edges(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, const u32 *loffs, u64 nl, u32 l,
                       const u32 *ev1, const u32 *ev2, const u32 *lstart, const u32 *estart, u32 ecount,
-                      euler_edge *ee, u32 *lev, u32 *ent);
+                      euler_edge *ee, u32 *lev, u32 *ent, const unsigned char *tf = nullptr);
 int graph_setup_edges_plain(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, const u32 *loffs, u64 nl, u32 l,
                             const PlainTable &pt, const u32 *lstart, const u32 *estart, u32 ecount, euler_edge *ee,
                             u32 *lev, u32 *ent);
@@ -86,8 +86,9 @@ int tour_swipe(euler_ctx *ctx, const euler_vertex *ev, const u32 *ent, u32 vcoun
                u32 ecount);
 int tour_contig_starts(euler_ctx *ctx, const euler_edge *ee, u32 ecount, u32 *start);
 // contig emission; *d_out ctx-owned device text, '\n'-terminated contigs
+// vk_hi: high words of the vertex keys when k > 32 (wide.cu), else NULL
 int tour_emit_contigs(euler_ctx *ctx, const euler_vertex *ev, u32 vcount, const euler_edge *ee, u32 ecount, u32 l,
-                      char **d_out, u64 *out_bytes, u64 *ncontigs);
+                      char **d_out, u64 *out_bytes, u64 *ncontigs, const u64 *vk_hi = nullptr);
 
 // ---- synth.cu
 int synth_reads(euler_ctx *ctx, u64 G, u32 L, u32 err_ppm, u64 first, u64 nreads, void *d_out);

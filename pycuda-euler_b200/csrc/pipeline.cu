@@ -6,6 +6,7 @@
 #include "scan.cuh"
 #include "sort.cuh"
 #include "tmp.cuh"
+#include "wide.cuh"
 #include <stdlib.h>
 
 struct LtTable {
@@ -85,6 +86,12 @@ struct Pipeline {
     bool ingested = false;    // in_buf / in_off hold reads parsed on device by euler_ingest
     void *recv_buf = nullptr;  // peer-visible receive buffer of the partitioned path (plain cudaMalloc)
     u64 recv_cap = 0;
+    // 128-bit keys (l in 33..64, wide.cu): tables, high key words, first/last base codes per l-mer
+    DevArr<K128> wlt_keys, wvt_keys;
+    DevArr<u32> wlt_cnt;
+    DevArr<u64> lkeys_hi, vkeys_hi;
+    DevArr<unsigned char> tf;
+    bool wide = false;
     euler_stats st = {};
 };
 
@@ -98,6 +105,7 @@ void pipeline_destroy(Pipeline *p)
     p->lcount.free(); p->ecount.free(); p->lstart.free(); p->estart.free(); p->ev.free(); p->ee.free();
     if (p->recv_buf) cudaFree(p->recv_buf);
     p->lev.free(); p->ent.free(); p->sort_k.free(); p->sort_v.free(); p->sort_hist.free();
+    p->wlt_keys.free(); p->wvt_keys.free(); p->wlt_cnt.free(); p->lkeys_hi.free(); p->vkeys_hi.free(); p->tf.free();
     delete p;
 }
 
@@ -144,9 +152,108 @@ static bool use_packed_table()
 }
 static u64 cap_for(u64 n) { return round_up((u64)((double)(n < 64 ? 64 : n) / table_load()) + 1, 1024); }
 
+// l in 33..64: the same stages over two-word keys (wide.cu).  Correctness-first: one thread per read,
+// explicit both-strand l-mer arrays, ids in slot order or ascending (hi, lo) order.
+static int pipeline_run_wide(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 distinct_hint, euler_stats *stats)
+{
+    P->l = l; P->flags = flags; P->have_graph = false; P->expanded = false; P->text_valid = false; P->wide = true;
+    const u32 k = l - 1;
+    const u64 B = P->n_bases;
+    cudaStream_t s = ctx->stream;
+    memset(&P->st, 0, sizeof(P->st));
+    P->st.n_reads = P->nreads; P->st.n_bases = B;
+    EULER_TRY(P->stats.reserve(ctx, 16));
+    u64 est_l, est_v;
+    if (distinct_hint) { est_l = distinct_hint; est_v = distinct_hint + distinct_hint / 16; }
+    else if (P->learned_bases == B && P->learned_lc) { est_l = P->learned_lc + P->learned_lc / 32; est_v = P->learned_vc + P->learned_vc / 32; }
+    else { est_l = B ? B : 1; est_v = est_l; }
+    u64 lt_cap = cap_for(est_l), vt_cap = cap_for(est_v);
+    u64 h[8] = {0};
+    u32 retries = 0, launches = 0;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    while (true) {
+        P->lt_cap = lt_cap; P->vt_cap = vt_cap;
+        EULER_TRY(P->wlt_keys.reserve(ctx, lt_cap)); EULER_TRY(P->wlt_cnt.reserve(ctx, lt_cap)); EULER_TRY(P->lt_base.reserve(ctx, lt_cap));
+        EULER_TRY(P->wvt_keys.reserve(ctx, vt_cap)); EULER_TRY(P->vt_id0.reserve(ctx, vt_cap));
+        CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 16 * sizeof(u64), s));
+        EULER_TRY(wide_table_clear(ctx, P->wlt_keys.ptr(), P->wlt_cnt.ptr(), lt_cap));
+        EULER_TRY(wide_table_clear(ctx, P->wvt_keys.ptr(), nullptr, vt_cap));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
+        EULER_TRY(wide_count(ctx, P->d_buf, P->d_off, P->nreads, l, P->wlt_keys.ptr(), P->wlt_cnt.ptr(), lt_cap, P->stats.ptr()));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+        EULER_TRY(wide_slot_scan(ctx, P->wlt_keys.ptr(), lt_cap, l, P->lt_base.ptr(), P->stats.ptr() + 3));
+        EULER_TRY(wide_vertex_insert(ctx, P->wlt_keys.ptr(), lt_cap, l, P->wvt_keys.ptr(), vt_cap, P->stats.ptr() + 2));
+        EULER_TRY(wide_slot_scan(ctx, P->wvt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(), P->stats.ptr() + 4));
+        launches += 4;
+        EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 6));
+        if ((h[2] & 3) == 0) break;
+        if (++retries > 10) return euler_fail(ctx, EULER_ERR_OVERFLOW, "hash table overflow after %u regrows", retries);
+        if (h[2] & 1) lt_cap *= 2;
+        if (h[2] & 2) vt_cap *= 2;
+    }
+    const u64 N_l = h[0], N_k = h[1], U_l = h[3], V = h[4];
+    const u64 E = 2 * N_l;
+    P->U_l = U_l; P->V = V; P->E = E;
+    if (V >= 0x3fffffffull || N_l >= 0x7fffffffull)
+        return euler_fail(ctx, EULER_ERR_RANGE, "graph exceeds u32 ids (U_l=%llu V=%llu E=%llu)", U_l, V, E);
+    EULER_TRY(P->lkeys.reserve(ctx, U_l)); EULER_TRY(P->lkeys_hi.reserve(ctx, U_l)); EULER_TRY(P->lvals.reserve(ctx, U_l));
+    EULER_TRY(P->loffs.reserve(ctx, U_l)); EULER_TRY(P->ev1.reserve(ctx, U_l)); EULER_TRY(P->ev2.reserve(ctx, U_l));
+    EULER_TRY(P->tf.reserve(ctx, U_l + 16));
+    EULER_TRY(P->vkeys.reserve(ctx, V)); EULER_TRY(P->vkeys_hi.reserve(ctx, V));
+    EULER_TRY(P->lcount.reserve(ctx, 4 * V + 4)); EULER_TRY(P->ecount.reserve(ctx, 4 * V + 4));
+    EULER_TRY(P->lstart.reserve(ctx, 4 * V + 4)); EULER_TRY(P->estart.reserve(ctx, 4 * V + 4));
+    EULER_TRY(P->ev.reserve(ctx, V));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->lcount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+    EULER_TRY(wide_compact_vertices(ctx, P->wvt_keys.ptr(), P->vt_id0.ptr(), vt_cap, k, P->vkeys.ptr(), P->vkeys_hi.ptr()));
+    EULER_TRY(wide_compact_lmers(ctx, P->wlt_keys.ptr(), P->wlt_cnt.ptr(), P->lt_base.ptr(), lt_cap, l, P->lkeys.ptr(),
+                                 P->lkeys_hi.ptr(), P->lvals.ptr()));
+    const u32 *id1 = nullptr;
+    if (flags & EULER_RUN_CANONICAL_IDS) {
+        EULER_TRY(P->vt_id1.reserve(ctx, vt_cap));
+        EULER_TRY(wide_sort(ctx, P->lkeys.ptr(), P->lkeys_hi.ptr(), P->lvals.ptr(), U_l, 2 * (int)l));
+        EULER_TRY(wide_sort(ctx, P->vkeys.ptr(), P->vkeys_hi.ptr(), nullptr, V, 2 * (int)k));
+        EULER_TRY(wide_assign_sorted_ids(ctx, P->vkeys.ptr(), P->vkeys_hi.ptr(), V, P->wvt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(),
+                                         P->vt_id1.ptr()));
+        id1 = P->vt_id1.ptr();
+        launches += 3 * ((2 * l + 7) / 8) + 3 * ((2 * k + 7) / 8) + 12;
+    }
+    EULER_TRY(wide_degree_slots(ctx, P->lkeys.ptr(), P->lkeys_hi.ptr(), P->lvals.ptr(), U_l, l, P->wvt_keys.ptr(), P->vt_id0.ptr(), id1,
+                                vt_cap, P->lcount.ptr(), P->ecount.ptr(), P->ev1.ptr(), P->ev2.ptr(), P->tf.ptr()));
+    EULER_TRY(scan_exclusive(ctx, ScanInU32{P->lvals.ptr()}, U_l, P->loffs.ptr(), (u64 *)nullptr));
+    EULER_TRY(graph_vertices_fused(ctx, P->lcount.ptr(), P->ecount.ptr(), P->vkeys.ptr(), V, P->lstart.ptr(), P->estart.ptr(),
+                                   P->ev.ptr()));
+    launches += 5;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+    if (flags & EULER_RUN_EXPAND_EDGES) {
+        launches += 1;
+        EULER_TRY(P->ee.reserve(ctx, E)); EULER_TRY(P->lev.reserve(ctx, E)); EULER_TRY(P->ent.reserve(ctx, E));
+        EULER_TRY(graph_setup_edges(ctx, nullptr, P->lvals.ptr(), P->loffs.ptr(), U_l, l, P->ev1.ptr(), P->ev2.ptr(), P->lstart.ptr(),
+                                    P->estart.ptr(), (u32)E, P->ee.ptr(), P->lev.ptr(), P->ent.ptr(), P->tf.ptr()));
+        P->expanded = true;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    P->have_graph = true;
+    P->learned_bases = B;
+    P->learned_lc = (U_l + 1) / 2 + 16; P->learned_vc = (V + 1) / 2 + 16;
+    euler_stats &st = P->st;
+    st.n_kmer_windows = N_k; st.n_lmer_windows = N_l; st.distinct_lmers = U_l; st.distinct_kmers = V; st.edge_count = E;
+    st.lmer_table_capacity = lt_cap; st.kmer_table_capacity = vt_cap; st.retries = retries;
+    cudaEventElapsedTime(&st.ms_count, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&st.ms_graph, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[2]);
+    cudaEventElapsedTime(&st.ms_count_kernel, ctx->ev[4], ctx->ev[1]);
+    st.kernel_launches = launches;
+    if (stats) *stats = st;
+    return EULER_OK;
+}
+
 static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 distinct_hint, euler_stats *stats)
 {
-    if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
+    if (l < 2 || l > 64) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,64]", l);
+    if (l > 32) return pipeline_run_wide(ctx, P, l, flags, distinct_hint, stats);
+    P->wide = false;
     P->l = l; P->flags = flags; P->have_graph = false; P->expanded = false; P->text_valid = false;
     const u32 k = l - 1;
     const u64 B = P->n_bases;
@@ -344,6 +451,12 @@ static int artifact(euler_ctx *ctx, int which, void **p, u64 *bytes)
     case EULER_ART_LMER_VALUES: *p = P->lvals.ptr(); *bytes = U * 4; break;
     case EULER_ART_LMER_OFFSETS: *p = P->loffs.ptr(); *bytes = U * 4; break;
     case EULER_ART_KMER_KEYS: *p = P->vkeys.ptr(); *bytes = V * 8; break;
+    case EULER_ART_LMER_KEYS_HI:
+    case EULER_ART_KMER_KEYS_HI:
+        if (!P->wide) return euler_fail(ctx, EULER_ERR_STATE, "high key words exist only for l > 32");
+        if (which == EULER_ART_LMER_KEYS_HI) { *p = P->lkeys_hi.ptr(); *bytes = U * 8; }
+        else { *p = P->vkeys_hi.ptr(); *bytes = V * 8; }
+        break;
     case EULER_ART_LCOUNT: *p = P->lcount.ptr(); *bytes = 4 * V * 4; break;
     case EULER_ART_ECOUNT: *p = P->ecount.ptr(); *bytes = 4 * V * 4; break;
     case EULER_ART_LSTART: *p = P->lstart.ptr(); *bytes = 4 * V * 4; break;
@@ -431,7 +544,8 @@ int euler_pipeline_contigs(euler_ctx *ctx, char *out, uint64_t *out_bytes, uint6
         }
         char *d_text = nullptr;
         u64 bytes = 0, nc = 0;
-        EULER_TRY(tour_emit_contigs(ctx, P->ev.ptr(), V, P->ee.ptr(), E, P->l, &d_text, &bytes, &nc));
+        EULER_TRY(tour_emit_contigs(ctx, P->ev.ptr(), V, P->ee.ptr(), E, P->l, &d_text, &bytes, &nc,
+                                    P->wide ? P->vkeys_hi.ptr() : nullptr));
         P->text_bytes = bytes; P->text_n = nc; P->text_valid = true;
         if (!out) {
             *out_bytes = bytes; *ncontigs = nc;

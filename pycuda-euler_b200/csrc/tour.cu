@@ -437,17 +437,19 @@ struct EulerChainModel {
     const euler_vertex *ev;
     const euler_edge *ee;
     u32 n;
+    const u64 *vk_hi;
     static constexpr u32 HEAD_APPENDS = 1;
     __device__ __forceinline__ u32 succ(u32 i) const { return ee[i].s; }
     __device__ __forceinline__ u64 head_key(u32 i) const { return ev[ee[i].v1].vid; }
+    __device__ __forceinline__ u64 head_key_hi(u32 i) const { return vk_hi ? vk_hi[ee[i].v1] : 0ull; }
     __device__ __forceinline__ char base(u32 i) const { return "ACGT"[ev[ee[i].v2].vid & 3]; }
     __device__ __forceinline__ bool emit(const u32 *, u32) const { return true; }
 };
 
 int tour_emit_contigs(euler_ctx *ctx, const euler_vertex *ev, u32 vcount, const euler_edge *ee, u32 n, u32 l,
-                      char **d_out, u64 *out_bytes, u64 *ncontigs)
+                      char **d_out, u64 *out_bytes, u64 *ncontigs, const u64 *vk_hi)
 {
     (void)vcount;
-    EulerChainModel m = {ev, ee, n};
+    EulerChainModel m = {ev, ee, n, vk_hi};
     return chain_emit(ctx, m, n, l - 1, d_out, out_bytes, ncontigs);
 }

@@ -106,6 +106,7 @@ struct UnitigChainModel {
     static constexpr u32 HEAD_APPENDS = 0;
     __device__ __forceinline__ u32 succ(u32 i) const { return succ_[i]; }
     __device__ __forceinline__ u64 head_key(u32 i) const { return nkeys[i]; }
+    __device__ __forceinline__ u64 head_key_hi(u32) const { return 0ull; }
     __device__ __forceinline__ char base(u32 i) const { return "ACGT"[nkeys[i] & 3]; }
     // write each unitig once: the strand whose component label is the smaller one
     __device__ __forceinline__ bool emit(const u32 *D, u32 i) const { return D[i] <= D[twin_id[i]]; }

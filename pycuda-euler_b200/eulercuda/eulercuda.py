@@ -97,6 +97,10 @@ def readLmersKmersCuda(readBuffer, readLength, partitionReadCount, lmerLength, l
     lv = ctx.download(_native.ART_LMER_VALUES)
     kk = ctx.download(_native.ART_KMER_KEYS)
     kv = np.arange(kk.size, dtype=np.uint32)
+    if int(lmerLength) > 32:
+        # two-word keys (csrc/wide.cu): hand them back as Python integers, like the reference's lists
+        lk = (ctx.download(_native.ART_LMER_KEYS_HI).astype(object) << 64) | lk.astype(object)
+        kk = (ctx.download(_native.ART_KMER_KEYS_HI).astype(object) << 64) | kk.astype(object)
     return [int(lk.size), int(kk.size), lk, lv, kk, kv]
 
 
