@@ -26,13 +26,9 @@
 __device__ __forceinline__ u32 dist_m(u32 k) { return k < DIST_M ? k : DIST_M; }
 __device__ __forceinline__ u32 owner_from_score(u32 score, u32 nranks)
 {
-    u32 h = score;
-    h ^= h >> 16;
-    h *= 0x85ebca6bu;
-    h ^= h >> 13;
-    h *= 0xc2b2ae35u;
-    h ^= h >> 16;
-    return (u32)(((u64)h * nranks) >> 32);
+    // The minimum of many scores hugs 0 in its HIGH bits; its low 16 bits (low16(c * odd) xor higher
+    // product bits, see mmer_score) stay uniform, so they are what is scaled to the rank count.
+    return ((score & 0xffffu) * nranks) >> 16;
 }
 // owners of the prefix and suffix k-mer of an l-mer (either orientation: the minimizer is strand symmetric)
 __device__ __forceinline__ void owners_of_lmer(u64 x, u32 l, u32 nranks, u32 &own_prefix, u32 &own_suffix)
@@ -279,6 +275,182 @@ __global__ void __launch_bounds__(PB, 4) dist_partition_kernel(const uint4 *__re
     }
 }
 
+// ---- the same pass for nranks <= 8 with rolling minimizers (the multi-GPU hot kernel) -------------
+// One roll for the m-mer scores and the sliding minima, owners kept as 4-bit fields of two u64
+// registers, per-lane per-destination counts as 8-bit fields of ONE u64, everything unrolled so that
+// nothing is indexed dynamically (no local memory, no shared owner table).  The warp scan runs on
+// 16-bit fields; prefix sums ACROSS the fields of a word are one multiply by 0x0001000100010001.
+#define P8_FIELDS 0x0001000100010001ull
+__device__ __forceinline__ u64 spread8to16(u32 x)
+{
+    u64 t = x;
+    t = (t | (t << 16)) & 0x0000FFFF0000FFFFull;
+    return (t | (t << 8)) & 0x00FF00FF00FF00FFull;
+}
+template <bool SCATTER, int WK>
+__global__ void __launch_bounds__(PB, 4) dist_partition8_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
+                                                                 const u32 *__restrict__ start_bits, u32 l, u32 nranks, u64 ntiles,
+                                                                 u64 *__restrict__ counts, u64 *__restrict__ cursors,
+                                                                 u64 *__restrict__ send, const u64 *__restrict__ seg_off, u64 seg_cap)
+{
+    __shared__ u64 s_stage[SCATTER ? (PB / 32) * PB_STAGE : 1];
+    u64 *stage = s_stage + (SCATTER ? (threadIdx.x >> 5) * PB_STAGE : 0);
+    const int lane = threadIdx.x & 31;
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    const u32 k = l - 1, top = 2 * (l - 1);
+    const u64 lmask = key_mask_d(l);
+    const u32 mmask = (1u << (2 * DIST_M)) - 1u;   // WK > 0 implies k >= DIST_M
+    const u32 rsh = 2 * WK;
+    const bool wide8 = nranks > 4;
+    u32 nl_tot = 0, nk_tot = 0;
+    const u64 seg_reg = (u32)lane < nranks ? seg_off[lane] : 0ull;
+
+    for (u64 tile = warp; tile < ntiles; tile += nwarps) {
+        const long long chunk = (long long)(tile * ENC_ADV) - ENC_HALO + lane;
+        const Chunk c = load_chunk(buf16, chunk, n_bases, start_bits);
+        const u32 p1 = __shfl_up_sync(0xffffffffu, c.codes, 1), p2 = __shfl_up_sync(0xffffffffu, c.codes, 2);
+        const u32 v1 = __shfl_up_sync(0xffffffffu, c.vmask, 1), v2 = __shfl_up_sync(0xffffffffu, c.vmask, 2);
+        const u32 s1 = __shfl_up_sync(0xffffffffu, c.smask, 1), s2 = __shfl_up_sync(0xffffffffu, c.smask, 2);
+        const u64 f0 = ((u64)p2 << 32) | p1;
+        const u64 rc0 = revcomp64(f0 & lmask, l);
+        // m-mer scores of the 16 positions of this chunk, then the WK before them from the lanes below
+        u32 wp[16], ws[16];
+        {
+            u32 sc[16];
+            u64 f2 = f0, r2 = rc0;
+            u32 cd = c.codes;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const u32 cc = cd >> 30;
+                cd <<= 2;
+                f2 = (f2 << 2) | cc;
+                r2 = (r2 >> 2) | ((u64)(3u - cc) << top);
+                const u32 w = (u32)f2 & mmask, rw = (u32)(r2 >> rsh) & mmask;
+                sc[i] = mmer_score(w < rw ? w : rw);
+            }
+            u32 sv[WK + 16];
+#pragma unroll
+            for (int j = 0; j < WK; j++) {
+                const int pos = j - WK;
+                sv[j] = (pos >= -16) ? __shfl_up_sync(0xffffffffu, sc[(pos + 16) & 15], 1)
+                                     : __shfl_up_sync(0xffffffffu, sc[(pos + 32) & 15], 2);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) sv[WK + i] = sc[i];
+            WinMin2<WK>::run(sv, wp, ws);
+        }
+        // validity, owners, per-destination counts
+        const u32 pv = (v2 << 16) | v1, ps = (s2 << 16) | s1;
+        u32 vrun = (lane < ENC_HALO) ? 0u : ((pv == 0xffffffffu) ? 32u : (u32)__ffs(~pv) - 1u);
+        u32 srun = ps ? (u32)__ffs(ps) - 1u : 32u;
+        u32 vm = (lane < ENC_HALO) ? 0u : (c.vmask << 16);   // halo lanes own no windows
+        u32 sm = c.smask << 16;
+        u64 own1 = 0, own2 = 0, cnt = 0;
+        u32 okmask = 0, nk = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const bool valid = (vm >> 31) != 0, start = (sm >> 31) != 0;
+            vm <<= 1;
+            sm <<= 1;
+            vrun = valid ? vrun + 1u : 0u;
+            srun = start ? 0u : srun + 1u;
+            nk += (vrun >= k && srun + 1u >= k) ? 1u : 0u;
+            const bool ok = vrun >= l && srun + 1u >= l;
+            const u32 o1 = owner_from_score(wp[i], nranks), o2 = owner_from_score(ws[i], nranks);
+            own1 |= (u64)o1 << (4 * i);
+            own2 |= (u64)o2 << (4 * i);
+            if (ok) {
+                okmask |= 1u << i;
+                cnt += 1ull << (8 * o1);
+                if (o2 != o1) cnt += 1ull << (8 * o2);
+            }
+        }
+        nk_tot += nk;
+        nl_tot += __popc(okmask);
+        // warp scan of the counts (16-bit fields: destinations 0-3 in lo, 4-7 in hi)
+        const u64 cLo = spread8to16((u32)cnt), cHi = wide8 ? spread8to16((u32)(cnt >> 32)) : 0ull;
+        u64 iLo = cLo, iHi = cHi;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u64 t = __shfl_up_sync(0xffffffffu, iLo, d);
+            if (lane >= d) iLo += t;
+        }
+        if (wide8) {
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u64 t = __shfl_up_sync(0xffffffffu, iHi, d);
+                if (lane >= d) iHi += t;
+            }
+        }
+        const u64 tLo = __shfl_sync(0xffffffffu, iLo, 31), tHi = wide8 ? __shfl_sync(0xffffffffu, iHi, 31) : 0ull;
+        const u32 mine_reg = (u32)(((lane & 4) ? tHi : tLo) >> (16 * (lane & 3))) & 0xffffu;   // lane d < 8: keys for destination d
+        if (!SCATTER) {
+            if ((u32)lane < nranks && mine_reg) atomicAdd(counts + lane, (u64)mine_reg);
+            continue;
+        }
+        u64 base_reg = 0;
+        if ((u32)lane < nranks && mine_reg) base_reg = atomicAdd(cursors + lane, (u64)mine_reg);   // ONE cursor atomic per destination per tile
+        // staging layout: destination after destination; start of each = prefix sum across the fields
+        const u64 fLo = tLo * P8_FIELDS, fHi = tHi * P8_FIELDS + (fLo >> 48) * P8_FIELDS;
+        const u64 wLo = fLo - tLo, wHi = fHi - tHi;
+        u64 posLo = wLo + (iLo - cLo), posHi = wHi + (iHi - cHi);
+        const u32 woff_reg = (u32)(((lane & 4) ? wHi : wLo) >> (16 * (lane & 3))) & 0xffffu;
+        {
+            u64 f = f0, rc = rc0;
+            u32 codes = c.codes;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const u32 cc = codes >> 30;
+                codes <<= 2;
+                f = (f << 2) | cc;
+                rc = (rc >> 2) | ((u64)(3u - cc) << top);
+                if ((okmask >> i) & 1u) {
+                    const u64 fm = f & lmask;
+                    const u64 key = fm < rc ? fm : rc;
+                    const u32 o1 = (u32)(own1 >> (4 * i)) & 15u, o2 = (u32)(own2 >> (4 * i)) & 15u;
+                    {
+                        const u32 sh = 16 * (o1 & 3);
+                        u32 slot;
+                        if (o1 & 4) { slot = (u32)(posHi >> sh) & 0xffffu; posHi += 1ull << sh; }
+                        else { slot = (u32)(posLo >> sh) & 0xffffu; posLo += 1ull << sh; }
+                        stage[slot] = key;
+                    }
+                    if (o2 != o1) {
+                        const u32 sh = 16 * (o2 & 3);
+                        u32 slot;
+                        if (o2 & 4) { slot = (u32)(posHi >> sh) & 0xffffu; posHi += 1ull << sh; }
+                        else { slot = (u32)(posLo >> sh) & 0xffffu; posLo += 1ull << sh; }
+                        stage[slot] = key;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // copy-out: contiguous, fully coalesced runs per destination (local HBM or a peer's over NVLink)
+        for (u32 d = 0; d < nranks; d++) {
+            const u32 tot = __shfl_sync(0xffffffffu, mine_reg, d);
+            const u64 base = __shfl_sync(0xffffffffu, base_reg, d);
+            const u64 seg = __shfl_sync(0xffffffffu, seg_reg, d);
+            const u32 wo = __shfl_sync(0xffffffffu, woff_reg, d);
+            for (u32 j = lane; j < tot; j += 32) {
+                const u64 at = base + j;
+                if (at < seg_cap) send[seg + at] = stage[wo + j];
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        nl_tot += __shfl_xor_sync(0xffffffffu, nl_tot, o);
+        nk_tot += __shfl_xor_sync(0xffffffffu, nk_tot, o);
+    }
+    if (lane == 0) {
+        if (nl_tot) atomicAdd(counts + 16, (u64)nl_tot);
+        if (nk_tot) atomicAdd(counts + 17, (u64)nk_tot);
+    }
+}
+
 int dist_partition(euler_ctx *ctx, bool scatter, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u32 nranks,
                    u64 *d_counts, u64 *d_cursors, u64 *d_send, const u64 *d_seg_off, u64 seg_cap)
 {
@@ -295,6 +467,19 @@ int dist_partition(euler_ctx *ctx, bool scatter, const void *d_buf, u64 n_bases,
 #define LAUNCH_PART(S, WW)                                                                                              \
     dist_partition_kernel<S, WW><<<g, PB, 0, ctx->stream>>>(b16, n_bases, d_bits, l, nranks, ntiles, d_counts, d_cursors, \
                                                             d_send, d_seg_off, seg_cap)
+#define LAUNCH_P8(S, WW)                                                                                                  \
+    dist_partition8_kernel<S, WW><<<g8, PB, 0, ctx->stream>>>(b16, n_bases, d_bits, l, nranks, ntiles, d_counts, d_cursors, \
+                                                              d_send, d_seg_off, seg_cap)
+    if (nranks <= 8 && (WK == 20 || WK == 10)) {
+        u64 grid8 = (u64)ctx->num_sms * 4;
+        if (grid8 > need) grid8 = need;
+        const unsigned g8 = (unsigned)grid8;
+        if (scatter) { if (WK == 20) LAUNCH_P8(true, 20); else LAUNCH_P8(true, 10); }
+        else { if (WK == 20) LAUNCH_P8(false, 20); else LAUNCH_P8(false, 10); }
+        CUDA_TRY(ctx, cudaGetLastError());
+        return EULER_OK;
+    }
+#undef LAUNCH_P8
     if (!scatter) {
         if (WK == 20) LAUNCH_PART(false, 20);
         else if (WK == 10) LAUNCH_PART(false, 10);
@@ -310,6 +495,29 @@ int dist_partition(euler_ctx *ctx, bool scatter, const void *d_buf, u64 n_bases,
 }
 
 // ---- count received canonical keys into the local table ----------------------------------------
+// The key stream is read once: it goes through L2 with an evict-first policy so that it does not
+// push the table (the only data with reuse) out.  stats[5] += number of slots newly claimed, i.e. the
+// distinct canonical keys this rank holds -- the size the next run of the same input needs.
+__device__ __forceinline__ u64 ld_evict_first_u64(const u64 *p, u64 policy)
+{
+    u64 v;
+    asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ int bucket_claim_fresh(u64 *bucket_keys, const K4 &q, u64 key, u32 &fresh)
+{
+#pragma unroll
+    for (int j = 0; j < EULER_BUCKET; j++) {
+        const u64 kv = q.k[j];
+        if (kv == key) return j;
+        if (kv == EULER_EMPTY_KEY) {
+            const u64 old = atomicCAS(bucket_keys + j, EULER_EMPTY_KEY, key);
+            if (old == EULER_EMPTY_KEY) { fresh++; return j; }
+            if (old == key) return j;
+        }
+    }
+    return -1;
+}
 __global__ void __launch_bounds__(DB, 4) dist_count_keys_kernel(const u64 *__restrict__ keys_in, u64 n, u64 *__restrict__ tab_keys,
                                                                  u32 *__restrict__ tab_cnt, u64 cap, u64 *__restrict__ stats)
 {
@@ -318,6 +526,9 @@ __global__ void __launch_bounds__(DB, 4) dist_count_keys_kernel(const u64 *__res
     const u64 stride = (u64)gridDim.x * blockDim.x;
     const u64 t0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     bool overflow = false;
+    u32 fresh = 0;
+    u64 policy;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     // every lane of a warp runs the same number of iterations (the loop bound is warp-uniform)
     const u64 iters = (n + stride * 4 - 1) / (stride * 4);
     for (u64 it = 0; it < iters; it++) {
@@ -328,7 +539,7 @@ __global__ void __launch_bounds__(DB, 4) dist_count_keys_kernel(const u64 *__res
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const u64 idx = (it * 4 + i) * stride + t0;
-            key[i] = idx < n ? keys_in[idx] : 0;
+            key[i] = idx < n ? ld_evict_first_u64(keys_in + idx, policy) : 0;
             if (idx < n) pend |= 1u << i;
             bucket[i] = (u32)hash_bucket(key[i], nbuckets);
         }
@@ -340,7 +551,7 @@ __global__ void __launch_bounds__(DB, 4) dist_count_keys_kernel(const u64 *__res
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 if (pend & (1u << i)) {
-                    const int j = bucket_claim(tab_keys + (u64)bucket[i] * EULER_BUCKET, q[i], key[i]);
+                    const int j = bucket_claim_fresh(tab_keys + (u64)bucket[i] * EULER_BUCKET, q[i], key[i], fresh);
                     if (j >= 0) {
                         atomicAdd(tab_cnt + (u64)bucket[i] * EULER_BUCKET + j, 1u);
                         pend &= ~(1u << i);
@@ -352,6 +563,9 @@ __global__ void __launch_bounds__(DB, 4) dist_count_keys_kernel(const u64 *__res
             if (++probes >= max_probe && pend) { overflow = true; pend = 0; }
         }
     }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, o);
+    if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(stats + 5, (u64)fresh);
     if (overflow) atomicOr((unsigned long long *)(stats + 2), 1ull);
 }
 

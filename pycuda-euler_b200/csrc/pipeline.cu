@@ -810,9 +810,9 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
     P->l = l; P->flags = 0; P->have_graph = false; P->expanded = false;
     memset(&P->st, 0, sizeof(P->st));
     EULER_TRY(P->stats.reserve(ctx, 64));
-    u64 est = distinct_hint ? distinct_hint : ((P->learned_bases == nkeys && P->learned_lc) ? P->learned_lc + P->learned_lc / 32
-                                                                                            : (nkeys ? nkeys : 1));
-    u64 lt_cap = cap_for(est), vt_cap = cap_for(est);
+    const bool learned = !distinct_hint && P->learned_bases == nkeys && P->learned_lc;
+    const u64 est = distinct_hint ? distinct_hint : (learned ? P->learned_lc : (nkeys ? nkeys : 1));
+    u64 lt_cap = cap_for(est), vt_cap = cap_for(learned ? P->learned_vc : est);
     u64 h[8] = {0};
     u32 retries = 0, launches = 0;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
@@ -864,9 +864,10 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     P->have_graph = true;
     P->learned_bases = nkeys;
-    // distinct canonical l-mers held by this rank (homed or not): occupied slots are not counted
-    // separately, the homed both-strand count is a safe size for the next run of the same input
-    P->learned_lc = U_l + 16;
+    // sizes for the next run of the same input: distinct canonical l-mers held by this rank (homed or
+    // not; counted by the insert kernel) and canonical owned vertices (palindromes are rare)
+    P->learned_lc = h[5] + h[5] / 32 + 16;
+    P->learned_vc = (V + 1) / 2 + V / 32 + 16;
     euler_stats &st = P->st;
     st.n_bases = 0; st.n_reads = 0; st.n_lmer_windows = nkeys; st.distinct_lmers = U_l; st.distinct_kmers = V; st.edge_count = E;
     st.lmer_table_capacity = lt_cap; st.kmer_table_capacity = vt_cap; st.retries = retries;

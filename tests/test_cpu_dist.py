@@ -10,14 +10,6 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _fmix32(h):
-    h ^= h >> 16
-    h = (h * 0x85ebca6b) & 0xffffffff
-    h ^= h >> 13
-    h = (h * 0xc2b2ae35) & 0xffffffff
-    return h ^ (h >> 16)
-
-
 def _owner_kmer(v, k, world, revcomp):
     m = min(12, k)
     mask = (1 << (2 * m)) - 1
@@ -28,7 +20,7 @@ def _owner_kmer(v, k, world, revcomp):
         s = (c * 2654435761) & 0xffffffff
         s ^= s >> 15
         best = min(best, s)
-    return (_fmix32(best) * world) >> 32
+    return ((best & 0xffff) * world) >> 16
 
 
 def _worker(rank, world, port, q):

@@ -10,16 +10,8 @@ pytestmark = pytest.mark.gpu
 NO_ID = 0xFFFFFFFF
 
 
-def _fmix32(h):
-    h ^= h >> 16
-    h = (h * 0x85ebca6b) & 0xffffffff
-    h ^= h >> 13
-    h = (h * 0xc2b2ae35) & 0xffffffff
-    return h ^ (h >> 16)
-
-
 def owner_kmer(v, k, world):
-    """numpy-free restatement of the device rule: owner = fmix32(min scrambled canonical m-mer) scaled"""
+    """numpy-free restatement of the device rule: owner = low 16 bits of the min scrambled canonical m-mer score, scaled"""
     m = min(12, k)
     mask = (1 << (2 * m)) - 1
     best = 0xffffffff
@@ -29,7 +21,7 @@ def owner_kmer(v, k, world):
         s = (c * 2654435761) & 0xffffffff
         s ^= s >> 15
         best = min(best, s)
-    return (_fmix32(best) * world) >> 32
+    return ((best & 0xffff) * world) >> 16
 
 
 def owner_np(kmers, world, k):
