@@ -33,6 +33,8 @@ WORKLOADS = {
     "ecoli_4.6Mbp_100bp_30x_k31": dict(G=4_600_000, L=100, cov=30, err_ppm=0, k=31),
     # configs[2] (per-GPU share when sharded)
     "100Mbp_150bp_40x_1pct_k31": dict(G=100_000_000, L=150, cov=40, err_ppm=10_000, k=31),
+    # configs[3]: 1 Gbp, 8 GPUs (strong scaling: the data set is split over the ranks)
+    "1Gbp_150bp_30x_k31": dict(G=1_000_000_000, L=150, cov=30, err_ppm=0, k=31),
     "small_smoke": dict(G=200_000, L=100, cov=20, err_ppm=0, k=31),
 }
 DEFAULT_WORKLOAD = "ecoli_4.6Mbp_100bp_30x_k31"
@@ -311,7 +313,7 @@ def main():
                        "edges": int(st.edge_count), "lmer_table_capacity": int(st.lmer_table_capacity),
                        "retries": int(st.retries)},
             "stage_ms": {"count_kernel": kern_ms_max, "graph": graph_ms, "step_wall": wall_ms},
-            "roofline": {"bound": "hbm", "kernel": "count_canonical_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "count_canonical_kernel" if world == 1 else "dist_count_keys_kernel (one launch per source rank)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": a_kernel,
                          "path_algorithmic_bytes": a_path,

@@ -338,6 +338,27 @@ int graph_setup_edges_plain(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, 
     return EULER_OK;
 }
 
+// ---- 64-bit sum of a u32 array (true edge total when it does not fit the 32-bit scan field) -------
+__global__ void __launch_bounds__(GB) sum_u32_kernel(const u32 *__restrict__ v, u64 n, u64 *__restrict__ out)
+{
+    u64 acc = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) acc += v[i];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd((unsigned long long *)out, (unsigned long long)acc);
+}
+int graph_sum_u32(euler_ctx *ctx, const u32 *v, u64 n, u64 *d_out)
+{
+    CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, sizeof(u64), ctx->stream));
+    if (!n) return EULER_OK;
+    u64 grid = (u64)ctx->num_sms * 8;
+    const u64 need = (n + GB - 1) / GB;
+    if (grid > need) grid = need;
+    sum_u32_kernel<<<(unsigned)grid, GB, 0, ctx->stream>>>(v, n, d_out);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
 // ---- plain table (module-level gpuhash API) ----------------------------------------------------
 __global__ void __launch_bounds__(GB) plain_build_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, u64 n,
                                                           u64 *__restrict__ TK, u32 *__restrict__ TV, u64 cap, u64 *flags)

@@ -61,6 +61,8 @@ int graph_setup_edges(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, const 
 int graph_setup_edges_plain(euler_ctx *ctx, const u64 *lkeys, const u32 *lvals, const u32 *loffs, u64 nl, u32 l,
                             const PlainTable &pt, const u32 *lstart, const u32 *estart, u32 ecount, euler_edge *ee,
                             u32 *lev, u32 *ent);
+// *d_out = sum of v[0..n) as u64
+int graph_sum_u32(euler_ctx *ctx, const u32 *v, u64 n, u64 *d_out);
 // plain table build / lookup
 int graph_plain_build(euler_ctx *ctx, const u64 *keys, const u32 *vals, u64 n, u64 *TK, u32 *TV, u64 cap, u64 *d_flags);
 int graph_plain_lookup(euler_ctx *ctx, const PlainTable &pt, const u64 *q, u64 nq, u32 *out);

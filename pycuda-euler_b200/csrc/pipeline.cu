@@ -842,8 +842,16 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
         if (h[2] & 1) lt_cap *= 2;
         if (h[2] & 2) vt_cap *= 2;
     }
-    const u64 U_l = h[3] & 0xffffffffull, E = h[3] >> 32, V = h[4];
-    P->U_l = U_l; P->V = V; P->E = E;
+    const u64 U_l = h[3] & 0xffffffffull, V = h[4];
+    u64 E = h[3] >> 32;
+    // Every received key adds at most 2 to the edge total.  Past 2^32 the 32-bit offsets of the
+    // reference layout (lmerOffsets, lstart / estart, EulerVertex.lp / .ep: `unsigned int`,
+    // pydebruijn.py:90-101) cannot address the expanded edge arrays, which would not fit one GPU
+    // either (32 B per edge): the compressed graph (keys, multiplicities, v1 / v2, degree slots) stays
+    // exact, the offsets are kept modulo 2^32, and edge_count is the true 64-bit total.
+    const char *force_big = getenv("EULER_B200_FORCE_BIG");   // test hook: take the 64-bit-total path on small inputs
+    const bool big = 2 * nkeys >= 0xffffffffull || (force_big && atoi(force_big) == 1);
+    P->U_l = U_l; P->V = V;
     if (V >= 0x3fffffffull) return euler_fail(ctx, EULER_ERR_RANGE, "vertex count exceeds u32 ids");
     EULER_TRY(P->lkeys.reserve(ctx, U_l)); EULER_TRY(P->lvals.reserve(ctx, U_l)); EULER_TRY(P->loffs.reserve(ctx, U_l));
     EULER_TRY(P->ev1.reserve(ctx, U_l)); EULER_TRY(P->ev2.reserve(ctx, U_l)); EULER_TRY(P->vkeys.reserve(ctx, V));
@@ -857,9 +865,21 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
     EULER_TRY(dist_edges(ctx, P->lt.keys(), P->lt.cnt(), P->lt_base.ptr(), P->lt_eoff.ptr(), lt_cap, l, vt, P->lt_own.ptr(),
                          P->lkeys.ptr(), P->lvals.ptr(), P->loffs.ptr(), P->ev1.ptr(), P->ev2.ptr(), P->lcount.ptr(),
                          P->ecount.ptr()));
-    EULER_TRY(graph_vertices_fused(ctx, P->lcount.ptr(), P->ecount.ptr(), P->vkeys.ptr(), V, P->lstart.ptr(), P->estart.ptr(),
-                                   P->ev.ptr()));
-    launches += 3;
+    if (!big) {
+        EULER_TRY(graph_vertices_fused(ctx, P->lcount.ptr(), P->ecount.ptr(), P->vkeys.ptr(), V, P->lstart.ptr(), P->estart.ptr(),
+                                       P->ev.ptr()));
+        launches += 3;
+    } else {
+        // the pair scan would carry the overflow of one sum into the other: two u32 scans (wrapping), then D5
+        EULER_TRY(scan_exclusive(ctx, ScanInU32{P->lcount.ptr()}, 4 * V, P->lstart.ptr(), (u64 *)nullptr));
+        EULER_TRY(scan_exclusive(ctx, ScanInU32{P->ecount.ptr()}, 4 * V, P->estart.ptr(), (u64 *)nullptr));
+        EULER_TRY(graph_setup_vertices(ctx, P->vkeys.ptr(), V, P->lcount.ptr(), P->lstart.ptr(), P->ecount.ptr(), P->estart.ptr(),
+                                       P->ev.ptr()));
+        EULER_TRY(graph_sum_u32(ctx, P->lvals.ptr(), U_l, P->stats.ptr() + 6));
+        EULER_TRY(read_u64(ctx, P->stats.ptr() + 6, &E));
+        launches += 6;
+    }
+    P->E = E;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     P->have_graph = true;

@@ -120,3 +120,40 @@ def test_partition_counts_are_exact(ctx):
         seg = np.sort(keys[int(send_off[d]):int(send_off[d]) + int(sc[d])])
         want = np.sort(np.concatenate([canon[o1 == d], canon[(o2 == d) & (o2 != o1)]]))
         assert np.array_equal(seg, want)
+
+
+def test_big_edge_total_path_matches_the_fused_one(ctx):
+    """Ranks whose edge total may pass 2^32 (BASELINE configs[3], 1 Gbp) scan lcount / ecount separately and
+    sum the multiplicities in 64 bits; on an input without overflow both paths must give the same artefacts."""
+    import os
+    from eulercuda.dist import emulate_partitioned
+    reads = random_reads(33, 500, genome_len=4000)
+    shards = [oracle.pack_reads(reads[r::2]) for r in range(2)]
+    a, _ = emulate_partitioned(ctx, shards, 32, 2)
+    os.environ["EULER_B200_FORCE_BIG"] = "1"
+    try:
+        b, _ = emulate_partitioned(ctx, shards, 32, 2)
+    finally:
+        del os.environ["EULER_B200_FORCE_BIG"]
+    def canon(p):
+        # slot-order ids depend on the table capacity and on insertion races: compare through the keys
+        o = np.argsort(p["LMER_KEYS"], kind="stable")
+        ov = np.argsort(p["KMER_KEYS"], kind="stable")
+        vk = p["KMER_KEYS"]
+        v2 = p["EDGE_V2"][o]
+        v2k = np.where(v2 == NO_ID, np.uint64(0xFFFFFFFFFFFFFFFF), vk[np.minimum(v2, vk.size - 1)])
+        return (p["LMER_KEYS"][o], p["LMER_VALUES"][o], vk[p["EDGE_V1"][o]], v2k, vk[ov],
+                p["LCOUNT"].reshape(-1, 4)[ov], p["ECOUNT"].reshape(-1, 4)[ov])
+
+    for pa, pb in zip(a, b):
+        for x, y in zip(canon(pa), canon(pb)):
+            assert np.array_equal(x, y)
+        assert pa["stats"]["edge_count"] == pb["stats"]["edge_count"] == int(pb["LMER_VALUES"].sum())
+        for p in (pa, pb):   # offsets are exclusive scans in id order (modulo 2^32 on the big path)
+            lc, ec = p["LCOUNT"].astype(np.uint64), p["ECOUNT"].astype(np.uint64)
+            assert np.array_equal(p["LSTART"], (np.concatenate([np.zeros(1, np.uint64), np.cumsum(lc)[:-1]]) & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+            assert np.array_equal(p["ESTART"], (np.concatenate([np.zeros(1, np.uint64), np.cumsum(ec)[:-1]]) & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+            assert np.array_equal(p["EV"]["vid"], p["KMER_KEYS"])
+            assert np.array_equal(p["EV"]["lp"], p["LSTART"][::4]) and np.array_equal(p["EV"]["ep"], p["ESTART"][::4])
+            assert np.array_equal(p["EV"]["lcount"], p["LCOUNT"].reshape(-1, 4).sum(1))
+            assert np.array_equal(p["EV"]["ecount"], p["ECOUNT"].reshape(-1, 4).sum(1))
