@@ -580,6 +580,101 @@ int dist_count_keys(euler_ctx *ctx, const u64 *d_keys, u64 n, u64 *tab_keys, u32
     return EULER_OK;
 }
 
+// ---- L2 blocking for tables far larger than L2 -----------------------------------------------------
+// A 3 GB table (1 Gbp over 8 GPUs) turns every insert into DRAM sector traffic plus TLB misses.  The
+// received keys are first split into `nparts` runs by the high bits of their table hash, so that
+// each run only touches one contiguous ~48 MB stretch of the table; the runs are then counted one
+// after another with that stretch resident in L2.  Order inside a run is irrelevant, so the split
+// is a counting sort per 4096-key tile in shared memory with ONE global cursor atomic per
+// (tile, part) and coalesced run copies.  Parts have a fixed capacity (the hash is uniform); a part
+// that overflows raises flags[0] and the caller falls back to the unblocked kernel.
+#define BK_THREADS 256
+#define BK_ITEMS 16
+#define BK_TILE (BK_THREADS * BK_ITEMS)
+#define BK_MAXP 256
+__device__ __forceinline__ u32 key_part(u64 key, u32 nparts)
+{
+    const u64 h = (key ^ (key >> 29)) * 0x9E3779B97F4A7C15ull;   // same mix as hash_bucket: parts are bucket ranges
+    return (u32)(((h >> 32) * (u64)nparts) >> 32);
+}
+__global__ void __launch_bounds__(BK_THREADS) dist_block_keys_kernel(const u64 *__restrict__ in, u64 n, u32 nparts,
+                                                                      u64 *__restrict__ cursors, u64 *__restrict__ out, u64 part_cap,
+                                                                      u64 *__restrict__ flags)
+{
+    __shared__ u64 stage[BK_TILE];
+    __shared__ u32 hist[BK_MAXP], loff[BK_MAXP], fill[BK_MAXP], wsum[BK_THREADS / 32];
+    __shared__ u64 gbase[BK_MAXP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 ntiles = (n + BK_TILE - 1) / BK_TILE;
+    u64 policy;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    bool over = false;
+    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        hist[tid] = 0;
+        fill[tid] = 0;
+        __syncthreads();
+        const u64 base = tile * BK_TILE;
+        const u32 cnt = (u32)(n - base < BK_TILE ? n - base : BK_TILE);
+        u64 k[BK_ITEMS];
+        u32 part[BK_ITEMS];
+#pragma unroll
+        for (int j = 0; j < BK_ITEMS; j++) {
+            const u32 i = j * BK_THREADS + tid;
+            if (i < cnt) {
+                k[j] = ld_evict_first_u64(in + base + i, policy);
+                part[j] = key_part(k[j], nparts);
+                atomicAdd(&hist[part[j]], 1u);
+            }
+        }
+        __syncthreads();
+        {   // exclusive scan of the 256 bins: shuffle scan per warp, then warp totals
+            const u32 v = hist[tid];
+            u32 inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            u32 woff = 0;
+#pragma unroll
+            for (int w = 0; w < BK_THREADS / 32; w++)
+                if (w < warp) woff += wsum[w];
+            loff[tid] = woff + inc - v;
+            gbase[tid] = v ? atomicAdd((unsigned long long *)(cursors + tid), (unsigned long long)v) : 0ull;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < BK_ITEMS; j++) {
+            const u32 i = j * BK_THREADS + tid;
+            if (i < cnt) stage[loff[part[j]] + atomicAdd(&fill[part[j]], 1u)] = k[j];
+        }
+        __syncthreads();
+        for (u32 i = tid; i < cnt; i += BK_THREADS) {
+            const u64 key = stage[i];
+            const u32 pp = key_part(key, nparts);
+            const u64 at = gbase[pp] + (i - loff[pp]);
+            if (at < part_cap) out[(u64)pp * part_cap + at] = key;
+            else over = true;
+        }
+        __syncthreads();
+    }
+    if (over) atomicOr((unsigned long long *)flags, 1ull);
+}
+
+int dist_block_keys(euler_ctx *ctx, const u64 *d_keys, u64 n, u32 nparts, u64 *d_cursors, u64 *d_out, u64 part_cap, u64 *d_flags)
+{
+    if (!n) return EULER_OK;
+    if (nparts > BK_MAXP) return euler_fail(ctx, EULER_ERR_ARG, "too many table parts");
+    u64 grid = (u64)ctx->num_sms * 4;
+    const u64 need = (n + BK_TILE - 1) / BK_TILE;
+    if (grid > need) grid = need;
+    dist_block_keys_kernel<<<(unsigned)grid, BK_THREADS, 0, ctx->stream>>>(d_keys, n, nparts, d_cursors, d_out, part_cap, d_flags);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
 // ---- ownership-aware graph stage ----------------------------------------------------------------
 __global__ void __launch_bounds__(DB) dist_vertex_insert_kernel(const u64 *__restrict__ lt_keys, u64 lt_cap, u32 l,
                                                                  u64 *__restrict__ vt_keys, u64 vt_cap,

@@ -84,6 +84,7 @@ struct Pipeline {
     u64 text_bytes = 0, text_n = 0;
     bool text_valid = false;  // contig text of the current graph is resident
     bool ingested = false;    // in_buf / in_off hold reads parsed on device by euler_ingest
+    DevArr<u64> blk_keys, blk_cur;  // partitioned path, tables >> L2: keys regrouped by table region, run cursors
     void *recv_buf = nullptr;  // peer-visible receive buffer of the partitioned path (plain cudaMalloc)
     u64 recv_cap = 0;
     // 128-bit keys (l in 33..64, wide.cu): tables, high key words, first/last base codes per l-mer
@@ -105,6 +106,7 @@ void pipeline_destroy(Pipeline *p)
     p->lcount.free(); p->ecount.free(); p->lstart.free(); p->estart.free(); p->ev.free(); p->ee.free();
     if (p->recv_buf) cudaFree(p->recv_buf);
     p->lev.free(); p->ent.free(); p->sort_k.free(); p->sort_v.free(); p->sort_hist.free();
+    p->blk_keys.free(); p->blk_cur.free();
     p->wlt_keys.free(); p->wvt_keys.free(); p->wlt_cnt.free(); p->lkeys_hi.free(); p->vkeys_hi.free(); p->tf.free();
     delete p;
 }
@@ -149,6 +151,12 @@ static bool use_packed_table()
         on = (e && atoi(e) == 1) ? 1 : 0;
     }
     return on != 0;
+}
+// EULER_B200_BLOCK_MB: table size from which the partitioned path regroups keys for L2 (0 = never)
+static u32 dist_block_min_mb()
+{
+    const char *e = getenv("EULER_B200_BLOCK_MB");
+    return e ? (u32)atoi(e) : 512u;
 }
 static u64 cap_for(u64 n) { return round_up((u64)((double)(n < 64 ? 64 : n) / table_load()) + 1, 1024); }
 
@@ -826,9 +834,37 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
         EULER_TRY(graph_table_clear(ctx, P->lt.keys(), P->lt.cnt(), lt_cap));
         EULER_TRY(graph_table_clear(ctx, P->vt_keys.ptr(), nullptr, vt_cap));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
-        for (u32 r = 0; r < nregions; r++)
-            EULER_TRY(dist_count_keys(ctx, (const u64 *)d_keys + (u64)r * region_stride, region_counts[r], P->lt.keys(),
-                                      P->lt.cnt(), lt_cap, P->stats.ptr()));
+        // tables far larger than L2: regroup the keys by table region first (dist.cu, "L2 blocking")
+        bool blocked = false;
+        const u64 table_bytes = lt_cap * 12, block_min = (u64)dist_block_min_mb() << 20;
+        if (block_min && table_bytes >= block_min && nkeys >= 4096) {
+            u32 nparts = (u32)((table_bytes + (48ull << 20) - 1) / (48ull << 20));
+            if (nparts > 256) nparts = 256;
+            const u64 part_cap = round_up(nkeys / nparts + nkeys / (nparts * 32ull) + 65536, 1024);
+            u64 cur[256];
+            if (P->blk_keys.reserve(ctx, (u64)nparts * part_cap) == EULER_OK && P->blk_cur.reserve(ctx, 256 + 8) == EULER_OK) {
+                CUDA_TRY(ctx, cudaMemsetAsync(P->blk_cur.ptr(), 0, (256 + 8) * sizeof(u64), s));
+                for (u32 r = 0; r < nregions; r++)
+                    EULER_TRY(dist_block_keys(ctx, (const u64 *)d_keys + (u64)r * region_stride, region_counts[r], nparts,
+                                              P->blk_cur.ptr(), P->blk_keys.ptr(), part_cap, P->blk_cur.ptr() + 256));
+                u64 flag = 0;
+                EULER_TRY(read_u64s(ctx, P->blk_cur.ptr(), cur, (int)nparts));
+                EULER_TRY(read_u64(ctx, P->blk_cur.ptr() + 256, &flag));
+                if (!flag) {
+                    blocked = true;
+                    for (u32 q = 0; q < nparts; q++)
+                        EULER_TRY(dist_count_keys(ctx, P->blk_keys.ptr() + (u64)q * part_cap, cur[q], P->lt.keys(), P->lt.cnt(), lt_cap,
+                                                  P->stats.ptr()));
+                    launches += nregions + nparts;
+                }
+            } else {
+                ctx->err.clear();   // no room for the regrouped copy: count in arrival order
+            }
+        }
+        if (!blocked)
+            for (u32 r = 0; r < nregions; r++)
+                EULER_TRY(dist_count_keys(ctx, (const u64 *)d_keys + (u64)r * region_stride, region_counts[r], P->lt.keys(),
+                                          P->lt.cnt(), lt_cap, P->stats.ptr()));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
         EULER_TRY(dist_lt_scan(ctx, P->lt.keys(), P->lt.cnt(), lt_cap, l, rank, nranks, P->lt_base.ptr(),
                                P->lt_eoff.ptr(), P->lt_own.ptr(), P->stats.ptr() + 3));

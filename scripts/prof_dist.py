@@ -15,7 +15,7 @@ import _native  # noqa: E402
 
 WORLD = int(os.environ.get("WORLD", "8"))
 L, LMER = 100, 32
-G = 4_600_000 * WORLD
+G = int(os.environ.get("G_PER_RANK", "4600000")) * WORLD
 NREADS = 1_380_000
 REPS = int(os.environ.get("REPS", "3"))
 

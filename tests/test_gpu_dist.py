@@ -122,6 +122,18 @@ def test_partition_counts_are_exact(ctx):
         assert np.array_equal(seg, want)
 
 
+def _canon_part(p):
+    # slot-order ids depend on the table capacity and on insertion races: compare through the keys
+    o = np.argsort(p["LMER_KEYS"], kind="stable")
+    ov = np.argsort(p["KMER_KEYS"], kind="stable")
+    vk = p["KMER_KEYS"]
+    v2 = p["EDGE_V2"][o]
+    v2k = np.where(v2 == NO_ID, np.uint64(0xFFFFFFFFFFFFFFFF), vk[np.minimum(v2, vk.size - 1)])
+    return (p["LMER_KEYS"][o], p["LMER_VALUES"][o], vk[p["EDGE_V1"][o]], v2k, vk[ov],
+            p["LCOUNT"].reshape(-1, 4)[ov], p["ECOUNT"].reshape(-1, 4)[ov])
+
+
+
 def test_big_edge_total_path_matches_the_fused_one(ctx):
     """Ranks whose edge total may pass 2^32 (BASELINE configs[3], 1 Gbp) scan lcount / ecount separately and
     sum the multiplicities in 64 bits; on an input without overflow both paths must give the same artefacts."""
@@ -135,18 +147,8 @@ def test_big_edge_total_path_matches_the_fused_one(ctx):
         b, _ = emulate_partitioned(ctx, shards, 32, 2)
     finally:
         del os.environ["EULER_B200_FORCE_BIG"]
-    def canon(p):
-        # slot-order ids depend on the table capacity and on insertion races: compare through the keys
-        o = np.argsort(p["LMER_KEYS"], kind="stable")
-        ov = np.argsort(p["KMER_KEYS"], kind="stable")
-        vk = p["KMER_KEYS"]
-        v2 = p["EDGE_V2"][o]
-        v2k = np.where(v2 == NO_ID, np.uint64(0xFFFFFFFFFFFFFFFF), vk[np.minimum(v2, vk.size - 1)])
-        return (p["LMER_KEYS"][o], p["LMER_VALUES"][o], vk[p["EDGE_V1"][o]], v2k, vk[ov],
-                p["LCOUNT"].reshape(-1, 4)[ov], p["ECOUNT"].reshape(-1, 4)[ov])
-
     for pa, pb in zip(a, b):
-        for x, y in zip(canon(pa), canon(pb)):
+        for x, y in zip(_canon_part(pa), _canon_part(pb)):
             assert np.array_equal(x, y)
         assert pa["stats"]["edge_count"] == pb["stats"]["edge_count"] == int(pb["LMER_VALUES"].sum())
         for p in (pa, pb):   # offsets are exclusive scans in id order (modulo 2^32 on the big path)
@@ -157,3 +159,26 @@ def test_big_edge_total_path_matches_the_fused_one(ctx):
             assert np.array_equal(p["EV"]["lp"], p["LSTART"][::4]) and np.array_equal(p["EV"]["ep"], p["ESTART"][::4])
             assert np.array_equal(p["EV"]["lcount"], p["LCOUNT"].reshape(-1, 4).sum(1))
             assert np.array_equal(p["EV"]["ecount"], p["ECOUNT"].reshape(-1, 4).sum(1))
+
+
+def test_l2_blocked_count_matches_arrival_order_count(ctx):
+    """Tables far larger than L2 (1 Gbp over 8 GPUs: 3 GB) regroup the received keys by table region before
+    counting (EULER_B200_BLOCK_MB, default 512); forced here on a 4 MB table: same graph either way."""
+    import os
+    from eulercuda.dist import emulate_partitioned
+    G, L = 150_000, 100
+    nreads = G * 20 // L
+    reads = oracle.synth_reads(G, L, err_ppm=5000, first=0, count=nreads)
+    half = nreads // 2
+    shards = [(reads[:half * L], oracle.fixed_offsets(half, L)), (reads[half * L:], oracle.fixed_offsets(nreads - half, L))]
+    a, _ = emulate_partitioned(ctx, shards, 32, 2)
+    os.environ["EULER_B200_BLOCK_MB"] = "1"
+    try:
+        b, _ = emulate_partitioned(ctx, shards, 32, 2)
+    finally:
+        del os.environ["EULER_B200_BLOCK_MB"]
+    for pa, pb in zip(a, b):
+        assert pb["stats"]["kernel_launches"] > pa["stats"]["kernel_launches"]   # the blocked path really ran
+        for x, y in zip(_canon_part(pa), _canon_part(pb)):
+            assert np.array_equal(x, y)
+        assert pa["stats"]["edge_count"] == pb["stats"]["edge_count"]
