@@ -411,6 +411,95 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
     return EULER_OK;
 }
 
+// per-rank build of the partitioned path over 16-byte keys (wide_dist.cu); same contract as dist_build_impl
+static int wide_dist_build_impl(euler_ctx *ctx, Pipeline *P, const void *d_keys, uint64_t nkeys, uint32_t nregions,
+                                uint64_t region_stride, const uint64_t *region_counts, uint32_t l, uint32_t rank, uint32_t nranks,
+                                uint64_t distinct_hint, euler_stats *stats)
+{
+    if (nranks > 8) return euler_fail(ctx, EULER_ERR_ARG, "128-bit keys: at most 8 ranks");
+    cudaStream_t s = ctx->stream;
+    const u32 k = l - 1;
+    P->l = l; P->flags = 0; P->have_graph = false; P->expanded = false; P->text_valid = false; P->wide = true;
+    memset(&P->st, 0, sizeof(P->st));
+    EULER_TRY(P->stats.reserve(ctx, 64));
+    const bool learned = !distinct_hint && P->learned_bases == nkeys && P->learned_lc;
+    const u64 est = distinct_hint ? distinct_hint : (learned ? P->learned_lc : (nkeys ? nkeys : 1));
+    u64 lt_cap = cap_for(est), vt_cap = cap_for(learned ? P->learned_vc : est);
+    u64 h[8] = {0};
+    u32 retries = 0, launches = 0;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    while (true) {
+        P->lt_cap = lt_cap; P->vt_cap = vt_cap;
+        EULER_TRY(P->wlt_keys.reserve(ctx, lt_cap)); EULER_TRY(P->wlt_cnt.reserve(ctx, lt_cap)); EULER_TRY(P->lt_base.reserve(ctx, lt_cap));
+        EULER_TRY(P->lt_own.reserve(ctx, lt_cap));
+        EULER_TRY(P->wvt_keys.reserve(ctx, vt_cap)); EULER_TRY(P->vt_id0.reserve(ctx, vt_cap));
+        CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 8 * sizeof(u64), s));
+        EULER_TRY(wide_table_clear(ctx, P->wlt_keys.ptr(), P->wlt_cnt.ptr(), lt_cap));
+        EULER_TRY(wide_table_clear(ctx, P->wvt_keys.ptr(), nullptr, vt_cap));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
+        for (u32 r = 0; r < nregions; r++)
+            EULER_TRY(wide_count_keys(ctx, (const K128 *)d_keys + (u64)r * region_stride, region_counts[r], P->wlt_keys.ptr(),
+                                      P->wlt_cnt.ptr(), lt_cap, P->stats.ptr()));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+        EULER_TRY(wide_own_flags(ctx, P->wlt_keys.ptr(), lt_cap, l, rank, nranks, P->lt_own.ptr()));
+        EULER_TRY(wide_homed_scan(ctx, P->wlt_keys.ptr(), P->lt_own.ptr(), lt_cap, l, P->lt_base.ptr(), P->stats.ptr() + 3));
+        EULER_TRY(wide_dist_vertex_insert(ctx, P->wlt_keys.ptr(), lt_cap, l, P->lt_own.ptr(), P->wvt_keys.ptr(), vt_cap,
+                                          P->stats.ptr() + 2));
+        EULER_TRY(wide_slot_scan(ctx, P->wvt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(), P->stats.ptr() + 4));
+        launches += nregions + 4;
+        EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 6));
+        if ((h[2] & 3) == 0) break;
+        if (++retries > 8) return euler_fail(ctx, EULER_ERR_OVERFLOW, "hash table overflow after %u regrows", retries);
+        if (h[2] & 1) lt_cap *= 2;
+        if (h[2] & 2) vt_cap *= 2;
+    }
+    const u64 U_l = h[3], V = h[4];
+    P->U_l = U_l; P->V = V;
+    if (V >= 0x3fffffffull || U_l >= 0xffffffffull) return euler_fail(ctx, EULER_ERR_RANGE, "graph exceeds u32 ids");
+    EULER_TRY(P->lkeys.reserve(ctx, U_l)); EULER_TRY(P->lkeys_hi.reserve(ctx, U_l)); EULER_TRY(P->lvals.reserve(ctx, U_l));
+    EULER_TRY(P->loffs.reserve(ctx, U_l)); EULER_TRY(P->ev1.reserve(ctx, U_l)); EULER_TRY(P->ev2.reserve(ctx, U_l));
+    EULER_TRY(P->tf.reserve(ctx, U_l + 16));
+    EULER_TRY(P->vkeys.reserve(ctx, V)); EULER_TRY(P->vkeys_hi.reserve(ctx, V));
+    EULER_TRY(P->lcount.reserve(ctx, 4 * V + 4)); EULER_TRY(P->ecount.reserve(ctx, 4 * V + 4));
+    EULER_TRY(P->lstart.reserve(ctx, 4 * V + 4)); EULER_TRY(P->estart.reserve(ctx, 4 * V + 4));
+    EULER_TRY(P->ev.reserve(ctx, V));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->lcount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+    EULER_TRY(wide_compact_vertices(ctx, P->wvt_keys.ptr(), P->vt_id0.ptr(), vt_cap, k, P->vkeys.ptr(), P->vkeys_hi.ptr()));
+    EULER_TRY(wide_compact_homed(ctx, P->wlt_keys.ptr(), P->wlt_cnt.ptr(), P->lt_own.ptr(), P->lt_base.ptr(), lt_cap, l,
+                                 P->lkeys.ptr(), P->lkeys_hi.ptr(), P->lvals.ptr()));
+    EULER_TRY(wide_degree_slots(ctx, P->lkeys.ptr(), P->lkeys_hi.ptr(), P->lvals.ptr(), U_l, l, P->wvt_keys.ptr(), P->vt_id0.ptr(),
+                                nullptr, vt_cap, P->lcount.ptr(), P->ecount.ptr(), P->ev1.ptr(), P->ev2.ptr(), P->tf.ptr()));
+    EULER_TRY(wide_foreign_in_edges(ctx, P->wlt_keys.ptr(), P->wlt_cnt.ptr(), P->lt_own.ptr(), lt_cap, l, P->wvt_keys.ptr(),
+                                    P->vt_id0.ptr(), vt_cap, P->ecount.ptr()));
+    // offsets modulo 2^32 and the exact 64-bit edge total, as in dist_build_impl's large path
+    EULER_TRY(scan_exclusive(ctx, ScanInU32{P->lvals.ptr()}, U_l, P->loffs.ptr(), (u64 *)nullptr));
+    EULER_TRY(scan_exclusive(ctx, ScanInU32{P->lcount.ptr()}, 4 * V, P->lstart.ptr(), (u64 *)nullptr));
+    EULER_TRY(scan_exclusive(ctx, ScanInU32{P->ecount.ptr()}, 4 * V, P->estart.ptr(), (u64 *)nullptr));
+    EULER_TRY(graph_setup_vertices(ctx, P->vkeys.ptr(), V, P->lcount.ptr(), P->lstart.ptr(), P->ecount.ptr(), P->estart.ptr(),
+                                   P->ev.ptr()));
+    EULER_TRY(graph_sum_u32(ctx, P->lvals.ptr(), U_l, P->stats.ptr() + 6));
+    u64 E = 0;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+    EULER_TRY(read_u64(ctx, P->stats.ptr() + 6, &E));
+    launches += 10;
+    P->E = E;
+    P->have_graph = true;
+    P->learned_bases = nkeys;
+    P->learned_lc = h[5] + h[5] / 32 + 16;
+    P->learned_vc = (V + 1) / 2 + V / 32 + 16;
+    euler_stats &st = P->st;
+    st.n_lmer_windows = nkeys; st.distinct_lmers = U_l; st.distinct_kmers = V; st.edge_count = E;
+    st.lmer_table_capacity = lt_cap; st.kmer_table_capacity = vt_cap; st.retries = retries;
+    cudaEventElapsedTime(&st.ms_count, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&st.ms_graph, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[2]);
+    cudaEventElapsedTime(&st.ms_count_kernel, ctx->ev[4], ctx->ev[1]);
+    st.kernel_launches = launches;
+    if (stats) *stats = st;
+    return EULER_OK;
+}
+
 static Pipeline *get_pipe(euler_ctx *ctx)
 {
     if (!ctx->pipe) ctx->pipe = new Pipeline();
@@ -680,24 +769,28 @@ int euler_dist_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off
 
 // single pass: scatter into nranks fixed-capacity segments of d_send (segment d starts at d * seg_cap);
 // counts[d] may exceed seg_cap, in which case the caller must redo the exchange with exact sizes
-int euler_dist_scatter_segments(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads, uint64_t n_bases,
-                                uint32_t l, uint32_t nranks, void *d_send, uint64_t seg_cap, uint64_t *counts)
+// shared tail of the two segment-scatter entry points.  seg_off: per destination, in KEYS from d_send
+// (d_send == NULL: absolute address / key size).  Keys are 8 bytes for l <= 32, 16 bytes (wide_dist.cu) above.
+static int scatter_to_segments(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads, uint64_t n_bases,
+                               uint32_t l, uint32_t nranks, void *d_send, const u64 *seg_off, uint64_t seg_cap, uint64_t *counts)
 {
-    if (!ctx || !counts || (!d_send && n_bases)) return EULER_ERR_ARG;
-    if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
-    if (nranks < 1 || nranks > 16) return euler_fail(ctx, EULER_ERR_ARG, "nranks %u out of range [1,16]", nranks);
+    if (l < 2 || l > 64) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,64]", l);
+    if (nranks < 1 || nranks > (l > 32 ? 8u : 16u)) return euler_fail(ctx, EULER_ERR_ARG, "nranks %u out of range", nranks);
     if (((uintptr_t)d_buf & 15) != 0) return euler_fail(ctx, EULER_ERR_ARG, "d_buf must be 16-byte aligned");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     Pipeline *P = get_pipe(ctx);
     EULER_TRY(P->stats.reserve(ctx, 64));
-    EULER_TRY(P->start_bits.reserve(ctx, n_bases / 32 + 2));
     CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 64 * sizeof(u64), ctx->stream));
-    u64 seg_off[16];
-    for (u32 d = 0; d < 16; d++) seg_off[d] = (u64)d * seg_cap;
     CUDA_TRY(ctx, cudaMemcpyAsync(P->stats.ptr() + 24, seg_off, nranks * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-    EULER_TRY(enc_mark_starts(ctx, (const u64 *)d_read_off, nreads, n_bases, P->start_bits.ptr()));
-    EULER_TRY(dist_partition(ctx, true, d_buf, n_bases, P->start_bits.ptr(), l, nranks, P->stats.ptr() + 32, P->stats.ptr() + 8,
-                             (u64 *)d_send, P->stats.ptr() + 24, seg_cap));
+    if (l > 32) {
+        EULER_TRY(wide_dist_scatter(ctx, d_buf, (const u64 *)d_read_off, nreads, l, nranks, P->stats.ptr() + 32, P->stats.ptr() + 8,
+                                    d_send, P->stats.ptr() + 24, seg_cap));
+    } else {
+        EULER_TRY(P->start_bits.reserve(ctx, n_bases / 32 + 2));
+        EULER_TRY(enc_mark_starts(ctx, (const u64 *)d_read_off, nreads, n_bases, P->start_bits.ptr()));
+        EULER_TRY(dist_partition(ctx, true, d_buf, n_bases, P->start_bits.ptr(), l, nranks, P->stats.ptr() + 32, P->stats.ptr() + 8,
+                                 (u64 *)d_send, P->stats.ptr() + 24, seg_cap));
+    }
     u64 h[16], w[2];
     EULER_TRY(read_u64s(ctx, P->stats.ptr() + 8, h, 16));
     EULER_TRY(read_u64s(ctx, P->stats.ptr() + 48, w, 2));
@@ -705,6 +798,15 @@ int euler_dist_scatter_segments(euler_ctx *ctx, const void *d_buf, const void *d
     counts[nranks] = w[0];
     counts[nranks + 1] = w[1];
     return EULER_OK;
+}
+
+int euler_dist_scatter_segments(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads, uint64_t n_bases,
+                                uint32_t l, uint32_t nranks, void *d_send, uint64_t seg_cap, uint64_t *counts)
+{
+    if (!ctx || !counts || (!d_send && n_bases)) return EULER_ERR_ARG;
+    u64 seg_off[16];
+    for (u32 d = 0; d < 16; d++) seg_off[d] = (u64)d * seg_cap;
+    return scatter_to_segments(ctx, d_buf, d_read_off, nreads, n_bases, l, nranks, d_send, seg_off, seg_cap, counts);
 }
 
 // ---- peer-memory exchange: the scatter kernel stores straight into the destination ranks' receive
@@ -758,30 +860,14 @@ int euler_dist_scatter_peers(euler_ctx *ctx, const void *d_buf, const void *d_re
                              uint32_t l, uint32_t nranks, void *const *dst_ptrs, uint64_t seg_cap, uint64_t *counts)
 {
     if (!ctx || !counts || !dst_ptrs) return EULER_ERR_ARG;
-    if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
     if (nranks < 1 || nranks > 16) return euler_fail(ctx, EULER_ERR_ARG, "nranks %u out of range [1,16]", nranks);
-    if (((uintptr_t)d_buf & 15) != 0) return euler_fail(ctx, EULER_ERR_ARG, "d_buf must be 16-byte aligned");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    Pipeline *P = get_pipe(ctx);
-    EULER_TRY(P->stats.reserve(ctx, 64));
-    EULER_TRY(P->start_bits.reserve(ctx, n_bases / 32 + 2));
-    CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 64 * sizeof(u64), ctx->stream));
+    const u64 key_bytes = l > 32 ? 16 : 8;
     u64 seg_off[16];
     for (u32 d = 0; d < nranks; d++) {
-        if (((uintptr_t)dst_ptrs[d] & 7) != 0) return euler_fail(ctx, EULER_ERR_ARG, "destination pointer %u not 8-byte aligned", d);
-        seg_off[d] = (u64)(uintptr_t)dst_ptrs[d] / sizeof(u64);   // the kernel indexes u64 words from address 0
+        if (((uintptr_t)dst_ptrs[d] & (key_bytes - 1)) != 0) return euler_fail(ctx, EULER_ERR_ARG, "destination pointer %u not key-aligned", d);
+        seg_off[d] = (u64)(uintptr_t)dst_ptrs[d] / key_bytes;   // the kernel indexes keys from address 0
     }
-    CUDA_TRY(ctx, cudaMemcpyAsync(P->stats.ptr() + 24, seg_off, nranks * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-    EULER_TRY(enc_mark_starts(ctx, (const u64 *)d_read_off, nreads, n_bases, P->start_bits.ptr()));
-    EULER_TRY(dist_partition(ctx, true, d_buf, n_bases, P->start_bits.ptr(), l, nranks, P->stats.ptr() + 32, P->stats.ptr() + 8,
-                             (u64 *)nullptr, P->stats.ptr() + 24, seg_cap));
-    u64 h[16], w[2];
-    EULER_TRY(read_u64s(ctx, P->stats.ptr() + 8, h, 16));
-    EULER_TRY(read_u64s(ctx, P->stats.ptr() + 48, w, 2));
-    for (u32 d = 0; d < nranks; d++) counts[d] = h[d];
-    counts[nranks] = w[0];
-    counts[nranks + 1] = w[1];
-    return EULER_OK;
+    return scatter_to_segments(ctx, d_buf, d_read_off, nreads, n_bases, l, nranks, nullptr, seg_off, seg_cap, counts);
 }
 
 static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_t nregions, uint64_t region_stride,
@@ -809,12 +895,14 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
                            euler_stats *stats)
 {
     if (!ctx) return EULER_ERR_ARG;
-    if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
+    if (l < 2 || l > 64) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,64]", l);
     if (nranks < 1 || nranks > 16 || rank >= nranks) return euler_fail(ctx, EULER_ERR_ARG, "bad rank %u / %u", rank, nranks);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     Pipeline *P = get_pipe(ctx);
+    if (l > 32) return wide_dist_build_impl(ctx, P, d_keys, nkeys, nregions, region_stride, region_counts, l, rank, nranks, distinct_hint, stats);
     cudaStream_t s = ctx->stream;
     const u32 k = l - 1;
+    P->wide = false;
     P->l = l; P->flags = 0; P->have_graph = false; P->expanded = false;
     memset(&P->st, 0, sizeof(P->st));
     EULER_TRY(P->stats.reserve(ctx, 64));

@@ -126,3 +126,16 @@ int wide_assign_sorted_ids(euler_ctx *ctx, const u64 *vk_lo, const u64 *vk_hi, u
 // tf[i] = (last base code) | (first base code << 2) of l-mer i, consumed by graph_setup_edges
 int wide_degree_slots(euler_ctx *ctx, const u64 *lk_lo, const u64 *lk_hi, const u32 *lvals, u64 nl, u32 l, const K128 *vt_keys,
                       const u32 *id0, const u32 *id1, u64 vt_cap, u32 *lcount, u32 *ecount, u32 *ev1, u32 *ev2, unsigned char *tf);
+
+// ---- wide_dist.cu (k-mer-space partition over 16-byte keys)
+int wide_dist_scatter(euler_ctx *ctx, const void *d_buf, const u64 *d_off, u64 nreads, u32 l, u32 nranks, u64 *d_counts,
+                      u64 *d_cursors, void *d_send, const u64 *d_seg_off, u64 seg_cap);
+int wide_count_keys(euler_ctx *ctx, const void *d_keys, u64 n, K128 *keys, u32 *cnt, u64 cap, u64 *d_stats);
+int wide_own_flags(euler_ctx *ctx, const K128 *keys, u64 cap, u32 l, u32 rank, u32 nranks, unsigned char *own);
+int wide_dist_vertex_insert(euler_ctx *ctx, const K128 *lt_keys, u64 lt_cap, u32 l, const unsigned char *own, K128 *vt_keys,
+                            u64 vt_cap, u64 *d_flags);
+int wide_homed_scan(euler_ctx *ctx, const K128 *keys, const unsigned char *own, u64 cap, u32 l, u32 *d_base, u64 *d_total);
+int wide_compact_homed(euler_ctx *ctx, const K128 *lt_keys, const u32 *lt_cnt, const unsigned char *own, const u32 *base, u64 cap,
+                       u32 l, u64 *lk_lo, u64 *lk_hi, u32 *lvals);
+int wide_foreign_in_edges(euler_ctx *ctx, const K128 *lt_keys, const u32 *lt_cnt, const unsigned char *own, u64 cap, u32 l,
+                          const K128 *vt_keys, const u32 *id0, u64 vt_cap, u32 *ecount);

@@ -62,6 +62,7 @@ class PeerExchange:
     region r of d's buffer over NVLink (CUDA IPC), so the all-to-all is fused into the partition pass."""
 
     def __init__(self, ctx, rank, world, seg_cap, group=None):
+        """seg_cap is in 8-byte words (an l-mer key is one word for l <= 32, two above)"""
         import torch.distributed as dist
         self.ctx, self.rank, self.world, self.seg_cap, self.group = ctx, rank, world, int(seg_cap), group
         self.local_ptr, handle = ctx.dist_recv_alloc(self.seg_cap * world)
@@ -113,7 +114,15 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
     import torch
     import torch.distributed as dist
     dev = d_reads.device
+    kw = 2 if l > 32 else 1          # 8-byte words per key (128-bit keys above l = 32, csrc/wide_dist.cu)
     t0 = time.perf_counter()
+    if world == 1 and kw == 2:
+        cap1 = max(n_bases - nreads * (l - 1), 1) + 16
+        send = _buffer("send", cap1 * kw, dev)
+        counts = ctx.dist_scatter_segments(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, 1, send.data_ptr(), cap1)
+        st = ctx.dist_build(send.data_ptr(), int(counts[0]), l, 0, 1, distinct_hint)
+        return st, {"n_lmer_windows": int(counts[1]), "n_kmer_windows": int(counts[2]), "sent_keys": int(counts[0]),
+                    "recv_keys": int(counts[0]), "exchange_bytes": 0, "exact_fallback": False, "transport": "none"}
     if world == 1:
         counts = ctx.dist_count(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, 1)
         send = _buffer("send", int(counts[0]), dev)
@@ -124,13 +133,16 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
                     "recv_keys": int(counts[0]), "exchange_bytes": 0, "exact_fallback": False, "transport": "none"}
     # upper bound of windows; ~1.05 copies of each go out with minimizer ownership
     windows_ub = max(n_bases - nreads * (l - 1), 1)
-    seg_cap = int(windows_ub * slack * 1.15 / world) + 4096
-    px = _peer_exchange(ctx, rank, world, seg_cap, group) if use_peer else None
+    seg_cap = (int(windows_ub * slack * 1.15 / world) + 4096 + 1) & ~1
+    px = _peer_exchange(ctx, rank, world, seg_cap * kw, group) if use_peer else None
     if px is not None:
-        seg_cap = px.seg_cap
+        seg_cap = px.seg_cap // kw
+        if kw == 2 and px.seg_cap % 2:     # cached buffer with an odd word stride: regions would not be 16-byte aligned
+            px = None
+    if px is not None:
         counts = ctx.dist_scatter_peers(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world, px.dst_ptrs, seg_cap)
     else:
-        send = _buffer("send", seg_cap * world, dev)
+        send = _buffer("send", seg_cap * world * kw, dev)
         counts = ctx.dist_scatter_segments(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world, send.data_ptr(),
                                            seg_cap)
     send_counts = counts[:world].astype(np.int64).tolist()
@@ -145,6 +157,8 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
     recv_counts = [int(gathered[src, rank]) for src in range(world)]
     exact = bool(gathered[:, world].max())
     t2 = time.perf_counter()
+    if exact and kw == 2:
+        raise RuntimeError("128-bit keys: a destination segment overflowed (skewed minimizers); raise `slack`")
     if exact:   # rare: redo with exact sizes on every rank, over NCCL
         counts = ctx.dist_count(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world)
         send_counts = counts[:world].astype(np.int64).tolist()
@@ -164,13 +178,13 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
         st = ctx.dist_build_regions(px.local_ptr, seg_cap, recv_counts, l, rank, world, distinct_hint)
         transport = "peer stores over NVLink (CUDA IPC), fused into the scatter kernel"
     else:
-        recv = _buffer("recv", nkeys, dev)
+        recv = _buffer("recv", nkeys * kw, dev)
         out_list, in_list, pos = [], [], 0
         for src in range(world):
-            out_list.append(recv[pos:pos + recv_counts[src]])
+            out_list.append(recv[pos * kw:(pos + recv_counts[src]) * kw])
             pos += recv_counts[src]
         for d in range(world):
-            in_list.append(send[starts[d]:starts[d] + send_counts[d]])
+            in_list.append(send[starts[d] * kw:(starts[d] + send_counts[d]) * kw])
         dist.all_to_all(out_list, in_list, group=group)
         torch.cuda.current_stream().synchronize()
         t3 = time.perf_counter()
@@ -178,7 +192,7 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
         transport = "NCCL all_to_all"
     t4 = time.perf_counter()
     info = {"n_lmer_windows": n_l, "n_kmer_windows": n_k, "sent_keys": int(sum(send_counts)), "recv_keys": nkeys,
-            "exchange_bytes": 8 * (int(sum(send_counts)) - send_counts[rank]), "exact_fallback": exact, "transport": transport,
+            "exchange_bytes": 8 * kw * (int(sum(send_counts)) - send_counts[rank]), "exact_fallback": exact, "transport": transport,
             "phase_ms": {"partition": 1e3 * (t1 - t0), "count_exchange": 1e3 * (t2 - t1), "all_to_all": 1e3 * (t3 - t2),
                          "build": 1e3 * (t4 - t3)}}
     return st, info
@@ -195,6 +209,14 @@ def emulate_partitioned(ctx, shards, l, world):
         d_buf = torch.from_numpy(np.ascontiguousarray(buf)).cuda() if len(buf) else torch.zeros(16, dtype=torch.uint8, device="cuda")
         d_off = torch.from_numpy(np.ascontiguousarray(off).astype(np.int64)).cuda()
         nreads, n_bases = len(off) - 1, int(off[-1])
+        if l > 32:      # 16-byte keys: fixed-capacity segments (csrc/wide_dist.cu), two int64 words per key
+            cap = max(n_bases, 1) + 16
+            send = torch.empty(cap * world * 2, dtype=torch.int64, device="cuda")
+            counts = ctx.dist_scatter_segments(d_buf.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world, send.data_ptr(), cap)
+            windows.append((int(counts[world]), int(counts[world + 1])))
+            for d in range(world):
+                buckets[r][d] = send[2 * cap * d:2 * (cap * d + int(counts[d]))].clone()
+            continue
         counts = ctx.dist_count(d_buf.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world)
         sc = counts[:world].astype(np.int64)
         windows.append((int(counts[world]), int(counts[world + 1])))
@@ -212,11 +234,11 @@ def emulate_partitioned(ctx, shards, l, world):
             recv = torch.zeros(1, dtype=torch.int64, device="cuda")
             nkeys = 0
         else:
-            nkeys = recv.numel()
+            nkeys = recv.numel() // (2 if l > 32 else 1)
         st = ctx.dist_build(recv.data_ptr(), nkeys, l, d, world, 0)
-        art = {name: ctx.download(getattr(N, "ART_" + name)) for name in
-               ("LMER_KEYS", "LMER_VALUES", "LMER_OFFSETS", "KMER_KEYS", "LCOUNT", "ECOUNT", "LSTART", "ESTART", "EV",
-                "EDGE_V1", "EDGE_V2")}
+        names = ("LMER_KEYS", "LMER_VALUES", "LMER_OFFSETS", "KMER_KEYS", "LCOUNT", "ECOUNT", "LSTART", "ESTART", "EV",
+                 "EDGE_V1", "EDGE_V2") + (("LMER_KEYS_HI", "KMER_KEYS_HI") if l > 32 else ())
+        art = {name: ctx.download(getattr(N, "ART_" + name)) for name in names}
         art["stats"] = st.as_dict()
         art["recv_keys"] = nkeys
         out.append(art)

@@ -182,3 +182,69 @@ def test_l2_blocked_count_matches_arrival_order_count(ctx):
         for x, y in zip(_canon_part(pa), _canon_part(pb)):
             assert np.array_equal(x, y)
         assert pa["stats"]["edge_count"] == pb["stats"]["edge_count"]
+
+
+def _rc(x, n):
+    """reverse complement of an n-mer held in a Python int (any width)"""
+    r = 0
+    for _ in range(n):
+        r = (r << 2) | (3 - (x & 3))
+        x >>= 2
+    return r
+
+
+def _wide(lo, hi):
+    return [(int(h) << 64) | int(x) for x, h in zip(lo, hi)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("l", [33, 48, 64])
+def test_partitioned_wide_graph_equals_oracle(ctx, world, l):
+    """128-bit keys (k up to 63) through the partition: union of the per-rank graphs == the oracle's graph."""
+    from eulercuda.dist import emulate_partitioned
+    reads = random_reads(23, 400, genome_len=4000, lens=(64, 80, 100, 100, 150), n_frac=0.1) + ["A" * 150, "ACGT" * 30]
+    k = l - 1
+    shards = [oracle.pack_reads(reads[r::world]) for r in range(world)]
+    parts, windows = emulate_partitioned(ctx, shards, l, world)
+    buf, off = oracle.pack_reads(reads)
+    g = oracle.graph_build(buf, off, l, expand=False)
+    assert sum(w[0] for w in windows) * 2 == g.ne
+    gv = _wide(g.vk_lo, g.vk_hi)
+    gl = _wide(g.lk_lo, g.lk_hi)
+    okey = {v: i for i, v in enumerate(gv)}
+    kmask = (1 << (2 * k)) - 1
+    seen_v, seen_l, total_e = [], {}, 0
+    for r, p in enumerate(parts):
+        vk = _wide(p["KMER_KEYS"], p["KMER_KEYS_HI"])
+        seen_v += vk
+        assert all(owner_kmer(min(v, _rc(v, k)), k, world) == r for v in vk)
+        ids = np.array([okey[v] for v in vk], dtype=np.int64)
+        lc, ec = p["LCOUNT"].reshape(-1, 4), p["ECOUNT"].reshape(-1, 4)
+        assert np.array_equal(lc, g.lcount.reshape(-1, 4)[ids]) and np.array_equal(ec, g.ecount.reshape(-1, 4)[ids])
+        ev = p["EV"]
+        assert np.array_equal(ev["vid"], p["KMER_KEYS"])
+        assert np.array_equal(ev["lcount"], lc.sum(1)) and np.array_equal(ev["ecount"], ec.sum(1))
+        z = np.zeros(1, np.uint64)
+        if len(vk):
+            assert np.array_equal(p["LSTART"], np.concatenate([z, np.cumsum(lc.ravel().astype(np.uint64))[:-1]]).astype(np.uint32))
+            assert np.array_equal(p["ESTART"], np.concatenate([z, np.cumsum(ec.ravel().astype(np.uint64))[:-1]]).astype(np.uint32))
+            assert np.array_equal(ev["lp"], p["LSTART"][::4]) and np.array_equal(ev["ep"], p["ESTART"][::4])
+        lk = _wide(p["LMER_KEYS"], p["LMER_KEYS_HI"])
+        lv = p["LMER_VALUES"]
+        total_e += int(lv.sum())
+        assert p["stats"]["edge_count"] == int(lv.sum())
+        if len(lk):
+            assert np.array_equal(p["LMER_OFFSETS"], np.concatenate([z, np.cumsum(lv.astype(np.uint64))[:-1]]).astype(np.uint32))
+        for x, m, v1, v2 in zip(lk, lv, p["EDGE_V1"], p["EDGE_V2"]):
+            assert x not in seen_l          # every both-strand l-mer homed exactly once
+            seen_l[x] = int(m)
+            assert vk[v1] == x >> 2         # v1 always local
+            suf = x & kmask
+            own_s = owner_kmer(min(suf, _rc(suf, k)), k, world)
+            if v2 == NO_ID:
+                assert own_s != r
+            else:
+                assert own_s == r and vk[v2] == suf
+    assert sorted(seen_v) == gv
+    assert seen_l == {x: int(m) for x, m in zip(gl, g.lvals)}
+    assert total_e == g.ne
