@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = genome and reads grow with N (default); strong = the named data set is split over the ranks")
+    ap.add_argument("--k", type=int, default=0,
+                    help="override the workload's k (BASELINE configs[4] k sweep: 21 / 31 / 63; k = 63 uses 128-bit keys)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -157,6 +159,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     wl = dict(WORKLOADS[args.workload])
+    if args.k:
+        wl["k"] = args.k
     wl["R"] = -(-wl["G"] * wl["cov"] // wl["L"])
 
     if args.impl == "reference":
@@ -284,7 +288,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        a_kernel, a_path = algorithmic_bytes(st)
+        a_kernel, a_path = algorithmic_bytes(st, 16 if l > 32 else 8)
         achieved = a_kernel / (kern_ms_max * 1e-3) / 1e9
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
@@ -297,7 +301,7 @@ def main():
         line = {
             "metric": METRIC, "value": nk_total / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
-            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u64" if l <= 32 else "u128", "data": "synthetic",
             "config": {
                 "workload": args.workload, "genome_bp": wl["G"], "read_len": L, "coverage": wl["cov"], "err_ppm": wl["err_ppm"],
                 "k": k, "reads_per_gpu": R, "bases_per_gpu": R * L,
@@ -313,7 +317,8 @@ def main():
                        "edges": int(st.edge_count), "lmer_table_capacity": int(st.lmer_table_capacity),
                        "retries": int(st.retries)},
             "stage_ms": {"count_kernel": kern_ms_max, "graph": graph_ms, "step_wall": wall_ms},
-            "roofline": {"bound": "hbm", "kernel": "count_canonical_kernel" if world == 1 else "dist_count_keys_kernel (one launch per source rank)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": ("count_canonical_kernel" if l <= 32 else "wide_count_kernel") if world == 1 else
+                         ("dist_count_keys_kernel" if l <= 32 else "wide_count_keys_kernel") + " (one launch per source rank)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": a_kernel,
                          "path_algorithmic_bytes": a_path,

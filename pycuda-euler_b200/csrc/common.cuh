@@ -15,6 +15,7 @@ typedef unsigned int u32;
 #define EULER_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define EULER_NO_ID 0xFFFFFFFFu
 #define EULER_SMS 148
+#define EULER_PINNED_WORDS 1024
 
 // ---------------------------------------------------------------------------------------
 // context
@@ -32,7 +33,7 @@ struct euler_ctx {
     bool own_stream = false;
     std::string err;
     // pinned host staging for small device->host reads
-    u64 *h_pinned = nullptr;
+    u64 *h_pinned = nullptr;   // EULER_PINNED_WORDS u64 of pinned host memory for small read-backs
     Pipeline *pipe = nullptr;
     DevBuf scan_state;  // tile descriptors of the single-pass scan
     DevBuf cg_buf;      // circuit edges of the last tour_circuit_edges call
@@ -220,6 +221,35 @@ __device__ __forceinline__ u64 table_home(u64 key, u32 len, u32 nb, TableHash th
     u32 a, b, c;
     min_scores(key, len, th.m, a, b, c);
     return home_from_score(key, a, nb, th);
+}
+
+// ---- co-hashed tables ---------------------------------------------------------------------------------
+// The graph stage walks the canonical l-mer table in slot order and looks up each l-mer's prefix and
+// suffix vertex.  If the l-mer table is hashed by the canonical form of the PREFIX k-mer of the stored
+// (canonical) l-mer -- the very value the vertex table hashes -- an l-mer and its prefix vertex sit at
+// the same relative position of their tables: the prefix lookups, the prefix-side degree-slot writes
+// and half of the vertex inserts become sequential, only the suffix side stays random.  At most four
+// canonical l-mers share a home (one bucket).  TableHash{0, EULER_PREFIX_HOME} selects it.
+#define EULER_PREFIX_HOME 0xffffffffu
+// c = canonical l-mer, r = its reverse complement, kmask = mask of k = l-1 bases
+__device__ __forceinline__ u64 prefix_home_key(u64 c, u64 r, u64 kmask, u32 &flip)
+{
+    const u64 p = c >> 2, rp = r & kmask;   // rc(prefix(c)) = suffix(rc(c))
+    flip = rp < p ? 1u : 0u;
+    return flip ? rp : p;
+}
+// A vertex is the canonical prefix of up to two canonical l-mers (its out-edge when that is canonical
+// as written, its in-edge when the reverse complement is).  Both in one bucket raises the bucket-load
+// variance (count kernel 1.52 -> 1.88 ms); the second kind one bucket up makes ADJACENT buckets
+// correlated, which lengthens the overflow cascades (probe rounds +17 %, 1.77 ms).  It therefore goes
+// EULER_FLIP_STRIDE buckets up: still the same neighbourhood of the table for the graph stage.
+#define EULER_FLIP_STRIDE 37u
+__device__ __forceinline__ u32 prefix_home_bucket(u64 c, u64 r, u64 kmask, u32 nbuckets)
+{
+    u32 flip;
+    const u64 hk = prefix_home_key(c, r, kmask, flip);
+    u32 b = (u32)hash_bucket(hk, nbuckets) + (flip ? EULER_FLIP_STRIDE : 0u);
+    return b >= nbuckets ? b % nbuckets : b;
 }
 
 // returns slot of `key` after inserting it if absent; EULER_NO_SLOT on overflow. cap % 4 == 0.

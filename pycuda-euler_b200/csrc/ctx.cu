@@ -84,7 +84,7 @@ int euler_ctx_create(int device, euler_ctx **out)
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return EULER_ERR_CUDA; }
     ctx->own_stream = true;
-    if (cudaMallocHost((void **)&ctx->h_pinned, 64 * sizeof(u64)) != cudaSuccess) { delete ctx; return EULER_ERR_NOMEM; }
+    if (cudaMallocHost((void **)&ctx->h_pinned, EULER_PINNED_WORDS * sizeof(u64)) != cudaSuccess) { delete ctx; return EULER_ERR_NOMEM; }
     for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->ev[i]);
     // keep stream-ordered temporaries cached between calls
     cudaMemPool_t pool;

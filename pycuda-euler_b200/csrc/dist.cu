@@ -518,8 +518,15 @@ __device__ __forceinline__ int bucket_claim_fresh(u64 *bucket_keys, const K4 &q,
     }
     return -1;
 }
+// home bucket of a received canonical l-mer: by the key, or (co-hashed tables, common.cuh) by its canonical prefix k-mer
+__device__ __forceinline__ u32 dist_home_bucket(u64 key, u32 cohash_l, u32 nbuckets)
+{
+    if (!cohash_l) return (u32)hash_bucket(key, nbuckets);
+    return prefix_home_bucket(key, revcomp64(key, cohash_l), key_mask_d(cohash_l - 1), nbuckets);
+}
 __global__ void __launch_bounds__(DB, 4) dist_count_keys_kernel(const u64 *__restrict__ keys_in, u64 n, u64 *__restrict__ tab_keys,
-                                                                 u32 *__restrict__ tab_cnt, u64 cap, u64 *__restrict__ stats)
+                                                                 u32 *__restrict__ tab_cnt, u64 cap, u32 cohash_l,
+                                                                 u64 *__restrict__ stats)
 {
     const u32 nbuckets = (u32)(cap / EULER_BUCKET);
     const u32 max_probe = nbuckets < 4096 ? nbuckets : 4096;
@@ -541,7 +548,7 @@ __global__ void __launch_bounds__(DB, 4) dist_count_keys_kernel(const u64 *__res
             const u64 idx = (it * 4 + i) * stride + t0;
             key[i] = idx < n ? ld_evict_first_u64(keys_in + idx, policy) : 0;
             if (idx < n) pend |= 1u << i;
-            bucket[i] = (u32)hash_bucket(key[i], nbuckets);
+            bucket[i] = dist_home_bucket(key[i], cohash_l, nbuckets);
         }
         u32 probes = 0;
         while (__any_sync(0xffffffffu, pend != 0)) {
@@ -569,13 +576,13 @@ __global__ void __launch_bounds__(DB, 4) dist_count_keys_kernel(const u64 *__res
     if (overflow) atomicOr((unsigned long long *)(stats + 2), 1ull);
 }
 
-int dist_count_keys(euler_ctx *ctx, const u64 *d_keys, u64 n, u64 *tab_keys, u32 *tab_cnt, u64 cap, u64 *d_stats)
+int dist_count_keys(euler_ctx *ctx, const u64 *d_keys, u64 n, u64 *tab_keys, u32 *tab_cnt, u64 cap, u32 cohash_l, u64 *d_stats)
 {
     if (!n) return EULER_OK;
     u64 grid = (u64)ctx->num_sms * 8;
     const u64 need = (n + DB * 4 - 1) / (DB * 4);
     if (grid > need) grid = need;
-    dist_count_keys_kernel<<<(unsigned)grid, DB, 0, ctx->stream>>>(d_keys, n, tab_keys, tab_cnt, cap, d_stats);
+    dist_count_keys_kernel<<<(unsigned)grid, DB, 0, ctx->stream>>>(d_keys, n, tab_keys, tab_cnt, cap, cohash_l, d_stats);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
@@ -592,14 +599,18 @@ int dist_count_keys(euler_ctx *ctx, const u64 *d_keys, u64 n, u64 *tab_keys, u32
 #define BK_ITEMS 16
 #define BK_TILE (BK_THREADS * BK_ITEMS)
 #define BK_MAXP 256
-__device__ __forceinline__ u32 key_part(u64 key, u32 nparts)
+__device__ __forceinline__ u32 key_part(u64 key, u32 nparts, u32 cohash_l)
 {
+    if (cohash_l) {
+        u32 flip;
+        key = prefix_home_key(key, revcomp64(key, cohash_l), key_mask_d(cohash_l - 1), flip);
+    }
     const u64 h = (key ^ (key >> 29)) * 0x9E3779B97F4A7C15ull;   // same mix as hash_bucket: parts are bucket ranges
     return (u32)(((h >> 32) * (u64)nparts) >> 32);
 }
 __global__ void __launch_bounds__(BK_THREADS) dist_block_keys_kernel(const u64 *__restrict__ in, u64 n, u32 nparts,
                                                                       u64 *__restrict__ cursors, u64 *__restrict__ out, u64 part_cap,
-                                                                      u64 *__restrict__ flags)
+                                                                      u32 cohash_l, u64 *__restrict__ flags)
 {
     __shared__ u64 stage[BK_TILE];
     __shared__ u32 hist[BK_MAXP], loff[BK_MAXP], fill[BK_MAXP], wsum[BK_THREADS / 32];
@@ -622,7 +633,7 @@ __global__ void __launch_bounds__(BK_THREADS) dist_block_keys_kernel(const u64 *
             const u32 i = j * BK_THREADS + tid;
             if (i < cnt) {
                 k[j] = ld_evict_first_u64(in + base + i, policy);
-                part[j] = key_part(k[j], nparts);
+                part[j] = key_part(k[j], nparts, cohash_l);
                 atomicAdd(&hist[part[j]], 1u);
             }
         }
@@ -653,7 +664,7 @@ __global__ void __launch_bounds__(BK_THREADS) dist_block_keys_kernel(const u64 *
         __syncthreads();
         for (u32 i = tid; i < cnt; i += BK_THREADS) {
             const u64 key = stage[i];
-            const u32 pp = key_part(key, nparts);
+            const u32 pp = key_part(key, nparts, cohash_l);
             const u64 at = gbase[pp] + (i - loff[pp]);
             if (at < part_cap) out[(u64)pp * part_cap + at] = key;
             else over = true;
@@ -663,14 +674,15 @@ __global__ void __launch_bounds__(BK_THREADS) dist_block_keys_kernel(const u64 *
     if (over) atomicOr((unsigned long long *)flags, 1ull);
 }
 
-int dist_block_keys(euler_ctx *ctx, const u64 *d_keys, u64 n, u32 nparts, u64 *d_cursors, u64 *d_out, u64 part_cap, u64 *d_flags)
+int dist_block_keys(euler_ctx *ctx, const u64 *d_keys, u64 n, u32 nparts, u64 *d_cursors, u64 *d_out, u64 part_cap, u32 cohash_l,
+                    u64 *d_flags)
 {
     if (!n) return EULER_OK;
     if (nparts > BK_MAXP) return euler_fail(ctx, EULER_ERR_ARG, "too many table parts");
     u64 grid = (u64)ctx->num_sms * 4;
     const u64 need = (n + BK_TILE - 1) / BK_TILE;
     if (grid > need) grid = need;
-    dist_block_keys_kernel<<<(unsigned)grid, BK_THREADS, 0, ctx->stream>>>(d_keys, n, nparts, d_cursors, d_out, part_cap, d_flags);
+    dist_block_keys_kernel<<<(unsigned)grid, BK_THREADS, 0, ctx->stream>>>(d_keys, n, nparts, d_cursors, d_out, part_cap, cohash_l, d_flags);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }

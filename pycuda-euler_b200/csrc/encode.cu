@@ -117,7 +117,8 @@ struct WinMin {
 // whole l-mer / k-mer of one read.  Keys are produced four at a time and probed right away, so the
 // live state is ~60 registers and the loop body stays inside the instruction cache.
 // W > 0: minimizer-ordered table (W = l - m + 1 m-mers per l-mer); W == 0: plain hash;
-// W < 0: minimizer-ordered with a per-window brute-force minimum (any l).
+// W == -1: minimizer-ordered with a per-window brute-force minimum (any l);
+// W == -2: plain hash of the canonical PREFIX k-mer (co-hashed with the vertex table, common.cuh).
 template <int W>
 __global__ void __launch_bounds__(CNT_BLOCK, 4) count_canonical_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
                                                                         const u32 *__restrict__ start_bits, u32 l,
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(CNT_BLOCK, 4) count_canonical_kernel(const uin
 #pragma unroll 1
         for (int b = 0; b < 4; b++) {
             u64 key[4];
+            u32 bucket[4];
             u32 pend = 0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -212,15 +214,16 @@ __global__ void __launch_bounds__(CNT_BLOCK, 4) count_canonical_kernel(const uin
                 const u64 fm = f & kmask;
                 key[i] = fm < rc ? fm : rc;
                 pend |= (ok ? 1u : 0u) << i;
+                if constexpr (W == -2) bucket[i] = prefix_home_bucket(key[i], fm < rc ? rc : fm, kmask >> 2, nbuckets);
             }
             // Probing proceeds in warp-uniform rounds: every round first issues the 256-bit bucket
             // loads of all still-pending keys (4 independent 32 B requests per lane in flight), then
             // resolves them, so lanes that need another bucket take it together.
-            u32 bucket[4];
             K4 q[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                if constexpr (W > 0) bucket[i] = (u32)home_from_score(key[i], s_win[(b * 4 + i) * CNT_BLOCK + threadIdx.x], nbuckets, th);
+                if constexpr (W == -2) { }
+                else if constexpr (W > 0) bucket[i] = (u32)home_from_score(key[i], s_win[(b * 4 + i) * CNT_BLOCK + threadIdx.x], nbuckets, th);
                 else if constexpr (W < 0) bucket[i] = (pend & (1u << i)) ? (u32)table_home(key[i], l, nbuckets, th) : 0u;
                 else bucket[i] = (u32)hash_bucket(key[i], nbuckets);
                 // L2 blocking knob: this launch only owns home buckets in [part_lo, part_hi)
@@ -275,7 +278,7 @@ int enc_count_canonical(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u3
     u64 parts = 1;
     const char *env = getenv("EULER_B200_COUNT_PARTS");
     if (env && atoi(env) > 0) parts = (u64)atoi(env);
-    const int W = th.span_nb ? (int)(l - th.m + 1) : 0;
+    const int W = th.span_nb ? (int)(l - th.m + 1) : (th.m == EULER_PREFIX_HOME ? -2 : 0);
     for (u64 p = 0; p < parts; p++) {
         const u64 nb = cap / EULER_BUCKET;
         const u64 lo = nb * p / parts, hi = nb * (p + 1) / parts;
@@ -285,6 +288,7 @@ int enc_count_canonical(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u3
     count_canonical_kernel<WW><<<g, CNT_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, tab_keys, \
                                                                  tab_cnt, cap, th, ntiles, d_stats, lo, hi, cw)
         if (W == 0) LAUNCH_CNT(0);
+        else if (W == -2) LAUNCH_CNT(-2);
         else if (W == 21) LAUNCH_CNT(21);   // l = 32 (k = 31), m = 12
         else if (W == 11) LAUNCH_CNT(11);   // l = 22 (k = 21), m = 12
         else LAUNCH_CNT(-1);                // any other l: per-window brute-force minimizer

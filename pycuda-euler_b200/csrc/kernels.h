@@ -114,9 +114,11 @@ int graph_vertices_fused(euler_ctx *ctx, const u32 *lcount, const u32 *ecount, c
 // d_counts: 18 u64 ([0..15] keys per destination (count pass), [16] N_l, [17] N_k)
 int dist_partition(euler_ctx *ctx, bool scatter, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u32 nranks,
                    u64 *d_counts, u64 *d_cursors, u64 *d_send, const u64 *d_seg_off, u64 seg_cap);
-int dist_count_keys(euler_ctx *ctx, const u64 *d_keys, u64 n, u64 *tab_keys, u32 *tab_cnt, u64 cap, u64 *d_stats);
+// cohash_l = l when the table is hashed by the canonical prefix k-mer (co-hashed tables), 0 = by the key
+int dist_count_keys(euler_ctx *ctx, const u64 *d_keys, u64 n, u64 *tab_keys, u32 *tab_cnt, u64 cap, u32 cohash_l, u64 *d_stats);
 // split keys into nparts runs of table-bucket ranges (out[part * part_cap + i]); d_cursors[nparts] = run lengths
-int dist_block_keys(euler_ctx *ctx, const u64 *d_keys, u64 n, u32 nparts, u64 *d_cursors, u64 *d_out, u64 part_cap, u64 *d_flags);
+int dist_block_keys(euler_ctx *ctx, const u64 *d_keys, u64 n, u32 nparts, u64 *d_cursors, u64 *d_out, u64 part_cap, u32 cohash_l,
+                    u64 *d_flags);
 int dist_vertex_insert(euler_ctx *ctx, const u64 *lt_keys, u64 lt_cap, u32 l, u64 *vt_keys, u64 vt_cap,
                        const unsigned char *own_flags, u64 *d_flags);
 int dist_lt_scan(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, u64 cap, u32 l, u32 rank, u32 nranks, u32 *base,

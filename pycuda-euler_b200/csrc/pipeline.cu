@@ -158,6 +158,15 @@ static u32 dist_block_min_mb()
     const char *e = getenv("EULER_B200_BLOCK_MB");
     return e ? (u32)atoi(e) : 512u;
 }
+// Co-hashed l-mer table (common.cuh).  Measured: on one GPU (config 2) the graph stage gains 0.15 ms and
+// the count kernel loses 0.14 ms (12 more instructions per key) -- a wash, so it is off there; with a
+// per-rank table far larger than L2 the graph stage gains 10 % (17.4 -> 15.6 ms on a 1 GB table), so the
+// partitioned path turns it on together with the L2 blocking.  EULER_B200_COHASH=0/1 overrides both.
+static bool use_cohash(bool dflt)
+{
+    const char *e = getenv("EULER_B200_COHASH");
+    return e ? atoi(e) != 0 : dflt;
+}
 static u64 cap_for(u64 n) { return round_up((u64)((double)(n < 64 ? 64 : n) / table_load()) + 1, 1024); }
 
 // l in 33..64: the same stages over two-word keys (wide.cu).  Correctness-first: one thread per read,
@@ -319,6 +328,7 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
             l2_window(ctx, P->lt.b.p, P->lt.bytes());
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
             lth = table_hash_for(lt_cap, k);
+            if (!lth.span_nb && use_cohash(false)) lth.m = EULER_PREFIX_HOME;
             EULER_TRY(enc_count_canonical(ctx, P->d_buf, B, P->start_bits.ptr(), l, P->lt.keys(), P->lt.cnt(), lt_cap,
                                           lth, P->stats.ptr()));
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
@@ -923,8 +933,9 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
         EULER_TRY(graph_table_clear(ctx, P->vt_keys.ptr(), nullptr, vt_cap));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
         // tables far larger than L2: regroup the keys by table region first (dist.cu, "L2 blocking")
-        bool blocked = false;
         const u64 table_bytes = lt_cap * 12, block_min = (u64)dist_block_min_mb() << 20;
+        const u32 cohash_l = use_cohash(block_min && table_bytes >= block_min) ? l : 0u;
+        bool blocked = false;
         if (block_min && table_bytes >= block_min && nkeys >= 4096) {
             u32 nparts = (u32)((table_bytes + (48ull << 20) - 1) / (48ull << 20));
             if (nparts > 256) nparts = 256;
@@ -934,7 +945,7 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
                 CUDA_TRY(ctx, cudaMemsetAsync(P->blk_cur.ptr(), 0, (256 + 8) * sizeof(u64), s));
                 for (u32 r = 0; r < nregions; r++)
                     EULER_TRY(dist_block_keys(ctx, (const u64 *)d_keys + (u64)r * region_stride, region_counts[r], nparts,
-                                              P->blk_cur.ptr(), P->blk_keys.ptr(), part_cap, P->blk_cur.ptr() + 256));
+                                              P->blk_cur.ptr(), P->blk_keys.ptr(), part_cap, cohash_l, P->blk_cur.ptr() + 256));
                 u64 flag = 0;
                 EULER_TRY(read_u64s(ctx, P->blk_cur.ptr(), cur, (int)nparts));
                 EULER_TRY(read_u64(ctx, P->blk_cur.ptr() + 256, &flag));
@@ -942,7 +953,7 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
                     blocked = true;
                     for (u32 q = 0; q < nparts; q++)
                         EULER_TRY(dist_count_keys(ctx, P->blk_keys.ptr() + (u64)q * part_cap, cur[q], P->lt.keys(), P->lt.cnt(), lt_cap,
-                                                  P->stats.ptr()));
+                                                  cohash_l, P->stats.ptr()));
                     launches += nregions + nparts;
                 }
             } else {
@@ -952,7 +963,7 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
         if (!blocked)
             for (u32 r = 0; r < nregions; r++)
                 EULER_TRY(dist_count_keys(ctx, (const u64 *)d_keys + (u64)r * region_stride, region_counts[r], P->lt.keys(),
-                                          P->lt.cnt(), lt_cap, P->stats.ptr()));
+                                          P->lt.cnt(), lt_cap, cohash_l, P->stats.ptr()));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
         EULER_TRY(dist_lt_scan(ctx, P->lt.keys(), P->lt.cnt(), lt_cap, l, rank, nranks, P->lt_base.ptr(),
                                P->lt_eoff.ptr(), P->lt_own.ptr(), P->stats.ptr() + 3));

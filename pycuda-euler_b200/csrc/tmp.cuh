@@ -39,6 +39,7 @@ static inline int read_u64(euler_ctx *ctx, const u64 *d, u64 *h)
 }
 static inline int read_u64s(euler_ctx *ctx, const u64 *d, u64 *h, int n)
 {
+    if (n < 0 || n > EULER_PINNED_WORDS) return euler_fail(ctx, EULER_ERR_ARG, "read_u64s: %d words exceed the pinned buffer", n);
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_pinned, d, n * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < n; i++) h[i] = ctx->h_pinned[i];

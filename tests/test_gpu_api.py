@@ -255,7 +255,7 @@ def test_errors_are_loud(ctx):
     import _native as N
     buf, off = oracle.pack_reads(["ACGTACGTACGT"])
     with pytest.raises(N.EulerError):
-        ctx.run_host(buf, off, 40)          # l > 32 is not supported by the u64 path
+        ctx.run_host(buf, off, 65)          # l > 64 does not fit two key words
     with pytest.raises(N.EulerError):
         ctx.run_host(buf, off, 1)
     with pytest.raises(N.EulerError):

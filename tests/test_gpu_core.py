@@ -237,11 +237,12 @@ def test_pipeline_device_resident_synthetic(ctx):
     assert np.array_equal(ctx.download(N.ART_LMER_VALUES), g.lvals)
 
 
-@pytest.mark.parametrize("knob", ["EULER_B200_MINHASH", "EULER_B200_PACKED"])
+@pytest.mark.parametrize("knob", ["EULER_B200_MINHASH", "EULER_B200_PACKED", "EULER_B200_COHASH"])
 def test_opt_in_table_variants_give_the_same_graph(knob):
     """EULER_B200_MINHASH=1 (minimizer-ordered homes; rolling-minimum kernels for l = 32 / 22, the
-    brute-force one otherwise) and EULER_B200_PACKED=1 (packed quotient count table, count-wrap side
-    table) must not change any artefact.  The knobs are read once per process, so this runs in a
+    brute-force one otherwise), EULER_B200_PACKED=1 (packed quotient count table, count-wrap side
+    table) and EULER_B200_COHASH=1 (l-mer table hashed by the canonical prefix k-mer) must not change
+    any artefact.  The knobs are read once per process, so this runs in a
     child process."""
     import os
     import subprocess
