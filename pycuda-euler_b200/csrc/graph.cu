@@ -512,32 +512,90 @@ int graph_edges_fused(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, con
 }
 
 // ---- vertex pass: pair scan of (lcount, ecount) that also writes the EulerVertex records ---------
-// scans pydebruijn.py:560-567 + setupVertices :280-294 in one read of the degree slots
-struct VertexScanPolicy {
-    typedef u64 T;
-    const u32 *lcount, *ecount;
-    const u64 *vkeys;
-    u32 *lstart, *estart;
-    euler_vertex *ev;
-    __device__ __forceinline__ u64 load(u64 i) const { return ((u64)ecount[i] << 32) | lcount[i]; }
-    __device__ __forceinline__ void store(u64 i, u64 ex, u64 v, bool valid) const
-    {
-        if (valid) { lstart[i] = (u32)ex; estart[i] = (u32)(ex >> 32); }
-        // the four slots of a vertex sit in four adjacent lanes of this row
-        u64 sum = v + __shfl_xor_sync(0xffffffffu, v, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        if (valid && (i & 3) == 0) {
+// scans pydebruijn.py:560-567 + setupVertices :280-294 in one read of the degree slots.  The scanned
+// item is a VERTEX: its four lcount and four ecount slots are one 16-byte load each, the four starts
+// one 16-byte store each, so a warp row moves 512 B per array and the warp scan runs once per 128 slots.
+#define VS_ROWS 4
+#define VS_TILE (SCAN_THREADS * VS_ROWS)
+__global__ void __launch_bounds__(SCAN_THREADS, 3) vertex_scan_kernel(const uint4 *__restrict__ lcount4, const uint4 *__restrict__ ecount4,
+                                                                      const u64 *__restrict__ vkeys, u64 nv,
+                                                                      uint4 *__restrict__ lstart4, uint4 *__restrict__ estart4,
+                                                                      euler_vertex *__restrict__ ev, ScanState *state, u64 *counter,
+                                                                      u64 ntiles)
+{
+    __shared__ u64 s_tile;
+    __shared__ u64 s_warp[SCAN_WARPS];
+    __shared__ u64 s_prefix;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(counter, 1ull);
+    __syncthreads();
+    const u64 tile = s_tile;
+    const u64 base = tile * (u64)VS_TILE + (u64)warp * (32 * VS_ROWS) + lane;
+    uint4 lc[VS_ROWS], ec[VS_ROWS];
+    u64 v[VS_ROWS];
+    u64 carry = 0;
+#pragma unroll
+    for (int r = 0; r < VS_ROWS; r++) {
+        const u64 idx = base + (u64)r * 32;
+        lc[r] = idx < nv ? lcount4[idx] : make_uint4(0, 0, 0, 0);
+        ec[r] = idx < nv ? ecount4[idx] : make_uint4(0, 0, 0, 0);
+        v[r] = ((u64)(ec[r].x + ec[r].y + ec[r].z + ec[r].w) << 32) | (u64)(lc[r].x + lc[r].y + lc[r].z + lc[r].w);
+        carry += v[r];
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) carry += __shfl_xor_sync(0xffffffffu, carry, d);
+    if (lane == 0) s_warp[warp] = carry;
+    __syncthreads();
+    u64 warp_off = 0, block_sum = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_WARPS; w++) {
+        const u64 t = s_warp[w];
+        if (w < warp) warp_off += t;
+        block_sum += t;
+    }
+    if (warp == 0) {
+        const u64 prefix = scan_lookback(state, tile, block_sum, lane, ntiles, (u64 *)nullptr);
+        if (lane == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    u64 off = s_prefix + warp_off;
+#pragma unroll
+    for (int r = 0; r < VS_ROWS; r++) {
+        const u64 idx = base + (u64)r * 32;
+        u64 inc = v[r];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u64 t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const u64 ex = off + inc - v[r];
+        off += __shfl_sync(0xffffffffu, inc, 31);
+        if (idx < nv) {
+            const u32 l0 = (u32)ex, e0 = (u32)(ex >> 32);
+            lstart4[idx] = make_uint4(l0, l0 + lc[r].x, l0 + lc[r].x + lc[r].y, l0 + lc[r].x + lc[r].y + lc[r].z);
+            estart4[idx] = make_uint4(e0, e0 + ec[r].x, e0 + ec[r].x + ec[r].y, e0 + ec[r].x + ec[r].y + ec[r].z);
             euler_vertex x;
-            x.vid = vkeys[i >> 2];
-            x.lp = (u32)ex; x.lcount = (u32)sum;
-            x.ep = (u32)(ex >> 32); x.ecount = (u32)(sum >> 32);
-            ev[i >> 2] = x;
+            x.vid = vkeys[idx];
+            x.lp = l0; x.lcount = (u32)v[r];
+            x.ep = e0; x.ecount = (u32)(v[r] >> 32);
+            ev[idx] = x;
         }
     }
-};
+}
 
 int graph_vertices_fused(euler_ctx *ctx, const u32 *lcount, const u32 *ecount, const u64 *vkeys, u64 nv, u32 *lstart,
                          u32 *estart, euler_vertex *ev)
 {
-    return scan_run(ctx, VertexScanPolicy{lcount, ecount, vkeys, lstart, estart, ev}, 4 * nv, (u64 *)nullptr);
+    if (!nv) return EULER_OK;
+    if ((((uintptr_t)lcount | (uintptr_t)ecount | (uintptr_t)lstart | (uintptr_t)estart) & 15) != 0)
+        return euler_fail(ctx, EULER_ERR_ARG, "degree-slot arrays must be 16-byte aligned");
+    const u64 ntiles = (nv + VS_TILE - 1) / VS_TILE;
+    ScanState *state = nullptr;
+    u64 *counter = nullptr;
+    EULER_TRY(scan_state_reserve(ctx, ntiles, &state, &counter));
+    CUDA_TRY(ctx, cudaMemsetAsync(state, 0, (ntiles + 1) * sizeof(ScanState), ctx->stream));
+    vertex_scan_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, ctx->stream>>>((const uint4 *)lcount, (const uint4 *)ecount, vkeys, nv,
+                                                                            (uint4 *)lstart, (uint4 *)estart, ev, state, counter, ntiles);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
 }

@@ -40,6 +40,44 @@ __device__ __forceinline__ void st_state(ScanState *p, u64 flag, u64 value)
     asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(flag), "l"(value) : "memory");
 }
 
+// Decoupled look-back, run by one full warp of the block that owns `tile`: publishes the tile's
+// aggregate, sums the predecessors' states back to the nearest inclusive prefix, publishes the
+// inclusive prefix and returns the exclusive one (all lanes).  The last tile writes *total.
+__device__ __forceinline__ u64 scan_lookback(ScanState *state, u64 tile, u64 block_sum, int lane, u64 ntiles, u64 *total)
+{
+    u64 prefix = 0;
+    if (tile == 0) {
+        if (lane == 0) st_state(state, SCAN_ST_INC, block_sum);
+    } else {
+        if (lane == 0) st_state(state + tile, SCAN_ST_AGG, block_sum);
+        long long look = (long long)tile - 1;
+        while (true) {
+            const long long idx = look - lane;
+            ScanState s;
+            if (idx >= 0) {
+                do { s = ld_state(state + idx); } while (s.flag == 0);
+            } else {
+                s.flag = SCAN_ST_INC;  // virtual tile before tile 0
+                s.value = 0;
+            }
+            const unsigned inc_mask = __ballot_sync(0xffffffffu, s.flag == SCAN_ST_INC);
+            u64 val = s.value;
+            if (inc_mask) {
+                const int first = __ffs(inc_mask) - 1;
+                if (lane > first) val = 0;
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+            prefix += val;
+            if (inc_mask) break;
+            look -= 32;
+        }
+        if (lane == 0) st_state(state + tile, SCAN_ST_INC, prefix + block_sum);
+    }
+    if (lane == 0 && tile == ntiles - 1 && total) *total = prefix + block_sum;
+    return prefix;
+}
+
 // state[0..ntiles): tile descriptors; counter: dynamic tile index; all zero on entry.
 template <typename P>
 __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_exclusive_kernel(P p, u64 n, ScanState *state, u64 *counter,
@@ -82,39 +120,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_exclusive_kernel(P p, u6
 
     // decoupled look-back by warp 0
     if (warp == 0) {
-        u64 prefix = 0;
-        if (tile == 0) {
-            if (lane == 0) st_state(state, SCAN_ST_INC, block_sum);
-        } else {
-            if (lane == 0) st_state(state + tile, SCAN_ST_AGG, block_sum);
-            long long look = (long long)tile - 1;
-            while (true) {
-                const long long idx = look - lane;
-                ScanState s;
-                if (idx >= 0) {
-                    do { s = ld_state(state + idx); } while (s.flag == 0);
-                } else {
-                    s.flag = SCAN_ST_INC;  // virtual tile before tile 0
-                    s.value = 0;
-                }
-                const unsigned inc_mask = __ballot_sync(0xffffffffu, s.flag == SCAN_ST_INC);
-                u64 val = s.value;
-                if (inc_mask) {
-                    const int first = __ffs(inc_mask) - 1;
-                    if (lane > first) val = 0;
-                }
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-                prefix += val;
-                if (inc_mask) break;
-                look -= 32;
-            }
-            if (lane == 0) st_state(state + tile, SCAN_ST_INC, prefix + block_sum);
-        }
-        if (lane == 0) {
-            s_prefix = prefix;
-            if (tile == ntiles - 1 && total) *total = prefix + block_sum;
-        }
+        const u64 prefix = scan_lookback(state, tile, block_sum, lane, ntiles, total);
+        if (lane == 0) s_prefix = prefix;
     }
     __syncthreads();
     u64 off = s_prefix + warp_off;
