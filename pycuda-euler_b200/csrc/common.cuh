@@ -252,6 +252,29 @@ __device__ __forceinline__ u32 prefix_home_bucket(u64 c, u64 r, u64 kmask, u32 n
     return b >= nbuckets ? b % nbuckets : b;
 }
 
+// ---- degree-slot writes of the edge kernels ----------------------------------------------------------
+// Reference layout: lcount[4 v + base], ecount[4 v + base] (pydebruijn.py:107-141) -- four scattered
+// 4-byte writes into four different sectors per canonical l-mer.  Paired layout (slot-order ids, where
+// the two strands of a vertex have adjacent ids): one 32-byte region per vertex id holding
+// [lcount(v) | ecount(partner(v))], partner = the other strand (itself for a palindrome).  The two
+// prefix-side writes of an l-mer (lcount of prefix(c), ecount of rc(prefix(c))) then share one sector and
+// so do the two suffix-side writes; the vertex pass (graph.cu) reads the regions back and writes the
+// reference arrays coalesced.
+struct DegOut {
+    u32 *lcount, *ecount;   // reference layout (used when deg == NULL)
+    u32 *deg;               // paired layout: u32[8 V]
+};
+__device__ __forceinline__ void deg_put_l(const DegOut &d, u32 v, u32 slot, u32 m)
+{
+    if (d.deg) d.deg[8ull * v + slot] = m;
+    else d.lcount[4ull * v + slot] = m;
+}
+__device__ __forceinline__ void deg_put_e(const DegOut &d, u32 v, u32 partner, u32 slot, u32 m)
+{
+    if (d.deg) d.deg[8ull * partner + 4u + slot] = m;
+    else d.ecount[4ull * v + slot] = m;
+}
+
 // returns slot of `key` after inserting it if absent; EULER_NO_SLOT on overflow. cap % 4 == 0.
 __device__ __forceinline__ u64 table_insert_at(u64 *keys, u64 cap, u64 key, u64 home, u64 max_probe)
 {

@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(DB) dist_edges_kernel(const u64 *__restrict__ 
                                                          VertexTable vt, const unsigned char *__restrict__ own_flags,
                                                          u64 *__restrict__ lkeys,
                                                          u32 *__restrict__ lvals, u32 *__restrict__ loffs, u32 *__restrict__ ev1,
-                                                         u32 *__restrict__ ev2, u32 *__restrict__ lcount, u32 *__restrict__ ecount)
+                                                         u32 *__restrict__ ev2, DegOut dg)
 {
     const u64 slot = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= cap) return;
@@ -794,25 +794,25 @@ __global__ void __launch_bounds__(DB) dist_edges_kernel(const u64 *__restrict__ 
     const u32 first_c = (u32)((c >> (2 * k)) & 3), first_r = (u32)((r >> (2 * k)) & 3);
     if (own_p) {  // strand c is homed here (leaves p); rc(c) enters rc(p), which is ours too
         lkeys[idx] = c; lvals[idx] = m0; loffs[idx] = eo; ev1[idx] = id_p; ev2[idx] = id_s;
-        lcount[4ull * id_p + (u32)(c & 3)] = m0;
-        if (!pal) ecount[4ull * id_rp + first_r] = n;
+        deg_put_l(dg, id_p, (u32)(c & 3), m0);
+        if (!pal) deg_put_e(dg, id_rp, id_p, first_r, n);
         idx++; eo += m0;
     }
     if (own_s) {  // c enters s (ours); rc(c) leaves rc(s) and is homed here
-        ecount[4ull * id_s + first_c] = m0;
+        deg_put_e(dg, id_s, id_rs, first_c, m0);
         if (!pal) {
             lkeys[idx] = r; lvals[idx] = n; loffs[idx] = eo; ev1[idx] = id_rs; ev2[idx] = id_rp;
-            lcount[4ull * id_rs + (u32)(r & 3)] = n;
+            deg_put_l(dg, id_rs, (u32)(r & 3), n);
         }
     }
 }
 
 int dist_edges(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, const u32 *base, const u32 *eoff, u64 cap, u32 l,
                const VertexTable &vt, const unsigned char *own_flags, u64 *lkeys, u32 *lvals, u32 *loffs, u32 *ev1, u32 *ev2,
-               u32 *lcount, u32 *ecount)
+               u32 *lcount, u32 *ecount, u32 *deg)
 {
     dist_edges_kernel<<<grid_for(cap, DB), DB, 0, ctx->stream>>>(lt_keys, lt_cnt, base, eoff, cap, l, vt, own_flags, lkeys, lvals,
-                                                                 loffs, ev1, ev2, lcount, ecount);
+                                                                 loffs, ev1, ev2, DegOut{lcount, ecount, deg});
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }

@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(GB) edges_fused_kernel(const u64 *__restrict__
                                                           const u32 *__restrict__ base, const u32 *__restrict__ eoff, u64 cap,
                                                           u32 l, VertexTable vt, u64 *__restrict__ lkeys, u32 *__restrict__ lvals,
                                                           u32 *__restrict__ loffs, u32 *__restrict__ ev1, u32 *__restrict__ ev2,
-                                                          u32 *__restrict__ lcount, u32 *__restrict__ ecount)
+                                                          DegOut dg)
 {
     const u64 slot = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= cap) return;
@@ -492,21 +492,22 @@ __global__ void __launch_bounds__(GB) edges_fused_kernel(const u64 *__restrict__
     const u32 id_s = (s == cs) ? s0 : s1, id_rs = (s == cs) ? s1 : s0;
     const u32 m0 = pal ? 2u * n : n;
     lkeys[idx] = c; lvals[idx] = m0; loffs[idx] = eo; ev1[idx] = id_p; ev2[idx] = id_s;
-    lcount[4ull * id_p + (u32)(c & 3)] = m0;
-    ecount[4ull * id_s + (u32)((c >> (2 * k)) & 3)] = m0;
+    deg_put_l(dg, id_p, (u32)(c & 3), m0);
+    deg_put_e(dg, id_s, id_rs, (u32)((c >> (2 * k)) & 3), m0);
     if (!pal) {  // reverse strand: rc(c) runs from rc(suffix c) to rc(prefix c)
         lkeys[idx + 1] = r; lvals[idx + 1] = n; loffs[idx + 1] = eo + n; ev1[idx + 1] = id_rs; ev2[idx + 1] = id_rp;
-        lcount[4ull * id_rs + (u32)(r & 3)] = n;
-        ecount[4ull * id_rp + (u32)((r >> (2 * k)) & 3)] = n;
+        deg_put_l(dg, id_rs, (u32)(r & 3), n);
+        deg_put_e(dg, id_rp, id_p, (u32)((r >> (2 * k)) & 3), n);
     }
 }
 
 int graph_edges_fused(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, const u32 *base, const u32 *eoff, u64 cap,
                       u32 l, const VertexTable &vt, u64 *lkeys, u32 *lvals, u32 *loffs, u32 *ev1, u32 *ev2, u32 *lcount,
-                      u32 *ecount)
+                      u32 *ecount, u32 *deg)
 {
+    if (deg && vt.id1) return euler_fail(ctx, EULER_ERR_ARG, "paired degree layout needs slot-order ids");
     edges_fused_kernel<<<grid_for(cap, GB), GB, 0, ctx->stream>>>(lt_keys, lt_cnt, base, eoff, cap, l, vt, lkeys, lvals, loffs,
-                                                                  ev1, ev2, lcount, ecount);
+                                                                  ev1, ev2, DegOut{lcount, ecount, deg});
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
@@ -517,7 +518,13 @@ int graph_edges_fused(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, con
 // one 16-byte store each, so a warp row moves 512 B per array and the warp scan runs once per 128 slots.
 #define VS_ROWS 4
 #define VS_TILE (SCAN_THREADS * VS_ROWS)
+// PAIRED: the degree slots come from the paired regions (common.cuh, DegOut): region(v) = [lcount(v) |
+// ecount(partner(v))]; ecount(v) is fetched from the partner's region -- the neighbouring lane, except
+// across a row boundary -- and the reference arrays lcount / ecount are written here, coalesced.
+template <bool PAIRED>
 __global__ void __launch_bounds__(SCAN_THREADS, 3) vertex_scan_kernel(const uint4 *__restrict__ lcount4, const uint4 *__restrict__ ecount4,
+                                                                      const uint4 *__restrict__ deg4, uint4 *__restrict__ lcount_out,
+                                                                      uint4 *__restrict__ ecount_out, u32 k,
                                                                       const u64 *__restrict__ vkeys, u64 nv,
                                                                       uint4 *__restrict__ lstart4, uint4 *__restrict__ estart4,
                                                                       euler_vertex *__restrict__ ev, ScanState *state, u64 *counter,
@@ -537,8 +544,29 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) vertex_scan_kernel(const uint
 #pragma unroll
     for (int r = 0; r < VS_ROWS; r++) {
         const u64 idx = base + (u64)r * 32;
-        lc[r] = idx < nv ? lcount4[idx] : make_uint4(0, 0, 0, 0);
-        ec[r] = idx < nv ? ecount4[idx] : make_uint4(0, 0, 0, 0);
+        if (!PAIRED) {
+            lc[r] = idx < nv ? lcount4[idx] : make_uint4(0, 0, 0, 0);
+            ec[r] = idx < nv ? ecount4[idx] : make_uint4(0, 0, 0, 0);
+        } else {
+            uint4 mine = make_uint4(0, 0, 0, 0);   // ecount(partner(idx)), parked in my region
+            long long partner = (long long)idx;
+            lc[r] = mine;
+            if (idx < nv) {
+                lc[r] = deg4[2 * idx];
+                mine = deg4[2 * idx + 1];
+                const u64 key = vkeys[idx], rk = revcomp64(key, k);
+                partner += key < rk ? 1 : (key > rk ? -1 : 0);
+            }
+            const int src = lane + (int)(partner - (long long)idx);
+            const bool in_row = src >= 0 && src < 32;
+            const int s2 = in_row ? src : lane;
+            ec[r].x = __shfl_sync(0xffffffffu, mine.x, s2);
+            ec[r].y = __shfl_sync(0xffffffffu, mine.y, s2);
+            ec[r].z = __shfl_sync(0xffffffffu, mine.z, s2);
+            ec[r].w = __shfl_sync(0xffffffffu, mine.w, s2);
+            if (!in_row && idx < nv) ec[r] = deg4[2 * (u64)partner + 1];
+            if (idx < nv) { lcount_out[idx] = lc[r]; ecount_out[idx] = ec[r]; }
+        }
         v[r] = ((u64)(ec[r].x + ec[r].y + ec[r].z + ec[r].w) << 32) | (u64)(lc[r].x + lc[r].y + lc[r].z + lc[r].w);
         carry += v[r];
     }
@@ -583,19 +611,38 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) vertex_scan_kernel(const uint
     }
 }
 
-int graph_vertices_fused(euler_ctx *ctx, const u32 *lcount, const u32 *ecount, const u64 *vkeys, u64 nv, u32 *lstart,
-                         u32 *estart, euler_vertex *ev)
+static int vertices_launch(euler_ctx *ctx, bool paired, const u32 *lcount, const u32 *ecount, const u32 *deg, u32 k, const u64 *vkeys,
+                           u64 nv, u32 *lstart, u32 *estart, euler_vertex *ev)
 {
     if (!nv) return EULER_OK;
-    if ((((uintptr_t)lcount | (uintptr_t)ecount | (uintptr_t)lstart | (uintptr_t)estart) & 15) != 0)
+    if ((((uintptr_t)lcount | (uintptr_t)ecount | (uintptr_t)lstart | (uintptr_t)estart | (uintptr_t)deg) & 15) != 0)
         return euler_fail(ctx, EULER_ERR_ARG, "degree-slot arrays must be 16-byte aligned");
     const u64 ntiles = (nv + VS_TILE - 1) / VS_TILE;
     ScanState *state = nullptr;
     u64 *counter = nullptr;
     EULER_TRY(scan_state_reserve(ctx, ntiles, &state, &counter));
     CUDA_TRY(ctx, cudaMemsetAsync(state, 0, (ntiles + 1) * sizeof(ScanState), ctx->stream));
-    vertex_scan_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, ctx->stream>>>((const uint4 *)lcount, (const uint4 *)ecount, vkeys, nv,
-                                                                            (uint4 *)lstart, (uint4 *)estart, ev, state, counter, ntiles);
+    if (paired)
+        vertex_scan_kernel<true><<<(unsigned)ntiles, SCAN_THREADS, 0, ctx->stream>>>(
+            nullptr, nullptr, (const uint4 *)deg, (uint4 *)lcount, (uint4 *)ecount, k, vkeys, nv, (uint4 *)lstart, (uint4 *)estart, ev,
+            state, counter, ntiles);
+    else
+        vertex_scan_kernel<false><<<(unsigned)ntiles, SCAN_THREADS, 0, ctx->stream>>>(
+            (const uint4 *)lcount, (const uint4 *)ecount, nullptr, nullptr, nullptr, k, vkeys, nv, (uint4 *)lstart, (uint4 *)estart, ev,
+            state, counter, ntiles);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
+}
+
+int graph_vertices_fused(euler_ctx *ctx, const u32 *lcount, const u32 *ecount, const u64 *vkeys, u64 nv, u32 *lstart,
+                         u32 *estart, euler_vertex *ev)
+{
+    return vertices_launch(ctx, false, lcount, ecount, nullptr, 0, vkeys, nv, lstart, estart, ev);
+}
+
+// same from the paired regions `deg` (u32[8 nv]); also writes the reference arrays lcount / ecount
+int graph_vertices_paired(euler_ctx *ctx, const u32 *deg, u32 k, const u64 *vkeys, u64 nv, u32 *lcount, u32 *ecount, u32 *lstart,
+                          u32 *estart, euler_vertex *ev)
+{
+    return vertices_launch(ctx, true, lcount, ecount, deg, k, vkeys, nv, lstart, estart, ev);
 }

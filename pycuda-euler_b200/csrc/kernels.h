@@ -106,9 +106,11 @@ int graph_lt_scan(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, u64 cap
                   u64 *d_total_packed);
 int graph_edges_fused(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, const u32 *base, const u32 *eoff, u64 cap,
                       u32 l, const VertexTable &vt, u64 *lkeys, u32 *lvals, u32 *loffs, u32 *ev1, u32 *ev2, u32 *lcount,
-                      u32 *ecount);
+                      u32 *ecount, u32 *deg = nullptr);   // deg != NULL: paired degree regions (common.cuh) instead of lcount / ecount
 int graph_vertices_fused(euler_ctx *ctx, const u32 *lcount, const u32 *ecount, const u64 *vkeys, u64 nv, u32 *lstart,
                          u32 *estart, euler_vertex *ev);
+int graph_vertices_paired(euler_ctx *ctx, const u32 *deg, u32 k, const u64 *vkeys, u64 nv, u32 *lcount, u32 *ecount, u32 *lstart,
+                          u32 *estart, euler_vertex *ev);
 
 // ---- dist.cu (k-mer-space partition across GPUs)
 // d_counts: 18 u64 ([0..15] keys per destination (count pass), [16] N_l, [17] N_k)
@@ -125,7 +127,7 @@ int dist_lt_scan(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, u64 cap,
                  u32 *eoff, unsigned char *own_flags, u64 *d_total_packed);
 int dist_edges(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, const u32 *base, const u32 *eoff, u64 cap, u32 l,
                const VertexTable &vt, const unsigned char *own_flags, u64 *lkeys, u32 *lvals, u32 *loffs, u32 *ev1, u32 *ev2,
-               u32 *lcount, u32 *ecount);
+               u32 *lcount, u32 *ecount, u32 *deg = nullptr);
 
 // ---- packed.cu (L2-sized quotient table for the count kernel)
 int enc_count_packed(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u64 *tab, u32 b,

@@ -71,6 +71,7 @@ struct Pipeline {
     // graph artefacts
     DevArr<u64> lkeys, vkeys;
     DevArr<u32> lvals, loffs, ev1, ev2, lcount, ecount, lstart, estart;
+    DevArr<u32> deg;  // paired degree regions u32[8 V] (common.cuh, DegOut) of the slot-order fast paths
     DevArr<euler_vertex> ev;
     DevArr<euler_edge> ee;
     DevArr<u32> lev, ent;
@@ -106,7 +107,7 @@ void pipeline_destroy(Pipeline *p)
     p->lcount.free(); p->ecount.free(); p->lstart.free(); p->estart.free(); p->ev.free(); p->ee.free();
     if (p->recv_buf) cudaFree(p->recv_buf);
     p->lev.free(); p->ent.free(); p->sort_k.free(); p->sort_v.free(); p->sort_hist.free();
-    p->blk_keys.free(); p->blk_cur.free();
+    p->blk_keys.free(); p->blk_cur.free(); p->deg.free();
     p->wlt_keys.free(); p->wvt_keys.free(); p->wlt_cnt.free(); p->lkeys_hi.free(); p->vkeys_hi.free(); p->tf.free();
     delete p;
 }
@@ -360,8 +361,14 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
     EULER_TRY(P->lstart.reserve(ctx, 4 * V + 4)); EULER_TRY(P->estart.reserve(ctx, 4 * V + 4));
     EULER_TRY(P->ev.reserve(ctx, V));
 
-    CUDA_TRY(ctx, cudaMemsetAsync(P->lcount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
-    CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+    const bool paired = !(flags & EULER_RUN_CANONICAL_IDS);   // slot-order ids: the strands of a vertex have adjacent ids
+    if (paired) {
+        EULER_TRY(P->deg.reserve(ctx, 8 * V + 8));
+        CUDA_TRY(ctx, cudaMemsetAsync(P->deg.ptr(), 0, (8 * V + 8) * sizeof(u32), s));
+    } else {
+        CUDA_TRY(ctx, cudaMemsetAsync(P->lcount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+        CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+    }
     EULER_TRY(graph_compact_vertices(ctx, P->vt_keys.ptr(), P->vt_id0.ptr(), vt_cap, k, P->vkeys.ptr()));
     VertexTable vt = {P->vt_keys.ptr(), P->vt_id0.ptr(), nullptr, vt_cap, k, vth};
     if (flags & EULER_RUN_CANONICAL_IDS) {
@@ -387,12 +394,16 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
         // fast path: ids in table-slot order, one fused pass over the l-mer table
         EULER_TRY(graph_edges_fused(ctx, P->lt.keys(), P->lt.cnt(), P->lt_base.ptr(), P->lt_eoff.ptr(), lt_cap, l, vt,
                                     P->lkeys.ptr(), P->lvals.ptr(), P->loffs.ptr(), P->ev1.ptr(), P->ev2.ptr(),
-                                    P->lcount.ptr(), P->ecount.ptr()));
+                                    P->lcount.ptr(), P->ecount.ptr(), P->deg.ptr()));
         launches += 2;
     }
     // scans of the degree slots + EulerVertex records in one pass
-    EULER_TRY(graph_vertices_fused(ctx, P->lcount.ptr(), P->ecount.ptr(), P->vkeys.ptr(), V, P->lstart.ptr(), P->estart.ptr(),
-                                   P->ev.ptr()));
+    if (paired)
+        EULER_TRY(graph_vertices_paired(ctx, P->deg.ptr(), k, P->vkeys.ptr(), V, P->lcount.ptr(), P->ecount.ptr(), P->lstart.ptr(),
+                                        P->estart.ptr(), P->ev.ptr()));
+    else
+        EULER_TRY(graph_vertices_fused(ctx, P->lcount.ptr(), P->ecount.ptr(), P->vkeys.ptr(), V, P->lstart.ptr(), P->estart.ptr(),
+                                       P->ev.ptr()));
     launches += 1;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
     if (flags & EULER_RUN_EXPAND_EDGES) {
@@ -993,16 +1004,21 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
     EULER_TRY(P->lcount.reserve(ctx, 4 * V + 4)); EULER_TRY(P->ecount.reserve(ctx, 4 * V + 4));
     EULER_TRY(P->lstart.reserve(ctx, 4 * V + 4)); EULER_TRY(P->estart.reserve(ctx, 4 * V + 4));
     EULER_TRY(P->ev.reserve(ctx, V));
-    CUDA_TRY(ctx, cudaMemsetAsync(P->lcount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
-    CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+    if (!big) {   // paired degree regions: two sectors per l-mer instead of four (common.cuh, DegOut)
+        EULER_TRY(P->deg.reserve(ctx, 8 * V + 8));
+        CUDA_TRY(ctx, cudaMemsetAsync(P->deg.ptr(), 0, (8 * V + 8) * sizeof(u32), s));
+    } else {
+        CUDA_TRY(ctx, cudaMemsetAsync(P->lcount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+        CUDA_TRY(ctx, cudaMemsetAsync(P->ecount.ptr(), 0, (4 * V + 4) * sizeof(u32), s));
+    }
     EULER_TRY(graph_compact_vertices(ctx, P->vt_keys.ptr(), P->vt_id0.ptr(), vt_cap, k, P->vkeys.ptr()));
     VertexTable vt = {P->vt_keys.ptr(), P->vt_id0.ptr(), nullptr, vt_cap, k, TableHash{0, 0}};
     EULER_TRY(dist_edges(ctx, P->lt.keys(), P->lt.cnt(), P->lt_base.ptr(), P->lt_eoff.ptr(), lt_cap, l, vt, P->lt_own.ptr(),
                          P->lkeys.ptr(), P->lvals.ptr(), P->loffs.ptr(), P->ev1.ptr(), P->ev2.ptr(), P->lcount.ptr(),
-                         P->ecount.ptr()));
+                         P->ecount.ptr(), big ? nullptr : P->deg.ptr()));
     if (!big) {
-        EULER_TRY(graph_vertices_fused(ctx, P->lcount.ptr(), P->ecount.ptr(), P->vkeys.ptr(), V, P->lstart.ptr(), P->estart.ptr(),
-                                       P->ev.ptr()));
+        EULER_TRY(graph_vertices_paired(ctx, P->deg.ptr(), k, P->vkeys.ptr(), V, P->lcount.ptr(), P->ecount.ptr(), P->lstart.ptr(),
+                                        P->estart.ptr(), P->ev.ptr()));
         launches += 3;
     } else {
         // the pair scan would carry the overflow of one sum into the other: two u32 scans (wrapping), then D5
