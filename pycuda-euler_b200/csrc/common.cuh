@@ -306,6 +306,29 @@ __device__ __forceinline__ u64 table_find_at(const u64 *keys, u64 cap, u64 key, 
     return EULER_NO_SLOT;
 }
 
+// Vertex id lookup through per-bucket id bases: bbase[b] = id of the first strand stored in bucket b
+// (the exclusive scan of the strand weights at the bucket's first slot), so the id of slot j is
+// bbase[b] + the weights of the j slots before it -- known from the bucket just loaded.  One u32 per
+// bucket instead of one per slot: the array is 4x smaller than id0[] and stays in L2, which removes
+// one random DRAM sector per lookup.  k = vertex length (palindromes, weight 1, exist only for even k).
+__device__ __forceinline__ u32 table_find_id(const u64 *keys, u64 cap, u64 key, u64 home, const u32 *bbase, u32 k)
+{
+    const u32 nb = (u32)(cap / EULER_BUCKET);
+    u64 b = home;
+    for (u64 probe = 0; probe < nb; probe++) {
+        const K4 q = ld_bucket_nc(keys + b * EULER_BUCKET);
+        u32 before = 0;
+#pragma unroll
+        for (int j = 0; j < EULER_BUCKET; j++) {
+            if (q.k[j] == key) return bbase[b] + before;
+            if (q.k[j] == EULER_EMPTY_KEY) return EULER_NO_ID;
+            before += (!(k & 1u) && q.k[j] == revcomp64(q.k[j], k)) ? 1u : 2u;
+        }
+        if (++b == nb) b = 0;
+    }
+    return EULER_NO_ID;
+}
+
 // plain-hash forms (module-level gpuhash API, partitioned path)
 __device__ __forceinline__ u64 table_insert(u64 *keys, u64 cap, u64 key, u64 max_probe)
 {

@@ -776,16 +776,16 @@ __global__ void __launch_bounds__(DB) dist_edges_kernel(const u64 *__restrict__ 
     const bool own_p = (own & 1u) != 0, own_s = (own & 2u) != 0;
     u32 id_p = EULER_NO_ID, id_rp = EULER_NO_ID, id_s = EULER_NO_ID, id_rs = EULER_NO_ID;
     if (own_p) {
-        const u64 sp = table_find(vt.keys, vt.cap, cp);
-        if (sp == EULER_NO_SLOT) return;
-        const u32 a = vt.id0[sp], b = (p == rp) ? a : a + 1u;
+        const u32 a = table_find_id(vt.keys, vt.cap, cp, hash_bucket(cp, (u32)(vt.cap / EULER_BUCKET)), vt.bbase, k);
+        if (a == EULER_NO_ID) return;
+        const u32 b = (p == rp) ? a : a + 1u;
         id_p = (p == cp) ? a : b;
         id_rp = (p == cp) ? b : a;
     }
     if (own_s) {
-        const u64 ss = table_find(vt.keys, vt.cap, cs);
-        if (ss == EULER_NO_SLOT) return;
-        const u32 a = vt.id0[ss], b = (s == rs) ? a : a + 1u;
+        const u32 a = table_find_id(vt.keys, vt.cap, cs, hash_bucket(cs, (u32)(vt.cap / EULER_BUCKET)), vt.bbase, k);
+        if (a == EULER_NO_ID) return;
+        const u32 b = (s == rs) ? a : a + 1u;
         id_s = (s == cs) ? a : b;
         id_rs = (s == cs) ? b : a;
     }

@@ -93,6 +93,20 @@ int graph_compact_lmers(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, c
     return EULER_OK;
 }
 
+__global__ void __launch_bounds__(GB) bucket_bases_kernel(const u32 *__restrict__ id0, u64 nb, u32 *__restrict__ bbase)
+{
+    const u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) bbase[b] = id0[b * EULER_BUCKET];
+}
+int graph_bucket_bases(euler_ctx *ctx, const u32 *id0, u64 cap, u32 *bbase)
+{
+    const u64 nb = cap / EULER_BUCKET;
+    if (!nb) return EULER_OK;
+    bucket_bases_kernel<<<grid_for(nb, GB), GB, 0, ctx->stream>>>(id0, nb, bbase);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
 __global__ void __launch_bounds__(GB) compact_vertices_kernel(const u64 *__restrict__ vt_keys, const u32 *__restrict__ base,
                                                                u64 cap, u32 k, u64 *__restrict__ vkeys)
 {
@@ -482,12 +496,21 @@ __global__ void __launch_bounds__(GB) edges_fused_kernel(const u64 *__restrict__
     const u32 vnb = (u32)(vt.cap / EULER_BUCKET);
     u32 sca = 0, scp = 0, scs = 0;
     if (vt.th.span_nb) min_scores(c, l, vt.th.m, sca, scp, scs);
-    const u64 sp = table_find_at(vt.keys, vt.cap, cp, home_from_score(cp, scp, vnb, vt.th));
-    const u64 ss = table_find_at(vt.keys, vt.cap, cs, home_from_score(cs, scs, vnb, vt.th));
-    if (sp == EULER_NO_SLOT || ss == EULER_NO_SLOT) return;  // cannot happen: both were inserted from this slot
-    const u32 p0 = vt.id0[sp], s0 = vt.id0[ss];
-    const u32 p1 = vt.id1 ? vt.id1[sp] : (p == rp ? p0 : p0 + 1u);
-    const u32 s1 = vt.id1 ? vt.id1[ss] : (s == rs ? s0 : s0 + 1u);
+    u32 p0, s0, p1, s1;
+    if (vt.bbase) {   // slot-order ids from the per-bucket bases (no id0[] sector)
+        p0 = table_find_id(vt.keys, vt.cap, cp, home_from_score(cp, scp, vnb, vt.th), vt.bbase, k);
+        s0 = table_find_id(vt.keys, vt.cap, cs, home_from_score(cs, scs, vnb, vt.th), vt.bbase, k);
+        if (p0 == EULER_NO_ID || s0 == EULER_NO_ID) return;  // cannot happen: both were inserted from this slot
+        p1 = p == rp ? p0 : p0 + 1u;
+        s1 = s == rs ? s0 : s0 + 1u;
+    } else {
+        const u64 sp = table_find_at(vt.keys, vt.cap, cp, home_from_score(cp, scp, vnb, vt.th));
+        const u64 ss = table_find_at(vt.keys, vt.cap, cs, home_from_score(cs, scs, vnb, vt.th));
+        if (sp == EULER_NO_SLOT || ss == EULER_NO_SLOT) return;
+        p0 = vt.id0[sp]; s0 = vt.id0[ss];
+        p1 = vt.id1 ? vt.id1[sp] : (p == rp ? p0 : p0 + 1u);
+        s1 = vt.id1 ? vt.id1[ss] : (s == rs ? s0 : s0 + 1u);
+    }
     const u32 id_p = (p == cp) ? p0 : p1, id_rp = (p == cp) ? p1 : p0;   // id(prefix c), id(rc prefix c)
     const u32 id_s = (s == cs) ? s0 : s1, id_rs = (s == cs) ? s1 : s0;
     const u32 m0 = pal ? 2u * n : n;

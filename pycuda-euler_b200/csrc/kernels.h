@@ -21,6 +21,7 @@ struct VertexTable {
     u64 cap;
     u32 k;
     TableHash th;  // home rule of this table (plain or minimizer-ordered)
+    const u32 *bbase = nullptr;  // slot-order ids only: id of the first strand of each bucket (common.cuh, table_find_id)
 };
 // plain key -> value table of the module-level API (pygpuhash TK/TV)
 struct PlainTable {
@@ -38,6 +39,8 @@ int graph_slot_scan(euler_ctx *ctx, const u64 *keys, u64 cap, u32 len, u32 *d_ba
 // both-strand (key, multiplicity) pairs in slot order
 int graph_compact_lmers(euler_ctx *ctx, const u64 *lt_keys, const u32 *lt_cnt, const u32 *lt_base, u64 lt_cap, u32 l,
                         u64 *lkeys, u32 *lvals);
+// bbase[b] = id0[4 b]
+int graph_bucket_bases(euler_ctx *ctx, const u32 *id0, u64 cap, u32 *bbase);
 // both-strand vertex keys in slot order
 int graph_compact_vertices(euler_ctx *ctx, const u64 *vt_keys, const u32 *vt_base, u64 vt_cap, u32 k, u64 *vkeys);
 // id0/id1 of the table slot of each (sorted) vertex key: id = index in vkeys

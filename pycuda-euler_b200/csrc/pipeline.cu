@@ -71,6 +71,7 @@ struct Pipeline {
     // graph artefacts
     DevArr<u64> lkeys, vkeys;
     DevArr<u32> lvals, loffs, ev1, ev2, lcount, ecount, lstart, estart;
+    DevArr<u32> vt_bbase;  // id of the first strand of each vertex-table bucket (slot-order ids)
     DevArr<u32> deg;  // paired degree regions u32[8 V] (common.cuh, DegOut) of the slot-order fast paths
     DevArr<euler_vertex> ev;
     DevArr<euler_edge> ee;
@@ -107,7 +108,7 @@ void pipeline_destroy(Pipeline *p)
     p->lcount.free(); p->ecount.free(); p->lstart.free(); p->estart.free(); p->ev.free(); p->ee.free();
     if (p->recv_buf) cudaFree(p->recv_buf);
     p->lev.free(); p->ent.free(); p->sort_k.free(); p->sort_v.free(); p->sort_hist.free();
-    p->blk_keys.free(); p->blk_cur.free(); p->deg.free();
+    p->blk_keys.free(); p->blk_cur.free(); p->deg.free(); p->vt_bbase.free();
     p->wlt_keys.free(); p->wvt_keys.free(); p->wlt_cnt.free(); p->lkeys_hi.free(); p->vkeys_hi.free(); p->tf.free();
     delete p;
 }
@@ -392,6 +393,9 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
         launches += 3 * ((2 * l + 7) / 8) + 3 * ((2 * k + 7) / 8) + 5;
     } else {
         // fast path: ids in table-slot order, one fused pass over the l-mer table
+        EULER_TRY(P->vt_bbase.reserve(ctx, vt_cap / EULER_BUCKET + 1));
+        EULER_TRY(graph_bucket_bases(ctx, P->vt_id0.ptr(), vt_cap, P->vt_bbase.ptr()));
+        vt.bbase = P->vt_bbase.ptr();
         EULER_TRY(graph_edges_fused(ctx, P->lt.keys(), P->lt.cnt(), P->lt_base.ptr(), P->lt_eoff.ptr(), lt_cap, l, vt,
                                     P->lkeys.ptr(), P->lvals.ptr(), P->loffs.ptr(), P->ev1.ptr(), P->ev2.ptr(),
                                     P->lcount.ptr(), P->ecount.ptr(), P->deg.ptr()));
@@ -1013,6 +1017,9 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
     }
     EULER_TRY(graph_compact_vertices(ctx, P->vt_keys.ptr(), P->vt_id0.ptr(), vt_cap, k, P->vkeys.ptr()));
     VertexTable vt = {P->vt_keys.ptr(), P->vt_id0.ptr(), nullptr, vt_cap, k, TableHash{0, 0}};
+    EULER_TRY(P->vt_bbase.reserve(ctx, vt_cap / EULER_BUCKET + 1));
+    EULER_TRY(graph_bucket_bases(ctx, P->vt_id0.ptr(), vt_cap, P->vt_bbase.ptr()));
+    vt.bbase = P->vt_bbase.ptr();
     EULER_TRY(dist_edges(ctx, P->lt.keys(), P->lt.cnt(), P->lt_base.ptr(), P->lt_eoff.ptr(), lt_cap, l, vt, P->lt_own.ptr(),
                          P->lkeys.ptr(), P->lvals.ptr(), P->loffs.ptr(), P->ev1.ptr(), P->ev2.ptr(), P->lcount.ptr(),
                          P->ecount.ptr(), big ? nullptr : P->deg.ptr()));
