@@ -151,6 +151,17 @@ int euler_emit_contigs(euler_ctx *ctx, const euler_vertex *ev, uint32_t vcount, 
 int euler_unitigs(euler_ctx *ctx, const char *buf, const uint64_t *read_off, uint64_t nreads, uint32_t K,
                   uint32_t limit, char *out, uint64_t *out_bytes, uint64_t *ncontigs);
 
+/* referenceAssembler.all_contigs(d, k) (:79-88) on a K-mer dictionary, i.e. on the output of build /
+ * euler_count_mers: keys[n] (either strand or both; they are canonicalised), counts[n] (both-strand counts, every
+ * key present).  Output as euler_unitigs. */
+int euler_unitigs_from_kmers(euler_ctx *ctx, const uint64_t *keys, const uint32_t *counts, uint64_t n, uint32_t K,
+                             char *out, uint64_t *out_bytes, uint64_t *ncontigs);
+/* Link graph G of referenceAssembler.all_contigs (:90-111) for n contigs: text = the contigs back to back
+ * (no separators), off[n+1].  links: u32[16 n]; entry [16 i + 8 side + 2 base + o]: side 0 = candidates
+ * fw(last K-mer of contig i), side 1 = fw(twin(first K-mer)); base = A,C,G,T; o = 0: contig whose head is the
+ * candidate ('+'), o = 1: contig whose twin(tail) is ('-'); 0xffffffff = none.  K in [2,31]. */
+int euler_unitig_links(euler_ctx *ctx, const char *text, const uint64_t *off, uint64_t n, uint32_t K, uint32_t *links);
+
 /* =========================================================================================
  * Fused device-resident pipeline (the measured hot path)
  * ======================================================================================= */

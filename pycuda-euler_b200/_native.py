@@ -72,6 +72,8 @@ def load():
         "euler_count_lmers": [vp, vp, vp, u64, u32, vp, vp, vp, vp, vp, vp],
         "euler_count_mers": [vp, vp, vp, u64, u32, u32, vp, vp, vp],
         "euler_unitigs": [vp, vp, vp, u64, u32, u32, vp, vp, vp],
+        "euler_unitigs_from_kmers": [vp, vp, vp, u64, u32, vp, vp, vp],
+        "euler_unitig_links": [vp, vp, vp, u64, u32, vp],
         "euler_hash_build": [vp, vp, vp, u64, u64, vp, vp],
         "euler_hash_lookup": [vp, vp, vp, u64, vp, u64, vp],
         "euler_exclusive_scan_u32": [vp, vp, u64, vp],
@@ -218,6 +220,32 @@ class Context:
         self.check(self.lib.euler_unitigs(self.h, _p(buf), _p(off), len(off) - 1, int(K), int(limit), _p(out),
                                           C.byref(cap), C.byref(nc)))
         return out.tobytes().decode("ascii").split("\n")[:-1]
+
+    def unitigs_from_kmers(self, keys, counts, K):
+        """unitigs of a K-mer dictionary (packed keys, both-strand counts): referenceAssembler.all_contigs(d, k)"""
+        keys = _arr(keys, np.uint64)
+        counts = _arr(counts, np.uint32)
+        nb, nc = C.c_uint64(0), C.c_uint64(0)
+        self.check(self.lib.euler_unitigs_from_kmers(self.h, _p(keys), _p(counts), len(keys), int(K), None, C.byref(nb),
+                                                     C.byref(nc)))
+        if not nb.value:
+            return []
+        out = np.zeros(nb.value, np.uint8)
+        cap = C.c_uint64(nb.value)
+        self.check(self.lib.euler_unitigs_from_kmers(self.h, _p(keys), _p(counts), len(keys), int(K), _p(out), C.byref(cap),
+                                                     C.byref(nc)))
+        return out.tobytes().decode("ascii").split("\n")[:-1]
+
+    def unitig_links(self, contigs, K):
+        """(n, 16) uint32 link table of referenceAssembler.all_contigs' G (see euler_unitig_links)"""
+        n = len(contigs)
+        links = np.zeros((n, 16), np.uint32)
+        if n:
+            text = np.frombuffer("".join(contigs).encode("ascii"), dtype=np.uint8)
+            off = np.zeros(n + 1, np.uint64)
+            off[1:] = np.cumsum([len(c) for c in contigs], dtype=np.uint64)
+            self.check(self.lib.euler_unitig_links(self.h, _p(text), _p(off), n, int(K), _p(links)))
+        return links
 
     # ------------------------------------------------------------------ gpuhash
     def hash_capacity(self, n):

@@ -204,6 +204,61 @@ int euler_unitigs_ingested(euler_ctx *ctx, uint32_t K, uint32_t limit, char *out
     return unitigs_core(ctx, d_buf, d_off, nr, nb, K, limit, out, out_bytes, ncontigs);
 }
 
+// referenceAssembler.all_contigs(d, k) :79-88 on a K-mer dictionary (the output of build / euler_count_mers)
+int euler_unitigs_from_kmers(euler_ctx *ctx, const uint64_t *keys, const uint32_t *counts, uint64_t n, uint32_t K, char *out,
+                             uint64_t *out_bytes, uint64_t *ncontigs)
+{
+    ENTER(ctx);
+    if (!out_bytes || !ncontigs || (n && (!keys || !counts))) return euler_fail(ctx, EULER_ERR_ARG, "null argument");
+    if (K < 2 || K > 32) return euler_fail(ctx, EULER_ERR_ARG, "K %u out of range [2,32]", K);
+    const u64 cap_out = *out_bytes;
+    *out_bytes = 0; *ncontigs = 0;
+    if (!n) return EULER_OK;
+    const u64 cap = euler_hash_capacity(n);
+    DevTmp<u64> dk(ctx, n), tk(ctx, cap), flags(ctx, 1);
+    DevTmp<u32> dc(ctx, n), tc(ctx, cap);
+    TMP_CHECK(ctx, dk); TMP_CHECK(ctx, dc); TMP_CHECK(ctx, tk); TMP_CHECK(ctx, tc); TMP_CHECK(ctx, flags);
+    EULER_TRY(upload(ctx, dk, (const u64 *)keys, n));
+    EULER_TRY(upload(ctx, dc, counts, n));
+    CUDA_TRY(ctx, cudaMemsetAsync(flags, 0, sizeof(u64), ctx->stream));
+    EULER_TRY(graph_table_clear(ctx, tk, tc, cap));
+    EULER_TRY(unitig_dict_table(ctx, dk, dc, n, K, tk, tc, cap, flags));
+    u64 f = 0;
+    EULER_TRY(read_u64(ctx, flags, &f));
+    if (f) return euler_fail(ctx, EULER_ERR_OVERFLOW, "K-mer table full");
+    char *d_text = nullptr;
+    u64 bytes = 0, nc = 0, nn = 0;
+    EULER_TRY(unitig_from_table(ctx, tk, tc, cap, K, 0, &d_text, &bytes, &nc, &nn));
+    *out_bytes = bytes; *ncontigs = nc;
+    if (out) {
+        if (cap_out < bytes) return euler_fail(ctx, EULER_ERR_ARG, "output capacity too small");
+        EULER_TRY(download(ctx, out, (const char *)d_text, bytes));
+    }
+    FINISH(ctx);
+}
+
+// link graph G of referenceAssembler.all_contigs :90-111 for n contigs (text: the contigs back to back, no
+// separators; off[n+1]).  links: u32[16 n], entry [16 i + 8 side + 2 base + o]: side 0 = successors of the last
+// K-mer, side 1 = of twin(first K-mer); o = 0: the hit is a contig head ('+'), o = 1: a tail ('-'); 0xffffffff = none.
+int euler_unitig_links(euler_ctx *ctx, const char *text, const uint64_t *off, uint64_t n, uint32_t K, uint32_t *links)
+{
+    ENTER(ctx);
+    if (n && (!text || !off || !links)) return euler_fail(ctx, EULER_ERR_ARG, "null argument");
+    if (K < 2 || K > 31) return euler_fail(ctx, EULER_ERR_ARG, "K %u out of range [2,31]", K);
+    if (!n) return EULER_OK;
+    if (n >= 0xfffffffeull) return euler_fail(ctx, EULER_ERR_RANGE, "too many contigs");
+    const u64 B = off[n];
+    DevTmp<char> d_text(ctx, B + 16);
+    DevTmp<u64> d_off(ctx, n + 1);
+    DevTmp<u32> d_links(ctx, 16 * n);
+    TMP_CHECK(ctx, d_text); TMP_CHECK(ctx, d_off); TMP_CHECK(ctx, d_links);
+    EULER_TRY(upload(ctx, d_text, text, B));
+    EULER_TRY(upload(ctx, d_off, (const u64 *)off, n + 1));
+    EULER_TRY(unitig_link_graph(ctx, d_text, d_off, n, K, d_links));
+    EULER_TRY(download(ctx, links, d_links.get(), 16 * n));
+    FINISH(ctx);
+}
+
 int euler_hash_build(euler_ctx *ctx, const uint64_t *keys, const uint32_t *values, uint64_t n, uint64_t capacity,
                      uint64_t *TK, uint32_t *TV)
 {

@@ -102,6 +102,11 @@ int synth_reads(euler_ctx *ctx, u64 G, u32 L, u32 err_ppm, u64 first, u64 nreads
 int unitig_from_table(euler_ctx *ctx, const u64 *keys, const u32 *cnt, u64 cap, u32 K, u32 limit, char **d_out,
                       u64 *out_bytes, u64 *ncontigs, u64 *n_nodes);
 
+// canonical count table from a both-strand K-mer dictionary (keys, counts)
+int unitig_dict_table(euler_ctx *ctx, const u64 *d_keys, const u32 *d_counts, u64 n, u32 K, u64 *tk, u32 *tc, u64 cap, u64 *d_flags);
+// link graph of n contigs (text without separators, off[n+1]): links[16 i + 8 side + 2 base + (0 head '+' | 1 tail '-')]
+int unitig_link_graph(euler_ctx *ctx, const char *d_text, const u64 *d_off, u64 n, u32 K, u32 *d_links);
+
 // ---- graph.cu, fused fast path
 // pair scan over l-mer table slots: base = distinct both-strand l-mer index, eoff = edge offset;
 // *d_total_packed = (E << 32) | U_l

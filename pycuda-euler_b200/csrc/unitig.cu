@@ -135,3 +135,95 @@ int unitig_from_table(euler_ctx *ctx, const u64 *keys, const u32 *cnt, u64 cap, 
     UnitigChainModel m = {nkeys, succ, twin_id};
     return chain_emit(ctx, m, (u32)n, K, d_out, out_bytes, ncontigs);
 }
+
+// ---- a K-mer dictionary as input (referenceAssembler.all_contigs(d, k) takes the dict of build()) -------
+__global__ void __launch_bounds__(UB) kmer_dict_insert_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ counts, u64 n,
+                                                               u32 K, u64 *__restrict__ tk, u32 *__restrict__ tc, u64 cap, u64 *flags)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 x = keys[i] & key_mask_d(K), r = revcomp64(x, K);
+    const u64 c = x < r ? x : r;
+    const u64 slot = table_insert(tk, cap, c, cap / EULER_BUCKET);
+    if (slot == EULER_NO_SLOT) { atomicOr((unsigned long long *)flags, 1ull); return; }
+    // the table stores the canonical count n with both-strand count n (2n for a palindrome, :31-35)
+    const u32 v = counts[i];
+    atomicMax(tc + slot, x == r ? (v + 1u) / 2u : v);
+}
+int unitig_dict_table(euler_ctx *ctx, const u64 *d_keys, const u32 *d_counts, u64 n, u32 K, u64 *tk, u32 *tc, u64 cap, u64 *d_flags)
+{
+    if (!n) return EULER_OK;
+    kmer_dict_insert_kernel<<<grid_for(n, UB), UB, 0, ctx->stream>>>(d_keys, d_counts, n, K, tk, tc, cap, d_flags);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+// ---- link graph of the contigs: referenceAssembler.all_contigs :90-111 ------------------------------------
+// heads[x[:k]] = (i,'+'), tails[twin(x[-k:])] = (i,'-') (a later contig overwrites an earlier one: max i);
+// G[i][0] = for y in fw(x[-k:]): heads hit, tails hit; G[i][1] = for z in fw(twin(x[:k])): heads hit, tails hit.
+__device__ __forceinline__ u64 encode_text_kmer(const char *s, u32 K)
+{
+    u64 x = 0;
+    for (u32 i = 0; i < K; i++) {
+        const unsigned char c = (unsigned char)s[i];
+        x = (x << 2) | (u64)(((c >> 1) ^ (c >> 2)) & 3u);
+    }
+    return x;
+}
+__global__ void __launch_bounds__(UB) contig_ends_kernel(const char *__restrict__ text, const u64 *__restrict__ off, u64 n, u32 K,
+                                                          u64 *__restrict__ hk, u32 *__restrict__ hv, u64 *__restrict__ tk,
+                                                          u32 *__restrict__ tv, u64 cap, u64 *flags)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 b = off[i], e = off[i + 1];
+    if (e - b < K) return;
+    const u64 head = encode_text_kmer(text + b, K);
+    const u64 tail = revcomp64(encode_text_kmer(text + e - K, K), K);
+    const u64 sh = table_insert(hk, cap, head, cap / EULER_BUCKET), st = table_insert(tk, cap, tail, cap / EULER_BUCKET);
+    if (sh == EULER_NO_SLOT || st == EULER_NO_SLOT) { atomicOr((unsigned long long *)flags, 1ull); return; }
+    atomicMax(hv + sh, (u32)i + 1u);
+    atomicMax(tv + st, (u32)i + 1u);
+}
+__global__ void __launch_bounds__(UB) contig_links_kernel(const char *__restrict__ text, const u64 *__restrict__ off, u64 n, u32 K,
+                                                           const u64 *__restrict__ hk, const u32 *__restrict__ hv,
+                                                           const u64 *__restrict__ tk, const u32 *__restrict__ tv, u64 cap,
+                                                           u32 *__restrict__ links)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 *out = links + 16 * i;
+    for (int j = 0; j < 16; j++) out[j] = EULER_NO_ID;
+    const u64 b = off[i], e = off[i + 1];
+    if (e - b < K) return;
+    const u64 mask = key_mask_d(K);
+    const u64 last = encode_text_kmer(text + e - K, K);
+    const u64 first_tw = revcomp64(encode_text_kmer(text + b, K), K);
+    for (int side = 0; side < 2; side++) {
+        const u64 x = side ? first_tw : last;
+        for (u32 c = 0; c < 4; c++) {
+            const u64 y = ((x << 2) | c) & mask;
+            const u64 sh = table_find(hk, cap, y), st = table_find(tk, cap, y);
+            if (sh != EULER_NO_SLOT) out[8 * side + 2 * c] = hv[sh] - 1u;
+            if (st != EULER_NO_SLOT) out[8 * side + 2 * c + 1] = tv[st] - 1u;
+        }
+    }
+}
+int unitig_link_graph(euler_ctx *ctx, const char *d_text, const u64 *d_off, u64 n, u32 K, u32 *d_links)
+{
+    if (!n) return EULER_OK;
+    const u64 cap = ((u64)((double)(n < 16 ? 16 : n) / 0.55) + 1 + 1023) / 1024 * 1024;
+    DevTmp<u64> hk(ctx, cap), tk(ctx, cap), flags(ctx, 1);
+    DevTmp<u32> hv(ctx, cap), tv(ctx, cap);
+    TMP_CHECK(ctx, hk); TMP_CHECK(ctx, tk); TMP_CHECK(ctx, hv); TMP_CHECK(ctx, tv); TMP_CHECK(ctx, flags);
+    CUDA_TRY(ctx, cudaMemsetAsync(flags, 0, sizeof(u64), ctx->stream));
+    EULER_TRY(graph_table_clear(ctx, hk, hv, cap));
+    EULER_TRY(graph_table_clear(ctx, tk, tv, cap));
+    contig_ends_kernel<<<grid_for(n, UB), UB, 0, ctx->stream>>>(d_text, d_off, n, K, hk, hv, tk, tv, cap, flags);
+    contig_links_kernel<<<grid_for(n, UB), UB, 0, ctx->stream>>>(d_text, d_off, n, K, hk, hv, tk, tv, cap, d_links);
+    CUDA_TRY(ctx, cudaGetLastError());
+    u64 f = 0;
+    EULER_TRY(read_u64(ctx, flags, &f));
+    if (f) return euler_fail(ctx, EULER_ERR_OVERFLOW, "contig end table full");
+    return EULER_OK;
+}

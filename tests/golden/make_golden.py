@@ -37,10 +37,17 @@ def sha16(items):
 
 def run_case(ra, reads, k, limit):
     d = ra.build(reads, k, limit)
-    _, contigs = ra.all_contigs(d, k)
+    G, contigs = ra.all_contigs(d, k)
     canon = sorted(min(c, ra.twin(c)) for c in contigs)
+    # get_contig from the first k-mer of every contig and from one in its middle (string only)
+    probes = []
+    for c in contigs:
+        for km in (c[:k], c[(len(c) - k) // 2:(len(c) - k) // 2 + k]):
+            probes.append([km, ra.get_contig(d, km)[0]])
     return {
         "k": k, "limit": limit,
+        "links": [[[list(x) for x in G[i][0]], [list(x) for x in G[i][1]]] for i in range(len(contigs))],
+        "get_contig": probes,
         "kmers": sorted([km, c] for km, c in d.items()),
         "kmer_sha": sha16(["%s\t%d" % (km, c) for km, c in d.items()]),
         "contigs": contigs,

@@ -76,6 +76,10 @@ def test_import_layouts():
     import pygpuhash, pydebruijn, pyeulertour, pycomponent  # noqa: E401,F401
     assert eulercuda.assemble2 is ec.assemble2 and eulercuda.assemble is ec.assemble2
     assert pyeulertour.findEulerDevice is eulertour.pyeulertour.findEulerDevice
+    import referenceassembler as ra
+    from referenceassembler import referenceAssembler as ram
+    assert ra.build is ram.build and ra.all_contigs is ram.all_contigs
+    assert ra.twin("AACG") == "CGTT" and ra.contig_to_string(["ACG", "CGT", "GTT"]) == "ACGTT"
 
 
 def test_host_helpers():

@@ -54,6 +54,40 @@ def test_unitigs_match_reference_assembler(ctx, fixture):
         assert _canon_set(got, k, d) == _canon_set(case["contigs"], k, d), (fixture, k, limit)
 
 
+@pytest.mark.parametrize("fixture", ["g200.json", "synth_small.json"])
+def test_referenceassembler_module(ctx, fixture):
+    """The drop-in `referenceassembler` package against outputs of the unmodified reference module:
+    build() tables, all_contigs() contig sets, the link graph G on the reference's own contig lists
+    (exact), get_contig() strings (exact) and well-formed GFA / FASTA writers."""
+    import io
+    import referenceassembler as ra
+    from referenceassembler import referenceAssembler as ram
+    fx = _load(fixture)
+    for case in fx["cases"]:
+        k, limit = case["k"], case["limit"]
+        d = ra.build(fx["reads"], k, limit)
+        assert d == {km: c for km, c in case["kmers"]}, (k, limit)
+        G, r = ra.all_contigs(d, k)
+        assert _canon_set(r, k, d) == _canon_set(case["contigs"], k, d)
+        assert sorted(G) == list(range(len(r)))
+        # G is a function of the contig list: on the reference's list it must be the reference's G
+        got = ram.link_graph(case["contigs"], k)
+        exp = {i: ([tuple(x) for x in lk[0]], [tuple(x) for x in lk[1]]) for i, lk in enumerate(case["links"])}
+        assert got == exp, (k, limit)
+        for km, text in case["get_contig"]:
+            s, c = ra.get_contig(d, km)
+            assert s == text and ra.contig_to_string(c) == text and km in c
+        out = io.StringIO()
+        ram.write_gfa(G, r, k, out)
+        lines = out.getvalue().splitlines()
+        assert lines[0] == "H\tVN:Z:1.0" and sum(x.startswith("S\t") for x in lines) == len(r)
+        assert sum(x.startswith("L\t") for x in lines) == sum(len(a) + len(b) for a, b in G.values())
+    assert ra.twin("ACGTN") == "NACGT" and list(ra.fw("ACG")) == ["CGA", "CGC", "CGG", "CGT"]
+    assert list(ra.bw("ACG")) == ["AAC", "CAC", "GAC", "TAC"] and list(ra.kmers("ACGT", 3)) == ["ACG", "CGT"]
+    with pytest.raises(ValueError):
+        ra.get_contig_forward({"ACG": 2, "CGT": 2}, "TTT")
+
+
 def test_assemble_entry_points(tmp_path, g200_reads):
     import eulercuda as ec_pkg
     import eulercuda.eulercuda as ec

@@ -122,6 +122,39 @@ def test_partition_counts_are_exact(ctx):
         assert np.array_equal(seg, want)
 
 
+@pytest.mark.parametrize("l,world", [(32, 8), (22, 3), (20, 4)])
+def test_segment_scatter_matches_exact_scatter(ctx, l, world):
+    """The single-pass scatter into fixed-capacity segments (what the peer-store exchange uses) delivers the
+    same key multiset per destination as the exact two-pass scatter, and reports a segment that overflows."""
+    import torch
+    reads = random_reads(5, 500, genome_len=4000)
+    buf, off = oracle.pack_reads(reads)
+    d_buf = torch.from_numpy(buf).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    exact = ctx.dist_count(d_buf.data_ptr(), d_off.data_ptr(), len(reads), buf.size, l, world)
+    sc = exact[:world].astype(np.int64)
+    send_off = np.zeros(world, np.uint64)
+    send_off[1:] = np.cumsum(sc[:-1])
+    send = torch.zeros(max(int(sc.sum()), 1), dtype=torch.int64, device="cuda")
+    ctx.dist_scatter(d_buf.data_ptr(), d_off.data_ptr(), len(reads), buf.size, l, world, send.data_ptr(), send_off)
+    ctx.sync()
+    ref = send.cpu().numpy().view(np.uint64)
+    cap = int(sc.max()) + 7
+    seg = torch.zeros(cap * world, dtype=torch.int64, device="cuda")
+    counts = ctx.dist_scatter_segments(d_buf.data_ptr(), d_off.data_ptr(), len(reads), buf.size, l, world, seg.data_ptr(), cap)
+    assert np.array_equal(counts, exact)
+    got = seg.cpu().numpy().view(np.uint64)
+    for d in range(world):
+        a = np.sort(got[d * cap:d * cap + int(sc[d])])
+        b = np.sort(ref[int(send_off[d]):int(send_off[d]) + int(sc[d])])
+        assert np.array_equal(a, b)
+    small = max(int(sc.max()) // 2, 1)
+    seg2 = torch.full((small * world + 8,), -1, dtype=torch.int64, device="cuda")
+    counts2 = ctx.dist_scatter_segments(d_buf.data_ptr(), d_off.data_ptr(), len(reads), buf.size, l, world, seg2.data_ptr(), small)
+    assert np.array_equal(counts2, exact)                 # the cursors keep counting past the capacity ...
+    assert (seg2.cpu().numpy()[small * world:] == -1).all()   # ... but nothing is written outside the segments
+
+
 def _canon_part(p):
     # slot-order ids depend on the table capacity and on insertion races: compare through the keys
     o = np.argsort(p["LMER_KEYS"], kind="stable")
