@@ -7,6 +7,8 @@ reads, sends every canonical l-mer to the owner(s) of its prefix / suffix k-mer 
 ``all_to_all_single`` over NCCL, and builds its part of the graph from what it receives (see
 csrc/dist.cu).  torch.distributed is plumbing only; all compute is in libeuler_b200.so.
 """
+import os
+
 import numpy as np
 
 
@@ -64,15 +66,37 @@ class PeerExchange:
     def __init__(self, ctx, rank, world, seg_cap, group=None):
         """seg_cap is in 8-byte words (an l-mer key is one word for l <= 32, two above)"""
         import torch.distributed as dist
-        self.ctx, self.rank, self.world, self.seg_cap, self.group = ctx, rank, world, int(seg_cap), group
-        self.local_ptr, handle = ctx.dist_recv_alloc(self.seg_cap * world)
+        # every rank lays its receive buffer out as `world` regions of seg_cap words and writes into region
+        # `rank` of its peers: the stride must be the same everywhere, so the ranks agree on the largest
+        # proposal (their shards, hence their estimates, differ)
+        proposals = [None] * world
+        dist.all_gather_object(proposals, int(seg_cap), group=group)
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.seg_cap = (max(proposals) + 1) & ~1
+        # Two receive buffers used in turn: a rank that is one step ahead (it may start the next scatter as
+        # soon as the count exchange of this step is over) must not overwrite keys its peers are still
+        # counting.  Nobody can be two steps ahead -- the next count exchange needs everyone.
+        self.nbuf = 1 if os.environ.get("EULER_B200_PEER_DOUBLE", "1") == "0" else 2
+        self.phase = 0
+        self.base_ptr, handle = ctx.dist_recv_alloc(self.seg_cap * world * self.nbuf)
+        self.local_ptr = self.base_ptr
         handles = [None] * world
         dist.all_gather_object(handles, handle, group=group)
         self.bases = []
         for d in range(world):
-            self.bases.append(self.local_ptr if d == rank else ctx.dist_peer_open(handles[d]))
-        # my region inside every destination's buffer
-        self.dst_ptrs = [b + 8 * self.seg_cap * rank for b in self.bases]
+            self.bases.append(self.base_ptr if d == rank else ctx.dist_peer_open(handles[d]))
+        self.next_step()
+
+    def next_step(self):
+        """switch to the other receive buffer (every rank calls this once per exchange, in lock step)"""
+        import torch.distributed as dist
+        if self.nbuf == 1:
+            dist.barrier(group=self.group)     # single buffer: wait until every rank has consumed the last step
+        shift = 8 * self.seg_cap * self.world * (self.phase % self.nbuf)
+        self.phase += 1
+        self.local_ptr = self.base_ptr + shift
+        # my region inside every destination's current buffer
+        self.dst_ptrs = [b + shift + 8 * self.seg_cap * self.rank for b in self.bases]
 
     def close(self):
         for d, b in enumerate(self.bases):
@@ -88,17 +112,30 @@ _PEER = {}
 
 
 def _peer_exchange(ctx, rank, world, seg_cap, group):
+    """The exchange object of (ctx, world), created collectively on first use.  It is never re-created by
+    one rank alone (that would dead-lock the handshake): a rank that needs more than the agreed capacity
+    reports the overflow through the count exchange, every rank takes the exact-size fallback for that
+    step and drops the object (`_drop_peer_exchange`), and the next step agrees on a larger one."""
     key = (id(ctx), world)
     px = _PEER.get(key)
-    if px is None or px.seg_cap < seg_cap:
-        if px is not None:
-            px.close()
+    if px is None:
         try:
-            px = PeerExchange(ctx, rank, world, seg_cap, group)
+            px = PeerExchange(ctx, rank, world, max(int(seg_cap), _PEER_MIN.get(key, 0)), group)
         except Exception as e:          # no peer access on this box: fall back to NCCL all_to_all
             px = e
         _PEER[key] = px
     return None if isinstance(px, Exception) else px
+
+
+_PEER_MIN = {}
+
+
+def _drop_peer_exchange(ctx, world):
+    key = (id(ctx), world)
+    px = _PEER.pop(key, None)
+    if isinstance(px, PeerExchange):
+        _PEER_MIN[key] = int(px.seg_cap * 1.5)
+        px.close()
 
 
 def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint=0, group=None, slack=1.25,
@@ -140,6 +177,7 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
         if kw == 2 and px.seg_cap % 2:     # cached buffer with an odd word stride: regions would not be 16-byte aligned
             px = None
     if px is not None:
+        px.next_step()
         counts = ctx.dist_scatter_peers(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, world, px.dst_ptrs, seg_cap)
     else:
         send = _buffer("send", seg_cap * world * kw, dev)
@@ -157,6 +195,8 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
     recv_counts = [int(gathered[src, rank]) for src in range(world)]
     exact = bool(gathered[:, world].max())
     t2 = time.perf_counter()
+    if exact:
+        _drop_peer_exchange(ctx, world)     # collective knowledge: every rank sees the flag
     if exact and kw == 2:
         raise RuntimeError("128-bit keys: a destination segment overflowed (skewed minimizers); raise `slack`")
     if exact:   # rare: redo with exact sizes on every rank, over NCCL

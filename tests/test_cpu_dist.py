@@ -102,3 +102,22 @@ def test_plan_exchange_pure():
     from eulercuda.dist import plan_exchange
     off, recv = plan_exchange([3, 0, 5], lambda s: [7, 8, 9])
     assert off.tolist() == [0, 3, 3] and recv == [7, 8, 9]
+
+
+def test_assembler_driver_splits_files_at_record_boundaries():
+    """partition driver: byte ranges of a FASTA / FASTQ file per rank, cut at record boundaries"""
+    sys.path.insert(0, os.path.join(ROOT, "pycuda-euler_b200"))
+    from assembler import split_records, detect_format
+    fq = b"".join(b"@r%d\nACGT%s\n+\nIIII%s\n" % (i, b"A" * (i % 7), b"I" * (i % 7)) for i in range(101))
+    for world in (1, 2, 3, 8):
+        rs = split_records(fq, world, 2)
+        assert rs[0][0] == 0 and rs[-1][1] == len(fq) and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        for a, b in rs:
+            chunk = fq[a:b]
+            assert chunk == b"" or (chunk[:1] == b"@" and chunk.count(b"\n") % 4 == 0)
+        assert b"".join(fq[a:b] for a, b in rs) == fq
+    fa = b"".join(b">r%d\nACGTACGT\n" % i for i in range(50))
+    rs = split_records(fa, 4, 1)
+    assert b"".join(fa[a:b] for a, b in rs) == fa and all(fa[a:a + 1] in (b">", b"A", b"") for a, _ in rs)
+    assert split_records(b"", 3, 1) == [(0, 0)] * 3
+    assert detect_format("x.fq", b"") == 2 and detect_format("x.fasta", b"") == 1 and detect_format("x.txt", b"@r") == 2
