@@ -336,7 +336,7 @@ def main():
                 "workload": args.workload, "genome_bp": wl["G"], "read_len": L, "coverage": wl["cov"], "err_ppm": wl["err_ppm"],
                 "k": k, "reads_per_gpu": R, "bases_per_gpu": R * L,
                 "parallelism": "1 GPU" if world == 1 else
-                "%d GPUs: reads sharded, k-mer space hash-partitioned by vertex owner, one NCCL all_to_all of canonical l-mer keys" % world,
+                "%d GPUs: reads sharded, k-mer space partitioned by the minimizer of each vertex, one exchange of canonical l-mer keys (see dist.transport)" % world,
                 "genome_bp_total": G,
                 "l2": "inputs (%d MB ASCII) + table (%d MB) exceed the 126 MB L2; the table is re-initialised every step"
                       % (R * L // 10 ** 6, st.lmer_table_capacity * 12 // 10 ** 6),
