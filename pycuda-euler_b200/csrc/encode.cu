@@ -263,6 +263,138 @@ __global__ void __launch_bounds__(CNT_BLOCK, 4) count_canonical_kernel(const uin
     if (overflow) atomicOr((unsigned long long *)(stats + 2), 1ull);
 }
 
+// ---- the default count kernel: compact the valid windows of a tile, then probe --------------------------
+// In the kernel above every lane probes the windows of its own positions, so the lanes whose window is
+// not a whole l-mer of one read (31 % of the positions of 100 bp reads at l = 32) idle through the probe
+// code: ncu shows 21 of 32 threads active per instruction.  Here phase 1 rolls the 16 positions of the
+// tile in lock step and packs the valid canonical keys into a per-warp shared-memory buffer (one ballot
+// per position gives every lane its slot); phase 2 probes them 4 per lane with all lanes busy.  COHASH
+// selects the home rule (plain hash of the key / of the canonical prefix k-mer, common.cuh).
+#define CC_BLOCK 128
+#define CC_KEYS (ENC_ADV * 16)   // valid windows per tile <= 480
+__device__ __forceinline__ int bucket_match(const K4 &q, u64 key, int &first_empty)
+{
+    // slot of `key` in the bucket (0..3) or -1; first_empty = first EMPTY slot or 4
+    const unsigned m = (q.k[0] == key ? 1u : 0u) | (q.k[1] == key ? 2u : 0u) | (q.k[2] == key ? 4u : 0u) | (q.k[3] == key ? 8u : 0u);
+    const unsigned e = (q.k[0] == EULER_EMPTY_KEY ? 1u : 0u) | (q.k[1] == EULER_EMPTY_KEY ? 2u : 0u) |
+                       (q.k[2] == EULER_EMPTY_KEY ? 4u : 0u) | (q.k[3] == EULER_EMPTY_KEY ? 8u : 0u);
+    first_empty = e ? (int)__ffs(e) - 1 : 4;
+    return m ? (int)__ffs(m) - 1 : -1;
+}
+template <bool COHASH>
+__global__ void __launch_bounds__(CC_BLOCK, 8) count_compact_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
+                                                                     const u32 *__restrict__ start_bits, u32 l,
+                                                                     u64 *__restrict__ tab_keys, u32 *__restrict__ tab_cnt, u64 cap,
+                                                                     u64 ntiles, u64 *__restrict__ stats)
+{
+    __shared__ u64 s_keys[(CC_BLOCK / 32) * CC_KEYS];
+    u64 *stage = s_keys + (threadIdx.x >> 5) * CC_KEYS;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    const u32 nbuckets = (u32)(cap / EULER_BUCKET);
+    const u32 max_probe = nbuckets < 4096 ? nbuckets : 4096;
+    const u32 k = l - 1, top = 2 * (l - 1);
+    const u64 lmask = key_mask_d(l), kmask = lmask >> 2;
+    u32 nl_tot = 0, nk_tot = 0;
+    bool overflow = false;
+
+    for (u64 tile = warp; tile < ntiles; tile += nwarps) {
+        const long long chunk = (long long)(tile * ENC_ADV) - ENC_HALO + lane;
+        const Chunk c = load_chunk(buf16, chunk, n_bases, start_bits);
+        const u32 p1 = __shfl_up_sync(0xffffffffu, c.codes, 1), p2 = __shfl_up_sync(0xffffffffu, c.codes, 2);
+        const u32 v1 = __shfl_up_sync(0xffffffffu, c.vmask, 1), v2 = __shfl_up_sync(0xffffffffu, c.vmask, 2);
+        const u32 s1 = __shfl_up_sync(0xffffffffu, c.smask, 1), s2 = __shfl_up_sync(0xffffffffu, c.smask, 2);
+        u64 f = ((u64)p2 << 32) | p1;
+        u64 rc = revcomp64(f & lmask, l);
+        const u32 pv = (v2 << 16) | v1, ps = (s2 << 16) | s1;   // bit 0 = the most recent base
+        u32 vrun = (lane < ENC_HALO) ? 0u : ((pv == 0xffffffffu) ? 32u : (u32)__ffs(~pv) - 1u);
+        u32 srun = ps ? (u32)__ffs(ps) - 1u : 32u;
+        u32 codes = c.codes;
+        u32 vm = (lane < ENC_HALO) ? 0u : (c.vmask << 16);      // halo lanes own no windows
+        u32 sm = c.smask << 16;
+        // phase 1: roll, pack the valid canonical keys (co-hash: keys whose prefix is the reverse strand get bit
+        // patterns resolved again in phase 2 from the key itself, so only the key is staged)
+        u32 nvalid = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const u32 cc = codes >> 30;
+            codes <<= 2;
+            const bool valid = (vm >> 31) != 0, start = (sm >> 31) != 0;
+            vm <<= 1;
+            sm <<= 1;
+            f = (f << 2) | cc;
+            rc = (rc >> 2) | ((u64)(3u - cc) << top);
+            vrun = valid ? vrun + 1u : 0u;
+            srun = start ? 0u : srun + 1u;
+            nk_tot += (vrun >= k && srun + 1u >= k) ? 1u : 0u;
+            const bool ok = vrun >= l && srun + 1u >= l;
+            const unsigned okm = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const u64 fm = f & lmask;
+                stage[nvalid + __popc(okm & lt_mask)] = fm < rc ? fm : rc;
+            }
+            nvalid += __popc(okm);
+        }
+        nl_tot += nvalid;   // warp-uniform: counted once per warp below
+        __syncwarp();
+        // phase 2: probe 4 keys per lane per round of warp-uniform steps, every lane busy
+        for (u32 g = 0; g < nvalid; g += 128) {
+            u64 key[4];
+            u32 bucket[4];
+            K4 q[4];
+            u32 pend = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const u32 idx = g + i * 32 + lane;
+                key[i] = 0;
+                if (idx < nvalid) {
+                    key[i] = stage[idx];
+                    pend |= 1u << i;
+                }
+                if (COHASH) bucket[i] = prefix_home_bucket(key[i], revcomp64(key[i], l), kmask, nbuckets);
+                else bucket[i] = (u32)hash_bucket(key[i], nbuckets);
+            }
+            u32 probes = 0;
+            while (__any_sync(0xffffffffu, pend != 0)) {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (pend & (1u << i)) q[i] = ld_bucket_cg(tab_keys + (u64)bucket[i] * EULER_BUCKET);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (pend & (1u << i)) {
+                        u64 *bk = tab_keys + (u64)bucket[i] * EULER_BUCKET;
+                        int fe;
+                        int j = bucket_match(q[i], key[i], fe);
+                        while (j < 0 && fe < EULER_BUCKET) {   // claim the first empty slot (rarely contended)
+                            const u64 old = atomicCAS(bk + fe, EULER_EMPTY_KEY, key[i]);
+                            if (old == EULER_EMPTY_KEY || old == key[i]) j = fe;
+                            else fe++;
+                            // a slot after a lost race may be taken too: re-check it through the CAS itself
+                        }
+                        if (j >= 0) {
+                            atomicAdd(tab_cnt + (u64)bucket[i] * EULER_BUCKET + j, 1u);
+                            pend &= ~(1u << i);
+                        } else if (++bucket[i] == nbuckets) {
+                            bucket[i] = 0;
+                        }
+                    }
+                }
+                if (++probes >= max_probe && pend) { overflow = true; pend = 0; }
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) nk_tot += __shfl_xor_sync(0xffffffffu, nk_tot, d);
+    if (lane == 0) {
+        if (nl_tot) atomicAdd(stats + 0, (u64)nl_tot);
+        if (nk_tot) atomicAdd(stats + 1, (u64)nk_tot);
+    }
+    if (overflow) atomicOr((unsigned long long *)(stats + 2), 1ull);
+}
+
 int enc_count_canonical(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u64 *tab_keys,
                         u32 *tab_cnt, u64 cap, TableHash th, u64 *d_stats)
 {
@@ -279,6 +411,24 @@ int enc_count_canonical(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u3
     const char *env = getenv("EULER_B200_COUNT_PARTS");
     if (env && atoi(env) > 0) parts = (u64)atoi(env);
     const int W = th.span_nb ? (int)(l - th.m + 1) : (th.m == EULER_PREFIX_HOME ? -2 : 0);
+    static int compact = -1;
+    if (compact < 0) {
+        const char *e = getenv("EULER_B200_COUNT_COMPACT");   // 0: the per-position kernel above
+        compact = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (compact && parts == 1 && (W == 0 || W == -2)) {
+        u64 g2 = (u64)ctx->num_sms * 8;
+        const u64 need2 = (ntiles + CC_BLOCK / 32 - 1) / (CC_BLOCK / 32);
+        if (g2 > need2) g2 = need2;
+        if (W == 0)
+            count_compact_kernel<false><<<(unsigned)g2, CC_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, tab_keys,
+                                                                                   tab_cnt, cap, ntiles, d_stats);
+        else
+            count_compact_kernel<true><<<(unsigned)g2, CC_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, tab_keys,
+                                                                                  tab_cnt, cap, ntiles, d_stats);
+        CUDA_TRY(ctx, cudaGetLastError());
+        return EULER_OK;
+    }
     for (u64 p = 0; p < parts; p++) {
         const u64 nb = cap / EULER_BUCKET;
         const u64 lo = nb * p / parts, hi = nb * (p + 1) / parts;
