@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeuler_b200.so")
+LIB_PATH = os.environ.get("EULER_B200_LIBPATH") or os.path.join(_HERE, "libeuler_b200.so")
 
 EV_DTYPE = np.dtype([("vid", np.uint64), ("ep", np.uint32), ("ecount", np.uint32),
                      ("lp", np.uint32), ("lcount", np.uint32)])            # pydebruijn.py:607

@@ -272,17 +272,35 @@ __global__ void __launch_bounds__(CNT_BLOCK, 4) count_canonical_kernel(const uin
 // selects the home rule (plain hash of the key / of the canonical prefix k-mer, common.cuh).
 #define CC_BLOCK 128
 #define CC_KEYS (ENC_ADV * 16)   // valid windows per tile <= 480
+#ifndef CC_KPL
+#define CC_KPL 3   // keys in flight per lane (measured: 2..4 within 2 %)
+#endif
+#ifndef CC_MINB
+#define CC_MINB 9
+#endif
+template <int NK>
 __device__ __forceinline__ int bucket_match(const K4 &q, u64 key, int &first_empty)
 {
-    // slot of `key` in the bucket (0..3) or -1; first_empty = first EMPTY slot or 4
-    const unsigned m = (q.k[0] == key ? 1u : 0u) | (q.k[1] == key ? 2u : 0u) | (q.k[2] == key ? 4u : 0u) | (q.k[3] == key ? 8u : 0u);
-    const unsigned e = (q.k[0] == EULER_EMPTY_KEY ? 1u : 0u) | (q.k[1] == EULER_EMPTY_KEY ? 2u : 0u) |
-                       (q.k[2] == EULER_EMPTY_KEY ? 4u : 0u) | (q.k[3] == EULER_EMPTY_KEY ? 8u : 0u);
-    first_empty = e ? (int)__ffs(e) - 1 : 4;
+    // slot of `key` among the first NK slots of the bucket or -1; first_empty = first EMPTY slot or NK
+    unsigned m = 0, e = 0;
+#pragma unroll
+    for (int t = 0; t < NK; t++) {
+        m |= (q.k[t] == key ? 1u : 0u) << t;
+        e |= (q.k[t] == EULER_EMPTY_KEY ? 1u : 0u) << t;
+    }
+    first_empty = e ? (int)__ffs(e) - 1 : NK;
     return m ? (int)__ffs(m) - 1 : -1;
 }
-template <bool COHASH>
-__global__ void __launch_bounds__(CC_BLOCK, 8) count_compact_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
+// MERGED: the table is an array of 32-byte buckets {key, key, key, counts} -- three keys and one word of
+// counters (16 bits for slots 0 and 1 in the low half, 32 bits for slot 2 in the high half; 32-bit REDs:
+// the 64-bit RED of a 3 x 21-bit layout ran at half rate) -- so the counter of a key lives in the sector
+// the probe just loaded: one DRAM sector per insert instead of two (keys[] and counts[] of the SoA
+// layout).  `cap` then counts 8-byte words (4 per bucket).  A 16-bit counter that overflows carries into
+// its neighbour or is lost; the caller detects that through the checksum (sum of counts != windows) and
+// reruns with the SoA layout.
+#define MERGED_KEYS 3
+template <bool COHASH, bool MERGED>
+__global__ void __launch_bounds__(CC_BLOCK, CC_MINB) count_compact_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
                                                                      const u32 *__restrict__ start_bits, u32 l,
                                                                      u64 *__restrict__ tab_keys, u32 *__restrict__ tab_cnt, u64 cap,
                                                                      u64 ntiles, u64 *__restrict__ stats)
@@ -340,13 +358,13 @@ __global__ void __launch_bounds__(CC_BLOCK, 8) count_compact_kernel(const uint4 
         nl_tot += nvalid;   // warp-uniform: counted once per warp below
         __syncwarp();
         // phase 2: probe 4 keys per lane per round of warp-uniform steps, every lane busy
-        for (u32 g = 0; g < nvalid; g += 128) {
-            u64 key[4];
-            u32 bucket[4];
-            K4 q[4];
+        for (u32 g = 0; g < nvalid; g += 32 * CC_KPL) {
+            u64 key[CC_KPL];
+            u32 bucket[CC_KPL];
+            K4 q[CC_KPL];
             u32 pend = 0;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < CC_KPL; i++) {
                 const u32 idx = g + i * 32 + lane;
                 key[i] = 0;
                 if (idx < nvalid) {
@@ -359,22 +377,23 @@ __global__ void __launch_bounds__(CC_BLOCK, 8) count_compact_kernel(const uint4 
             u32 probes = 0;
             while (__any_sync(0xffffffffu, pend != 0)) {
 #pragma unroll
-                for (int i = 0; i < 4; i++)
+                for (int i = 0; i < CC_KPL; i++)
                     if (pend & (1u << i)) q[i] = ld_bucket_cg(tab_keys + (u64)bucket[i] * EULER_BUCKET);
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
+                for (int i = 0; i < CC_KPL; i++) {
                     if (pend & (1u << i)) {
                         u64 *bk = tab_keys + (u64)bucket[i] * EULER_BUCKET;
                         int fe;
-                        int j = bucket_match(q[i], key[i], fe);
-                        while (j < 0 && fe < EULER_BUCKET) {   // claim the first empty slot (rarely contended)
+                        int j = bucket_match<MERGED ? MERGED_KEYS : EULER_BUCKET>(q[i], key[i], fe);
+                        while (j < 0 && fe < (MERGED ? MERGED_KEYS : EULER_BUCKET)) {   // claim the first empty slot (rarely contended)
                             const u64 old = atomicCAS(bk + fe, EULER_EMPTY_KEY, key[i]);
                             if (old == EULER_EMPTY_KEY || old == key[i]) j = fe;
                             else fe++;
                             // a slot after a lost race may be taken too: re-check it through the CAS itself
                         }
                         if (j >= 0) {
-                            atomicAdd(tab_cnt + (u64)bucket[i] * EULER_BUCKET + j, 1u);
+                            if (MERGED) atomicAdd((u32 *)(bk + 3) + (j >> 1), j == 1 ? 0x10000u : 1u);
+                            else atomicAdd(tab_cnt + (u64)bucket[i] * EULER_BUCKET + j, 1u);
                             pend &= ~(1u << i);
                         } else if (++bucket[i] == nbuckets) {
                             bucket[i] = 0;
@@ -393,6 +412,58 @@ __global__ void __launch_bounds__(CC_BLOCK, 8) count_compact_kernel(const uint4 
         if (nk_tot) atomicAdd(stats + 1, (u64)nk_tot);
     }
     if (overflow) atomicOr((unsigned long long *)(stats + 2), 1ull);
+}
+
+// merged table -> the SoA layout the graph stage reads: keys[4 b + j] / cnt[4 b + j] for j < 3, slot 3 of every bucket empty
+__global__ void __launch_bounds__(256) merged_unpack_kernel(const uint4 *__restrict__ tab, u64 nbuckets, uint4 *__restrict__ keys,
+                                                            uint4 *__restrict__ cnt)
+{
+    const u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    const uint4 lo = tab[2 * b], hi = tab[2 * b + 1];   // {k0, k1}, {k2, counters}
+    keys[2 * b] = lo;
+    keys[2 * b + 1] = make_uint4(hi.x, hi.y, 0xffffffffu, 0xffffffffu);
+    cnt[b] = make_uint4(hi.z & 0xffffu, hi.z >> 16, hi.w, 0u);
+}
+__global__ void __launch_bounds__(256) merged_clear_kernel(uint4 *__restrict__ tab, u64 nbuckets)
+{
+    const u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    tab[2 * b] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    tab[2 * b + 1] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
+}
+// count into a merged table `tab` (cap_words = 4 * buckets, caller-cleared with enc_merged_clear), then unpack
+int enc_merged_clear(euler_ctx *ctx, u64 *tab, u64 cap_words)
+{
+    const u64 nb = cap_words / 4;
+    merged_clear_kernel<<<grid_for(nb, 256), 256, 0, ctx->stream>>>((uint4 *)tab, nb);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+int enc_count_merged(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u64 *tab, u64 cap_words, bool cohash,
+                     u64 *d_stats)
+{
+    if (!n_bases) return EULER_OK;
+    const u64 nchunks = (n_bases + 15) / 16;
+    const u64 ntiles = (nchunks + ENC_ADV - 1) / ENC_ADV;
+    u64 g2 = (u64)ctx->num_sms * CC_MINB;
+    const u64 need2 = (ntiles + CC_BLOCK / 32 - 1) / (CC_BLOCK / 32);
+    if (g2 > need2) g2 = need2;
+    if (cohash)
+        count_compact_kernel<true, true><<<(unsigned)g2, CC_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, tab,
+                                                                                    nullptr, cap_words, ntiles, d_stats);
+    else
+        count_compact_kernel<false, true><<<(unsigned)g2, CC_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, tab,
+                                                                                     nullptr, cap_words, ntiles, d_stats);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+int enc_merged_unpack(euler_ctx *ctx, const u64 *tab, u64 cap_words, u64 *keys, u32 *cnt)
+{
+    const u64 nb = cap_words / 4;
+    merged_unpack_kernel<<<grid_for(nb, 256), 256, 0, ctx->stream>>>((const uint4 *)tab, nb, (uint4 *)keys, (uint4 *)cnt);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
 }
 
 int enc_count_canonical(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u64 *tab_keys,
@@ -417,14 +488,14 @@ int enc_count_canonical(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u3
         compact = (e && atoi(e) == 0) ? 0 : 1;
     }
     if (compact && parts == 1 && (W == 0 || W == -2)) {
-        u64 g2 = (u64)ctx->num_sms * 8;
+        u64 g2 = (u64)ctx->num_sms * CC_MINB;
         const u64 need2 = (ntiles + CC_BLOCK / 32 - 1) / (CC_BLOCK / 32);
         if (g2 > need2) g2 = need2;
         if (W == 0)
-            count_compact_kernel<false><<<(unsigned)g2, CC_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, tab_keys,
+            count_compact_kernel<false, false><<<(unsigned)g2, CC_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, tab_keys,
                                                                                    tab_cnt, cap, ntiles, d_stats);
         else
-            count_compact_kernel<true><<<(unsigned)g2, CC_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, tab_keys,
+            count_compact_kernel<true, false><<<(unsigned)g2, CC_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, tab_keys,
                                                                                   tab_cnt, cap, ntiles, d_stats);
         CUDA_TRY(ctx, cudaGetLastError());
         return EULER_OK;

@@ -11,6 +11,13 @@ int enc_compute_kmers(euler_ctx *ctx, const u64 *d_lmers, u64 n, u64 mask, u64 *
 int enc_count_canonical(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u64 *tab_keys,
                         u32 *tab_cnt, u64 cap, TableHash th, u64 *d_stats);
 
+// merged count table (32-byte buckets {key, key, key, 3 x 21-bit counters}; cap_words = 4 * buckets)
+int enc_merged_clear(euler_ctx *ctx, u64 *tab, u64 cap_words);
+int enc_count_merged(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u64 *tab, u64 cap_words, bool cohash,
+                     u64 *d_stats);
+// -> SoA keys[cap_words] / cnt[cap_words] (slot 3 of every bucket empty)
+int enc_merged_unpack(euler_ctx *ctx, const u64 *tab, u64 cap_words, u64 *keys, u32 *cnt);
+
 // ---- graph.cu
 // vertex-id lookup over the canonical k-mer table: id of strand 0 (canonical orientation) in id0,
 // strand 1 in id1 (id1 == NULL: slot-order ids, strand 1 = id0 + 1)

@@ -71,6 +71,7 @@ struct Pipeline {
     // graph artefacts
     DevArr<u64> lkeys, vkeys;
     DevArr<u32> lvals, loffs, ev1, ev2, lcount, ecount, lstart, estart;
+    DevArr<u64> lt_merged;  // merged count table (encode.cu, MERGED): 32-byte buckets {key, key, key, counters}
     DevArr<u32> vt_bbase;  // id of the first strand of each vertex-table bucket (slot-order ids)
     DevArr<u32> deg;  // paired degree regions u32[8 V] (common.cuh, DegOut) of the slot-order fast paths
     DevArr<euler_vertex> ev;
@@ -108,7 +109,7 @@ void pipeline_destroy(Pipeline *p)
     p->lcount.free(); p->ecount.free(); p->lstart.free(); p->estart.free(); p->ev.free(); p->ee.free();
     if (p->recv_buf) cudaFree(p->recv_buf);
     p->lev.free(); p->ent.free(); p->sort_k.free(); p->sort_v.free(); p->sort_hist.free();
-    p->blk_keys.free(); p->blk_cur.free(); p->deg.free(); p->vt_bbase.free();
+    p->blk_keys.free(); p->blk_cur.free(); p->deg.free(); p->vt_bbase.free(); p->lt_merged.free();
     p->wlt_keys.free(); p->wvt_keys.free(); p->wlt_cnt.free(); p->lkeys_hi.free(); p->vkeys_hi.free(); p->tf.free();
     delete p;
 }
@@ -169,6 +170,13 @@ static bool use_cohash(bool dflt)
     const char *e = getenv("EULER_B200_COHASH");
     return e ? atoi(e) != 0 : dflt;
 }
+// EULER_B200_MERGED=1: count into the merged table (one sector per insert) and unpack it for the graph stage
+static bool use_merged_table()
+{
+    const char *e = getenv("EULER_B200_MERGED");
+    return e && atoi(e) == 1;
+}
+static bool N_l_fits_merged(u64) { return true; }
 static u64 cap_for(u64 n) { return round_up((u64)((double)(n < 64 ? 64 : n) / table_load()) + 1, 1024); }
 
 // l in 33..64: the same stages over two-word keys (wide.cu).  Correctness-first: one thread per read,
@@ -291,6 +299,8 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
     u64 lt_cap = cap_for(est_l), vt_cap = cap_for(est_v);
     // packed count table: power-of-two bucket count, load factor in (0.375, 0.75]
     bool packed = use_packed_table();
+    bool merged = !packed && use_merged_table() && !table_hash_for(lt_cap, k).span_nb && N_l_fits_merged(B);
+    if (merged) lt_cap = round_up(lt_cap / 3 * 4 + 4, 1024);   // three key slots per 4-word bucket
     u32 pk_b = 8;
     const u64 side_cap = 16384;
     if (packed) {
@@ -325,6 +335,15 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
             EULER_TRY(enc_unpack(ctx, P->lt_packed.ptr(), pk_b, P->side_keys.ptr(), P->side_cnt.ptr(), side_cap,
                                  P->stats.ptr() + 7, P->lt.keys(), P->lt.cnt()));
             launches += 2;
+        } else if (merged) {
+            EULER_TRY(P->lt_merged.reserve(ctx, lt_cap));
+            EULER_TRY(enc_merged_clear(ctx, P->lt_merged.ptr(), lt_cap));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
+            EULER_TRY(enc_count_merged(ctx, P->d_buf, B, P->start_bits.ptr(), l, P->lt_merged.ptr(), lt_cap, use_cohash(false),
+                                       P->stats.ptr()));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+            EULER_TRY(enc_merged_unpack(ctx, P->lt_merged.ptr(), lt_cap, P->lt.keys(), P->lt.cnt()));
+            launches += 2;
         } else {
             EULER_TRY(graph_table_clear(ctx, P->lt.keys(), P->lt.cnt(), lt_cap));
             l2_window(ctx, P->lt.b.p, P->lt.bytes());
@@ -342,6 +361,13 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
         EULER_TRY(graph_vertex_insert(ctx, P->lt.keys(), lt_cap, l, P->vt_keys.ptr(), vt_cap, vth, P->stats.ptr() + 2));
         EULER_TRY(graph_slot_scan(ctx, P->vt_keys.ptr(), vt_cap, k, P->vt_id0.ptr(), P->stats.ptr() + 4));
         EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 6));
+        if (merged && (h[2] & 7) == 0 && (h[3] >> 32) != 2 * h[0]) {
+            // a 16-bit counter of the merged table overflowed: redo with the SoA table and its 32-bit counters
+            merged = false;
+            lt_cap = lt_cap / 4 * 3;
+            retries++;
+            continue;
+        }
         if ((h[2] & 7) == 0) break;
         if (++retries > 10) return euler_fail(ctx, EULER_ERR_OVERFLOW, "hash table overflow after %u regrows", retries);
         if (h[2] & 4) packed = false;   // wrap side table full (extreme repeats): use the SoA kernel

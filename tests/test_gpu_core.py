@@ -237,7 +237,7 @@ def test_pipeline_device_resident_synthetic(ctx):
     assert np.array_equal(ctx.download(N.ART_LMER_VALUES), g.lvals)
 
 
-@pytest.mark.parametrize("knob", ["EULER_B200_MINHASH", "EULER_B200_PACKED", "EULER_B200_COHASH"])
+@pytest.mark.parametrize("knob", ["EULER_B200_MINHASH", "EULER_B200_PACKED", "EULER_B200_COHASH", "EULER_B200_MERGED"])
 def test_opt_in_table_variants_give_the_same_graph(knob):
     """EULER_B200_MINHASH=1 (minimizer-ordered homes; rolling-minimum kernels for l = 32 / 22, the
     brute-force one otherwise), EULER_B200_PACKED=1 (packed quotient count table, count-wrap side
