@@ -357,51 +357,72 @@ __global__ void __launch_bounds__(CC_BLOCK, CC_MINB) count_compact_kernel(const 
         }
         nl_tot += nvalid;   // warp-uniform: counted once per warp below
         __syncwarp();
-        // phase 2: probe 4 keys per lane per round of warp-uniform steps, every lane busy
-        for (u32 g = 0; g < nvalid; g += 32 * CC_KPL) {
-            u64 key[CC_KPL];
-            u32 bucket[CC_KPL];
-            K4 q[CC_KPL];
-            u32 pend = 0;
-#pragma unroll
-            for (int i = 0; i < CC_KPL; i++) {
-                const u32 idx = g + i * 32 + lane;
-                key[i] = 0;
-                if (idx < nvalid) {
-                    key[i] = stage[idx];
-                    pend |= 1u << i;
-                }
-                if (COHASH) bucket[i] = prefix_home_bucket(key[i], revcomp64(key[i], l), kmask, nbuckets);
-                else bucket[i] = (u32)hash_bucket(key[i], nbuckets);
-            }
-            u32 probes = 0;
-            while (__any_sync(0xffffffffu, pend != 0)) {
-#pragma unroll
-                for (int i = 0; i < CC_KPL; i++)
-                    if (pend & (1u << i)) q[i] = ld_bucket_cg(tab_keys + (u64)bucket[i] * EULER_BUCKET);
+        // phase 2: probe CC_KPL keys per lane, every lane busy.  Pass 0 gives every key ONE probe step (its home
+        // bucket); the few keys whose home is full (~7 %) are packed back into the staging buffer and finished
+        // together in pass 1 -- otherwise every group of 96 keys would pay extra warp-wide rounds for its 6 stragglers.
+        u32 ncur = nvalid;
+#pragma unroll 1
+        for (int pass = 0; pass < 2 && ncur; pass++) {
+            u32 nleft = 0;
+#pragma unroll 1
+            for (u32 g = 0; g < ncur; g += 32 * CC_KPL) {
+                u64 key[CC_KPL];
+                u32 bucket[CC_KPL];
+                K4 q[CC_KPL];
+                u32 pend = 0;
 #pragma unroll
                 for (int i = 0; i < CC_KPL; i++) {
-                    if (pend & (1u << i)) {
-                        u64 *bk = tab_keys + (u64)bucket[i] * EULER_BUCKET;
-                        int fe;
-                        int j = bucket_match<MERGED ? MERGED_KEYS : EULER_BUCKET>(q[i], key[i], fe);
-                        while (j < 0 && fe < (MERGED ? MERGED_KEYS : EULER_BUCKET)) {   // claim the first empty slot (rarely contended)
-                            const u64 old = atomicCAS(bk + fe, EULER_EMPTY_KEY, key[i]);
-                            if (old == EULER_EMPTY_KEY || old == key[i]) j = fe;
-                            else fe++;
-                            // a slot after a lost race may be taken too: re-check it through the CAS itself
-                        }
-                        if (j >= 0) {
-                            if (MERGED) atomicAdd((u32 *)(bk + 3) + (j >> 1), j == 1 ? 0x10000u : 1u);
-                            else atomicAdd(tab_cnt + (u64)bucket[i] * EULER_BUCKET + j, 1u);
-                            pend &= ~(1u << i);
-                        } else if (++bucket[i] == nbuckets) {
-                            bucket[i] = 0;
+                    const u32 idx = g + i * 32 + lane;
+                    key[i] = 0;
+                    if (idx < ncur) {
+                        key[i] = stage[idx];
+                        pend |= 1u << i;
+                    }
+                    if (COHASH) bucket[i] = prefix_home_bucket(key[i], revcomp64(key[i], l), kmask, nbuckets);
+                    else bucket[i] = (u32)hash_bucket(key[i], nbuckets);
+                    if (pass && ++bucket[i] == nbuckets) bucket[i] = 0;   // stragglers: the home bucket was full
+                }
+                __syncwarp();   // all keys of this group are in registers before stragglers overwrite the buffer
+                u32 probes = 0;
+                while (__any_sync(0xffffffffu, pend != 0)) {
+#pragma unroll
+                    for (int i = 0; i < CC_KPL; i++)
+                        if (pend & (1u << i)) q[i] = ld_bucket_cg(tab_keys + (u64)bucket[i] * EULER_BUCKET);
+#pragma unroll
+                    for (int i = 0; i < CC_KPL; i++) {
+                        if (pend & (1u << i)) {
+                            u64 *bk = tab_keys + (u64)bucket[i] * EULER_BUCKET;
+                            int fe;
+                            int j = bucket_match<MERGED ? MERGED_KEYS : EULER_BUCKET>(q[i], key[i], fe);
+                            while (j < 0 && fe < (MERGED ? MERGED_KEYS : EULER_BUCKET)) {   // claim the first empty slot
+                                const u64 old = atomicCAS(bk + fe, EULER_EMPTY_KEY, key[i]);
+                                if (old == EULER_EMPTY_KEY || old == key[i]) j = fe;
+                                else fe++;   // lost the race for this slot: the next one is tried through its own CAS
+                            }
+                            if (j >= 0) {
+                                if (MERGED) atomicAdd((u32 *)(bk + 3) + (j >> 1), j == 1 ? 0x10000u : 1u);
+                                else atomicAdd(tab_cnt + (u64)bucket[i] * EULER_BUCKET + j, 1u);
+                                pend &= ~(1u << i);
+                            } else if (++bucket[i] == nbuckets) {
+                                bucket[i] = 0;
+                            }
                         }
                     }
+                    if (pass == 0) break;
+                    if (++probes >= max_probe && pend) { overflow = true; pend = 0; }
                 }
-                if (++probes >= max_probe && pend) { overflow = true; pend = 0; }
+                if (pass == 0) {   // pack the stragglers to the front of the buffer (fewer than the keys already consumed)
+#pragma unroll
+                    for (int i = 0; i < CC_KPL; i++) {
+                        const bool left = (pend >> i) & 1u;
+                        const unsigned lm = __ballot_sync(0xffffffffu, left);
+                        if (left) stage[nleft + __popc(lm & lt_mask)] = key[i];
+                        nleft += __popc(lm);
+                    }
+                }
             }
+            __syncwarp();
+            ncur = nleft;
         }
         __syncwarp();
     }
