@@ -167,6 +167,21 @@ __device__ __forceinline__ int bucket_claim(u64 *bucket_keys, const K4 &q, u64 k
     return -1;
 }
 
+// branch-free bucket match (count kernels)
+template <int NK>
+__device__ __forceinline__ int bucket_match(const K4 &q, u64 key, int &first_empty)
+{
+    // slot of `key` among the first NK slots of the bucket or -1; first_empty = first EMPTY slot or NK
+    unsigned m = 0, e = 0;
+#pragma unroll
+    for (int t = 0; t < NK; t++) {
+        m |= (q.k[t] == key ? 1u : 0u) << t;
+        e |= (q.k[t] == EULER_EMPTY_KEY ? 1u : 0u) << t;
+    }
+    first_empty = e ? (int)__ffs(e) - 1 : NK;
+    return m ? (int)__ffs(m) - 1 : -1;
+}
+
 // ---- minimizer-ordered homes -------------------------------------------------------------------
 // With a plain hash the ~70 l-mers of a read touch ~70 random sectors of a table far larger than
 // L2.  Ordering the table by the key's minimizer (smallest scrambled canonical m-mer) sends the

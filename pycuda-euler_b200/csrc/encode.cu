@@ -278,19 +278,6 @@ __global__ void __launch_bounds__(CNT_BLOCK, 4) count_canonical_kernel(const uin
 #ifndef CC_MINB
 #define CC_MINB 9
 #endif
-template <int NK>
-__device__ __forceinline__ int bucket_match(const K4 &q, u64 key, int &first_empty)
-{
-    // slot of `key` among the first NK slots of the bucket or -1; first_empty = first EMPTY slot or NK
-    unsigned m = 0, e = 0;
-#pragma unroll
-    for (int t = 0; t < NK; t++) {
-        m |= (q.k[t] == key ? 1u : 0u) << t;
-        e |= (q.k[t] == EULER_EMPTY_KEY ? 1u : 0u) << t;
-    }
-    first_empty = e ? (int)__ffs(e) - 1 : NK;
-    return m ? (int)__ffs(m) - 1 : -1;
-}
 // MERGED: the table is an array of 32-byte buckets {key, key, key, counts} -- three keys and one word of
 // counters (16 bits for slots 0 and 1 in the low half, 32 bits for slot 2 in the high half; 32-bit REDs:
 // the 64-bit RED of a 3 x 21-bit layout ran at half rate) -- so the counter of a key lives in the sector
