@@ -347,7 +347,7 @@ def main():
                        "edges": int(st.edge_count), "lmer_table_capacity": int(st.lmer_table_capacity),
                        "retries": int(st.retries)},
             "stage_ms": {"count_kernel": kern_ms_max, "graph": graph_ms, "step_wall": wall_ms},
-            "roofline": {"bound": "hbm", "kernel": ("count_canonical_kernel" if l <= 32 else "wide_count_kernel") if world == 1 else
+            "roofline": {"bound": "hbm", "kernel": ("count_compact_kernel" if l <= 32 else "wide_count_kernel") if world == 1 else
                          ("dist_count_keys_kernel" if l <= 32 else "wide_count_keys_kernel") + " (one launch per source rank)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": a_kernel,
