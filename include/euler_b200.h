@@ -194,6 +194,12 @@ int euler_pipeline_run_dev(euler_ctx *ctx, const void *d_buf, const void *d_read
 int euler_pipeline_run_host(euler_ctx *ctx, const char *buf, const uint64_t *read_off, uint64_t nreads,
                             uint32_t l, uint32_t flags, uint64_t distinct_hint, euler_stats *stats);
 
+/* the graph stage on an existing l-mer table instead of reads -- e.g. the per-rank tables of the partitioned
+ * path joined on one GPU (assembler.py): keys[n] (either strand or both; canonicalised), counts[n] = both-strand
+ * multiplicities.  l in [2,32].  Artefacts and contigs as after euler_pipeline_run_host. */
+int euler_pipeline_run_lmers(euler_ctx *ctx, const uint64_t *keys, const uint32_t *counts, uint64_t n, uint32_t l,
+                             uint32_t flags, euler_stats *stats);
+
 /* artefacts of the last run */
 enum {
     EULER_ART_LMER_KEYS = 0,   /* u64[U_l] */

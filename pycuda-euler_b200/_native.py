@@ -92,6 +92,7 @@ def load():
         "euler_emit_contigs": [vp, vp, u32, vp, u32, u32, vp, vp, vp],
         "euler_pipeline_run_dev": [vp, vp, vp, u64, u64, u32, u32, u64, vp],
         "euler_pipeline_run_host": [vp, vp, vp, u64, u32, u32, u64, vp],
+        "euler_pipeline_run_lmers": [vp, vp, vp, u64, u32, u32, vp],
         "euler_pipeline_artifact_bytes": [vp, i32, vp],
         "euler_pipeline_download": [vp, i32, vp, u64],
         "euler_pipeline_device_ptr": [vp, i32, vp],
@@ -448,6 +449,14 @@ class Context:
         st = Stats()
         self.check(self.lib.euler_pipeline_run_host(self.h, _p(buf), _p(off), len(off) - 1, int(l), int(flags),
                                                     int(distinct_hint), C.byref(st)))
+        return st
+
+    def run_lmers(self, keys, counts, l, flags=0):
+        """graph stage on an l-mer table (packed keys, both-strand counts) instead of reads"""
+        keys = _arr(keys, np.uint64)
+        counts = _arr(counts, np.uint32)
+        st = Stats()
+        self.check(self.lib.euler_pipeline_run_lmers(self.h, _p(keys), _p(counts), len(keys), int(l), int(flags), C.byref(st)))
         return st
 
     def run_host_ptr(self, buf_ptr, off_ptr, nreads, l, flags=0, distinct_hint=0):

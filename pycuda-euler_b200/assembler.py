@@ -14,6 +14,9 @@ Modes
                     which compacts it into unitigs and their link graph.  The result equals the single-GPU
                     assembly of the whole file -- unlike the reference's partitions, which never see each
                     other's reads.
+  euler             the GPU-Euler path (assemble2 mode='euler': de Bruijn graph with k-mer EDGES, Euler tour,
+                    partial contigs).  Across GPUs the per-rank edge tables are joined on rank 0, which runs the
+                    graph and tour stages (euler_pipeline_run_lmers): same contigs as on one GPU.
   replicas          the reference's semantics: every rank assembles its own partition of the reads
                     independently and writes <out>.part<rank>.
 Outputs: FASTA contigs in -o, the GFA link graph in <out>.gfa (unitig mode).
@@ -78,7 +81,7 @@ def main(argv=None):
     ap.add_argument('-k', dest='k', type=int, default=31, help='kmer size')
     ap.add_argument('-d', action='store_true', default=False, help='Use DDFS (accepted for compatibility; ignored)')
     ap.add_argument('--limit', type=int, default=1, help='keep k-mers with both-strand count > limit (build() default 1)')
-    ap.add_argument('--mode', choices=['unitig', 'replicas'], default='unitig')
+    ap.add_argument('--mode', choices=['unitig', 'euler', 'replicas'], default='unitig')
     args = ap.parse_args(argv)
     logging.basicConfig(level=logging.INFO, format='%(asctime)s %(levelname)s %(message)s')
     log = logging.getLogger("assembler")
@@ -96,6 +99,14 @@ def main(argv=None):
     nreads, nbases = ctx.ingest(data[a:b], fmt)
     log.info("rank %d/%d: bytes [%d, %d): %d reads, %d bases", rank, world, a, b, nreads, nbases)
 
+    if args.mode == 'euler' and world == 1:
+        contigs = []
+        if nbases:
+            ctx.run_ingested(K, N.RUN_CANONICAL_IDS | N.RUN_EXPAND_EDGES)
+            contigs = ctx.pipeline_contigs()
+        write_outputs(args.output_filename, contigs, None, K)
+        log.info("%d contigs -> %s", len(contigs), args.output_filename)
+        return 0
     if world == 1 or args.mode == 'replicas':
         contigs = ctx.unitigs_ingested(K, args.limit) if nbases else []
         from referenceassembler import referenceAssembler as ram
@@ -112,7 +123,7 @@ def main(argv=None):
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if K < 2 or K > 32:
-        raise SystemExit("unitig mode across GPUs needs 2 <= k <= 32")
+        raise SystemExit("one assembly across GPUs needs 2 <= k <= 32")
     buf, off = ctx.ingest_download()
     d_reads = torch.zeros(max(len(buf), 1) + 16, dtype=torch.uint8, device="cuda")
     d_reads[:len(buf)] = torch.from_numpy(np.ascontiguousarray(buf)).cuda()
@@ -122,8 +133,9 @@ def main(argv=None):
     st, info = build_partitioned(ctx, d_reads, d_off, nreads, nbases, K, rank, world, 0)
     keys = ctx.download(N.ART_LMER_KEYS)
     vals = ctx.download(N.ART_LMER_VALUES)
-    keep = vals > args.limit
-    keys, vals = keys[keep], vals[keep]
+    if args.mode == 'unitig':
+        keep = vals > args.limit
+        keys, vals = keys[keep], vals[keep]
     log.info("rank %d: %d k-mer windows sent, %d received, %d owned k-mers above the limit", rank, info["sent_keys"],
              info["recv_keys"], len(keys))
     gathered = [None] * world if rank == 0 else None
@@ -131,9 +143,15 @@ def main(argv=None):
     if rank == 0:
         all_k = np.concatenate([g[0] for g in gathered])
         all_v = np.concatenate([g[1] for g in gathered])
-        contigs = ctx.unitigs_from_kmers(all_k, all_v, K) if len(all_k) else []
         from referenceassembler import referenceAssembler as ram
-        G = ram.link_graph(contigs, K) if (contigs and K <= 31) else None
+        if args.mode == 'euler':
+            contigs, G = [], None
+            if len(all_k):
+                ctx.run_lmers(all_k, all_v, K, N.RUN_CANONICAL_IDS | N.RUN_EXPAND_EDGES)
+                contigs = ctx.pipeline_contigs()
+        else:
+            contigs = ctx.unitigs_from_kmers(all_k, all_v, K) if len(all_k) else []
+            G = ram.link_graph(contigs, K) if (contigs and K <= 31) else None
         write_outputs(args.output_filename, contigs, G, K)
         log.info("%d k-mers joined, %d contigs -> %s", len(all_k), len(contigs), args.output_filename)
     dist.barrier()

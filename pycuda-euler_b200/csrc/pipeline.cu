@@ -71,6 +71,11 @@ struct Pipeline {
     // graph artefacts
     DevArr<u64> lkeys, vkeys;
     DevArr<u32> lvals, loffs, ev1, ev2, lcount, ecount, lstart, estart;
+    // table input (euler_pipeline_run_lmers): both-strand or canonical l-mers with counts instead of reads
+    DevArr<u64> tbl_keys;
+    DevArr<u32> tbl_cnt;
+    u64 tbl_n = 0;
+    bool from_table = false;
     DevArr<u64> lt_merged;  // merged count table (encode.cu, MERGED): 32-byte buckets {key, key, key, counters}
     DevArr<u32> vt_bbase;  // id of the first strand of each vertex-table bucket (slot-order ids)
     DevArr<u32> deg;  // paired degree regions u32[8 V] (common.cuh, DegOut) of the slot-order fast paths
@@ -109,7 +114,7 @@ void pipeline_destroy(Pipeline *p)
     p->lcount.free(); p->ecount.free(); p->lstart.free(); p->estart.free(); p->ev.free(); p->ee.free();
     if (p->recv_buf) cudaFree(p->recv_buf);
     p->lev.free(); p->ent.free(); p->sort_k.free(); p->sort_v.free(); p->sort_hist.free();
-    p->blk_keys.free(); p->blk_cur.free(); p->deg.free(); p->vt_bbase.free(); p->lt_merged.free();
+    p->blk_keys.free(); p->blk_cur.free(); p->deg.free(); p->vt_bbase.free(); p->lt_merged.free(); p->tbl_keys.free(); p->tbl_cnt.free();
     p->wlt_keys.free(); p->wvt_keys.free(); p->wlt_cnt.free(); p->lkeys_hi.free(); p->vkeys_hi.free(); p->tf.free();
     delete p;
 }
@@ -296,10 +301,12 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
     if (distinct_hint) { est_l = distinct_hint; est_v = distinct_hint + distinct_hint / 16; }
     else if (P->learned_bases == B && P->learned_lc) { est_l = P->learned_lc + P->learned_lc / 32; est_v = P->learned_vc + P->learned_vc / 32; }
     else { est_l = B ? B : 1; est_v = est_l; }
+    const bool from_table = P->from_table;
+    if (from_table && !distinct_hint) { est_l = P->tbl_n ? P->tbl_n : 1; est_v = 2 * est_l; }
     u64 lt_cap = cap_for(est_l), vt_cap = cap_for(est_v);
     // packed count table: power-of-two bucket count, load factor in (0.375, 0.75]
-    bool packed = use_packed_table();
-    bool merged = !packed && use_merged_table() && !table_hash_for(lt_cap, k).span_nb && N_l_fits_merged(B);
+    bool packed = !from_table && use_packed_table();
+    bool merged = !from_table && !packed && use_merged_table() && !table_hash_for(lt_cap, k).span_nb && N_l_fits_merged(B);
     if (merged) lt_cap = round_up(lt_cap / 3 * 4 + 4, 1024);   // three key slots per 4-word bucket
     u32 pk_b = 8;
     const u64 side_cap = 16384;
@@ -312,7 +319,7 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
     TableHash lth = {0, 0}, vth = {0, 0};
     u32 retries = 0, launches = 1;  // mark_starts
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
-    EULER_TRY(enc_mark_starts(ctx, P->d_off, P->nreads, B, P->start_bits.ptr()));
+    if (!from_table) EULER_TRY(enc_mark_starts(ctx, P->d_off, P->nreads, B, P->start_bits.ptr()));
     while (true) {
         P->lt_cap = lt_cap; P->vt_cap = vt_cap;
         EULER_TRY(P->lt.reserve(ctx, lt_cap));
@@ -335,6 +342,14 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
             EULER_TRY(enc_unpack(ctx, P->lt_packed.ptr(), pk_b, P->side_keys.ptr(), P->side_cnt.ptr(), side_cap,
                                  P->stats.ptr() + 7, P->lt.keys(), P->lt.cnt()));
             launches += 2;
+        } else if (from_table) {
+            // the table of a previous count (e.g. the per-rank tables of the partitioned path, joined): canonical insert,
+            // both-strand count v -> canonical count (v for a palindrome is 2n)
+            EULER_TRY(graph_table_clear(ctx, P->lt.keys(), P->lt.cnt(), lt_cap));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
+            EULER_TRY(unitig_dict_table(ctx, P->tbl_keys.ptr(), P->tbl_cnt.ptr(), P->tbl_n, l, P->lt.keys(), P->lt.cnt(), lt_cap,
+                                        P->stats.ptr() + 2));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
         } else if (merged) {
             EULER_TRY(P->lt_merged.reserve(ctx, lt_cap));
             EULER_TRY(enc_merged_clear(ctx, P->lt_merged.ptr(), lt_cap));
@@ -374,7 +389,7 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
         if (h[2] & 1) { lt_cap *= 2; pk_b++; }
         if (h[2] & 2) vt_cap *= 2;
     }
-    const u64 N_l = h[0], N_k = h[1], U_l = h[3] & 0xffffffffull, V = h[4];
+    const u64 N_l = from_table ? (h[3] >> 32) / 2 : h[0], N_k = h[1], U_l = h[3] & 0xffffffffull, V = h[4];
     const u64 E = 2 * N_l;
     P->U_l = U_l; P->V = V; P->E = E;
     if (V >= 0x3fffffffull || N_l >= 0x7fffffffull)
@@ -587,6 +602,29 @@ int euler_pipeline_run_host(euler_ctx *ctx, const char *buf, const uint64_t *rea
     CUDA_TRY(ctx, cudaMemcpyAsync(P->in_off.ptr(), read_off, (nreads + 1) * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     P->d_buf = P->in_buf.ptr(); P->d_off = P->in_off.ptr(); P->nreads = nreads; P->n_bases = B;
     return pipeline_run(ctx, P, l, flags, distinct_hint, stats);
+}
+
+// graph stage on a given l-mer table (keys: either strand or both, counts: both-strand counts); l <= 32
+int euler_pipeline_run_lmers(euler_ctx *ctx, const uint64_t *keys, const uint32_t *counts, uint64_t n, uint32_t l, uint32_t flags,
+                             euler_stats *stats)
+{
+    if (!ctx) return EULER_ERR_ARG;
+    if (n && (!keys || !counts)) return euler_fail(ctx, EULER_ERR_ARG, "null table");
+    if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Pipeline *P = get_pipe(ctx);
+    P->ingested = false;
+    EULER_TRY(P->tbl_keys.reserve(ctx, n + 1));
+    EULER_TRY(P->tbl_cnt.reserve(ctx, n + 1));
+    if (n) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(P->tbl_keys.ptr(), keys, n * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(P->tbl_cnt.ptr(), counts, n * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    P->tbl_n = n; P->from_table = true;
+    P->d_buf = nullptr; P->d_off = nullptr; P->nreads = 0; P->n_bases = 0;
+    const int rc = pipeline_run(ctx, P, l, flags, 0, stats);
+    P->from_table = false;
+    return rc;
 }
 
 static int artifact(euler_ctx *ctx, int which, void **p, u64 *bytes)

@@ -32,3 +32,8 @@ print('single-GPU contigs', len(a), 'multi-GPU contigs', len(b), 'equal sets:', 
 assert a == b and len(a) > 0
 print('gfa links:', sum(1 for l in open('/tmp/multi.fa.gfa') if l[0] == 'L'), 'vs', sum(1 for l in open('/tmp/one.fa.gfa') if l[0] == 'L'))
 PY
+# Euler mode: identical contig LIST (canonical ids make the tour deterministic)
+python pycuda-euler_b200/assembler.py -i /tmp/reads.fq -o /tmp/one_e.fa -k 32 --mode euler
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29532 \
+    pycuda-euler_b200/assembler.py -i /tmp/reads.fq -o /tmp/multi_e.fa -k 32 --mode euler
+cmp /tmp/one_e.fa /tmp/multi_e.fa && echo "euler mode: identical output ($(grep -c '>' /tmp/one_e.fa) contigs)"

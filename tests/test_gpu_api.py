@@ -88,6 +88,34 @@ def test_referenceassembler_module(ctx, fixture):
         ra.get_contig_forward({"ACG": 2, "CGT": 2}, "TTT")
 
 
+@pytest.mark.parametrize("l", [10, 18, 32])
+def test_graph_stage_from_an_lmer_table(ctx, g200_reads, l):
+    """euler_pipeline_run_lmers: the graph stage fed with a count table (what the multi-GPU driver joins on one
+    rank) gives the artefacts and contigs of the run on the reads themselves."""
+    import _native as N
+    from util import random_reads
+    reads = g200_reads if l <= 18 else random_reads(9, 300, genome_len=3000)
+    buf, off = oracle.pack_reads(reads)
+    flags = N.RUN_EXPAND_EDGES | N.RUN_CANONICAL_IDS
+    st0 = ctx.run_host(buf, off, l, flags)
+    names = ("LMER_KEYS", "LMER_VALUES", "LMER_OFFSETS", "KMER_KEYS", "LCOUNT", "ECOUNT", "LSTART", "ESTART", "EV", "EDGE_V1",
+             "EDGE_V2", "EE", "LEV", "ENT")
+    a0 = {n: ctx.download(getattr(N, "ART_" + n)) for n in names}
+    c0 = ctx.pipeline_contigs()
+    lk, lv = a0["LMER_KEYS"], a0["LMER_VALUES"]
+    perm = np.random.default_rng(l).permutation(lk.size)
+    for keys, vals in ((lk[perm], lv[perm]), (lk, lv)):
+        st1 = ctx.run_lmers(keys, vals, l, flags)
+        assert (st1.distinct_lmers, st1.distinct_kmers, st1.edge_count) == (st0.distinct_lmers, st0.distinct_kmers, st0.edge_count)
+        for n in names:
+            assert np.array_equal(ctx.download(getattr(N, "ART_" + n)), a0[n]), n
+        assert ctx.pipeline_contigs() == c0
+    # one strand per l-mer is enough: the table is canonicalised
+    canon = np.array([min(int(x), oracle.revcomp(int(x), l)) == int(x) for x in lk])
+    ctx.run_lmers(lk[canon], lv[canon], l, flags)
+    assert ctx.pipeline_contigs() == c0
+
+
 def test_assemble_entry_points(tmp_path, g200_reads):
     import eulercuda as ec_pkg
     import eulercuda.eulercuda as ec
