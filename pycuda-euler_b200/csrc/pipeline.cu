@@ -440,7 +440,7 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
         EULER_TRY(graph_edges_fused(ctx, P->lt.keys(), P->lt.cnt(), P->lt_base.ptr(), P->lt_eoff.ptr(), lt_cap, l, vt,
                                     P->lkeys.ptr(), P->lvals.ptr(), P->loffs.ptr(), P->ev1.ptr(), P->ev2.ptr(),
                                     P->lcount.ptr(), P->ecount.ptr(), P->deg.ptr()));
-        launches += 2;
+        launches += 3;   // compact_vertices, bucket_bases, edges_fused
     }
     // scans of the degree slots + EulerVertex records in one pass
     if (paired)
