@@ -75,7 +75,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
+                time.sleep(0.002)
         except Exception as e:  # NVML not available: report that instead of inventing numbers
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 
@@ -142,7 +142,7 @@ def run_reference(args, wl, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
