@@ -202,7 +202,15 @@ static int pipeline_run_wide(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 
     u64 lt_cap = cap_for(est_l), vt_cap = cap_for(est_v);
     u64 h[8] = {0};
     u32 retries = 0, launches = 0;
+    // EULER_B200_WIDE_TILED=0: the one-thread-per-read count kernel (needs a 16-byte aligned buffer otherwise)
+    const char *wt = getenv("EULER_B200_WIDE_TILED");
+    const bool wide_tiled = !(wt && atoi(wt) == 0) && (((uintptr_t)P->d_buf & 15) == 0);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    if (wide_tiled) {
+        EULER_TRY(P->start_bits.reserve(ctx, B / 32 + 2));
+        EULER_TRY(enc_mark_starts(ctx, P->d_off, P->nreads, B, P->start_bits.ptr()));
+        launches++;
+    }
     while (true) {
         P->lt_cap = lt_cap; P->vt_cap = vt_cap;
         EULER_TRY(P->wlt_keys.reserve(ctx, lt_cap)); EULER_TRY(P->wlt_cnt.reserve(ctx, lt_cap)); EULER_TRY(P->lt_base.reserve(ctx, lt_cap));
@@ -211,7 +219,11 @@ static int pipeline_run_wide(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 
         EULER_TRY(wide_table_clear(ctx, P->wlt_keys.ptr(), P->wlt_cnt.ptr(), lt_cap));
         EULER_TRY(wide_table_clear(ctx, P->wvt_keys.ptr(), nullptr, vt_cap));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
-        EULER_TRY(wide_count(ctx, P->d_buf, P->d_off, P->nreads, l, P->wlt_keys.ptr(), P->wlt_cnt.ptr(), lt_cap, P->stats.ptr()));
+        if (wide_tiled)
+            EULER_TRY(wide_count_tiled(ctx, P->d_buf, B, P->start_bits.ptr(), l, P->wlt_keys.ptr(), P->wlt_cnt.ptr(), lt_cap,
+                                       P->stats.ptr()));
+        else
+            EULER_TRY(wide_count(ctx, P->d_buf, P->d_off, P->nreads, l, P->wlt_keys.ptr(), P->wlt_cnt.ptr(), lt_cap, P->stats.ptr()));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
         EULER_TRY(wide_slot_scan(ctx, P->wlt_keys.ptr(), lt_cap, l, P->lt_base.ptr(), P->stats.ptr() + 3));
         EULER_TRY(wide_vertex_insert(ctx, P->wlt_keys.ptr(), lt_cap, l, P->wvt_keys.ptr(), vt_cap, P->stats.ptr() + 2));

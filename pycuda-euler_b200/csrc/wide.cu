@@ -10,6 +10,7 @@
 #include "sort.cuh"
 #include "tmp.cuh"
 #include "wide.cuh"
+#include "encode.cuh"
 
 #define WB 256
 
@@ -56,6 +57,154 @@ int wide_count(euler_ctx *ctx, const void *d_buf, const u64 *d_off, u64 nreads, 
     if (!nreads) return EULER_OK;
     wide_count_kernel<<<grid_for(nreads, WB), WB, 0, ctx->stream>>>((const unsigned char *)d_buf, d_off, nreads, l, keys, cnt, cap,
                                                                    d_stats);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+// ---- count, tiled: the 64-bit count_compact_kernel (encode.cu) over two-word keys ---------------------------
+// A warp covers 32 chunks of 16 bytes; the first WT_HALO = 4 lanes only supply the 63 bases of left context, the
+// other 28 own the windows that end in their chunk.  Phase 1 rolls the 128-bit forward / reverse-complement
+// registers through the 16 positions in lock step and packs the valid canonical keys into shared memory; phase
+// 2 probes them two per lane: one step per key first, then the keys whose home bucket was full together.
+#define WT_HALO 4
+#define WT_ADV (32 - WT_HALO)
+#define WT_BLOCK 128
+#define WT_KEYS (WT_ADV * 16)
+#define WT_KPL 2
+__global__ void __launch_bounds__(WT_BLOCK, 4) wide_count_tiled_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
+                                                                       const u32 *__restrict__ start_bits, u32 l,
+                                                                       K128 *__restrict__ keys, u32 *__restrict__ cnt, u64 cap,
+                                                                       u64 ntiles, u64 *__restrict__ stats)
+{
+    __shared__ K128 s_keys[(WT_BLOCK / 32) * WT_KEYS];
+    K128 *stage = s_keys + (threadIdx.x >> 5) * WT_KEYS;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    const u32 nb = (u32)(cap / WIDE_BUCKET);
+    const u32 max_probe = nb < 8192 ? nb : 8192;
+    const u32 k = l - 1, top = 2 * (l - 1);
+    const K128 lmask = mask128(l);
+    u32 nl_tot = 0, nk_tot = 0, fresh = 0;
+    bool overflow = false;
+
+    for (u64 tile = warp; tile < ntiles; tile += nwarps) {
+        const long long chunk = (long long)(tile * WT_ADV) - WT_HALO + lane;
+        const Chunk c = load_chunk(buf16, chunk, n_bases, start_bits);
+        const u32 p1 = __shfl_up_sync(0xffffffffu, c.codes, 1), p2 = __shfl_up_sync(0xffffffffu, c.codes, 2);
+        const u32 p3 = __shfl_up_sync(0xffffffffu, c.codes, 3), p4 = __shfl_up_sync(0xffffffffu, c.codes, 4);
+        const u32 v1 = __shfl_up_sync(0xffffffffu, c.vmask, 1), v2 = __shfl_up_sync(0xffffffffu, c.vmask, 2);
+        const u32 v3 = __shfl_up_sync(0xffffffffu, c.vmask, 3), v4 = __shfl_up_sync(0xffffffffu, c.vmask, 4);
+        const u32 s1 = __shfl_up_sync(0xffffffffu, c.smask, 1), s2 = __shfl_up_sync(0xffffffffu, c.smask, 2);
+        const u32 s3 = __shfl_up_sync(0xffffffffu, c.smask, 3), s4 = __shfl_up_sync(0xffffffffu, c.smask, 4);
+        // the 64 bases before this chunk (p1 = the chunk just before), their validity / read starts (bit 0 = most recent)
+        K128 f{((u64)p2 << 32) | p1, ((u64)p4 << 32) | p3};
+        K128 rc = revcomp128(and128(f, lmask), l);
+        const u64 pv = ((u64)v4 << 48) | ((u64)v3 << 32) | ((u64)v2 << 16) | v1;
+        const u64 ps = ((u64)s4 << 48) | ((u64)s3 << 32) | ((u64)s2 << 16) | s1;
+        u32 vrun = (lane < WT_HALO) ? 0u : ((pv == ~0ull) ? 64u : (u32)__ffsll((long long)~pv) - 1u);
+        u32 srun = ps ? (u32)__ffsll((long long)ps) - 1u : 64u;
+        u32 codes = c.codes;
+        u32 vm = (lane < WT_HALO) ? 0u : (c.vmask << 16);   // halo lanes own no windows
+        u32 sm = c.smask << 16;
+        u32 nvalid = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const u32 cc = codes >> 30;
+            codes <<= 2;
+            const bool valid = (vm >> 31) != 0, start = (sm >> 31) != 0;
+            vm <<= 1;
+            sm <<= 1;
+            f = and128(shl2_or(f, cc), lmask);
+            rc = shr2_or_top(rc, 3u - cc, top);
+            vrun = valid ? vrun + 1u : 0u;
+            srun = start ? 0u : srun + 1u;
+            nk_tot += (vrun >= k && srun + 1u >= k) ? 1u : 0u;
+            const bool ok = vrun >= l && srun + 1u >= l;
+            const unsigned okm = __ballot_sync(0xffffffffu, ok);
+            if (ok) stage[nvalid + __popc(okm & lt_mask)] = lt128(f, rc) ? f : rc;
+            nvalid += __popc(okm);
+        }
+        nl_tot += nvalid;   // warp-uniform
+        __syncwarp();
+        u32 ncur = nvalid;
+#pragma unroll 1
+        for (int pass = 0; pass < 2 && ncur; pass++) {
+            u32 nleft = 0;
+#pragma unroll 1
+            for (u32 g = 0; g < ncur; g += 32 * WT_KPL) {
+                K128 key[WT_KPL];
+                u64 b[WT_KPL];
+                u32 pend = 0;
+#pragma unroll
+                for (int i = 0; i < WT_KPL; i++) {
+                    const u32 idx = g + i * 32 + lane;
+                    key[i] = K128{0, 0};
+                    if (idx < ncur) {
+                        key[i] = stage[idx];
+                        pend |= 1u << i;
+                    }
+                    b[i] = wide_hash_bucket(key[i], nb);
+                    if (pass && ++b[i] == nb) b[i] = 0;   // stragglers: the home bucket was full
+                }
+                __syncwarp();
+                u32 probes = 0;
+                while (__any_sync(0xffffffffu, pend != 0)) {
+#pragma unroll
+                    for (int i = 0; i < WT_KPL; i++) {
+                        if (pend & (1u << i)) {
+                            const u64 slot = wide_probe_step(keys, b[i], key[i], fresh);
+                            if (slot != EULER_NO_SLOT) {
+                                atomicAdd(cnt + slot, 1u);
+                                pend &= ~(1u << i);
+                            } else if (++b[i] == nb) {
+                                b[i] = 0;
+                            }
+                        }
+                    }
+                    if (pass == 0) break;
+                    if (++probes >= max_probe && pend) { overflow = true; pend = 0; }
+                }
+                if (pass == 0) {
+#pragma unroll
+                    for (int i = 0; i < WT_KPL; i++) {
+                        const bool left = (pend >> i) & 1u;
+                        const unsigned lm = __ballot_sync(0xffffffffu, left);
+                        if (left) stage[nleft + __popc(lm & lt_mask)] = key[i];
+                        nleft += __popc(lm);
+                    }
+                }
+            }
+            __syncwarp();
+            ncur = nleft;
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        nk_tot += __shfl_xor_sync(0xffffffffu, nk_tot, d);
+        fresh += __shfl_xor_sync(0xffffffffu, fresh, d);
+    }
+    if (lane == 0) {
+        if (nl_tot) atomicAdd(stats + 0, (u64)nl_tot);
+        if (nk_tot) atomicAdd(stats + 1, (u64)nk_tot);
+        if (fresh) atomicAdd(stats + 5, (u64)fresh);
+    }
+    if (overflow) atomicOr((unsigned long long *)(stats + 2), 1ull);
+}
+
+int wide_count_tiled(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, K128 *keys, u32 *cnt, u64 cap,
+                     u64 *d_stats)
+{
+    if (!n_bases) return EULER_OK;
+    const u64 nchunks = (n_bases + 15) / 16;
+    const u64 ntiles = (nchunks + WT_ADV - 1) / WT_ADV;
+    u64 grid = (u64)ctx->num_sms * 4;
+    const u64 need = (ntiles + WT_BLOCK / 32 - 1) / (WT_BLOCK / 32);
+    if (grid > need) grid = need;
+    wide_count_tiled_kernel<<<(unsigned)grid, WT_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, keys, cnt, cap,
+                                                                           ntiles, d_stats);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }

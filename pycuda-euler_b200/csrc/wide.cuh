@@ -110,9 +110,31 @@ __device__ __forceinline__ u64 wide_find(const K128 *keys, u64 cap, K128 key)
     return EULER_NO_SLOT;
 }
 
+// One probe step for `key` at bucket b (two 16-byte slots = one 32-byte sector, loaded with a single 256-bit
+// load): slot index of the key after claiming it if absent, EULER_NO_SLOT when both slots hold other keys.
+// *fresh is incremented when this call claimed the slot.
+__device__ __forceinline__ u64 wide_probe_step(K128 *keys, u64 b, K128 key, u32 &fresh)
+{
+    K128 *bk = keys + b * WIDE_BUCKET;
+    const K4 q = ld_bucket_cg((const u64 *)bk);
+    const bool m0 = q.k[0] == key.lo && q.k[1] == key.hi, m1 = q.k[2] == key.lo && q.k[3] == key.hi;
+    if (m0 | m1) return b * WIDE_BUCKET + (m0 ? 0 : 1);
+    const bool e0 = (q.k[0] & q.k[1]) == ~0ull, e1 = (q.k[2] & q.k[3]) == ~0ull;
+    const K128 empty{~0ull, ~0ull};
+    for (int j = e0 ? 0 : (e1 ? 1 : 2); j < WIDE_BUCKET; j++) {   // a lost race moves on to the next slot through its own CAS
+        const K128 old = cas128(bk + j, empty, key);
+        if (is_empty128(old)) { fresh++; return b * WIDE_BUCKET + j; }
+        if (eq128(old, key)) return b * WIDE_BUCKET + j;
+    }
+    return EULER_NO_SLOT;
+}
+
 // ---- wide.cu launchers (asynchronous on ctx->stream) -----------------------------------------------
 // d_stats: [0] += forward l-windows, [1] += forward (l-1)-windows, [2] |= 1 on table overflow
 int wide_count(euler_ctx *ctx, const void *d_buf, const u64 *d_off, u64 nreads, u32 l, K128 *keys, u32 *cnt, u64 cap, u64 *d_stats);
+// tiled form (warp per 28 chunks, shared-memory compaction of the valid keys); d_bits = read-start bitmap
+int wide_count_tiled(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, K128 *keys, u32 *cnt, u64 cap,
+                     u64 *d_stats);
 int wide_table_clear(euler_ctx *ctx, K128 *keys, u32 *vals, u64 cap);
 int wide_vertex_insert(euler_ctx *ctx, const K128 *lt_keys, u64 lt_cap, u32 l, K128 *vt_keys, u64 vt_cap, u64 *d_flags);
 int wide_slot_scan(euler_ctx *ctx, const K128 *keys, u64 cap, u32 len, u32 *d_base, u64 *d_total);

@@ -123,17 +123,57 @@ int wide_dist_scatter(euler_ctx *ctx, const void *d_buf, const u64 *d_off, u64 n
 __global__ void __launch_bounds__(256) wide_count_keys_kernel(const K128 *__restrict__ in, u64 n, K128 *__restrict__ keys,
                                                                u32 *__restrict__ cnt, u64 cap, u64 *__restrict__ stats)
 {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    // two keys per lane in flight; warp-uniform probing rounds as in dist_count_keys_kernel
     const u32 nb = (u32)(cap / WIDE_BUCKET);
-    const u64 slot = wide_insert(keys, cap, in[i], nb < 8192 ? nb : 8192);
-    if (slot == EULER_NO_SLOT) atomicOr((unsigned long long *)(stats + 2), 1ull);
-    else if (atomicAdd(cnt + slot, 1u) == 0u) atomicAdd((unsigned long long *)(stats + 5), 1ull);   // distinct keys held
+    const u32 max_probe = nb < 8192 ? nb : 8192;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const u64 t0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 iters = (n + stride * 2 - 1) / (stride * 2);
+    u32 fresh = 0;
+    bool overflow = false;
+    for (u64 it = 0; it < iters; it++) {
+        K128 key[2];
+        u64 b[2];
+        u32 pend = 0;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const u64 idx = (it * 2 + i) * stride + t0;
+            key[i] = K128{0, 0};
+            if (idx < n) {
+                key[i] = in[idx];
+                pend |= 1u << i;
+            }
+            b[i] = wide_hash_bucket(key[i], nb);
+        }
+        u32 probes = 0;
+        while (__any_sync(0xffffffffu, pend != 0)) {
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                if (pend & (1u << i)) {
+                    const u64 slot = wide_probe_step(keys, b[i], key[i], fresh);
+                    if (slot != EULER_NO_SLOT) {
+                        atomicAdd(cnt + slot, 1u);
+                        pend &= ~(1u << i);
+                    } else if (++b[i] == nb) {
+                        b[i] = 0;
+                    }
+                }
+            }
+            if (++probes >= max_probe && pend) { overflow = true; pend = 0; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, o);
+    if ((threadIdx.x & 31) == 0 && fresh) atomicAdd((unsigned long long *)(stats + 5), (unsigned long long)fresh);   // distinct keys held
+    if (overflow) atomicOr((unsigned long long *)(stats + 2), 1ull);
 }
 int wide_count_keys(euler_ctx *ctx, const void *d_keys, u64 n, K128 *keys, u32 *cnt, u64 cap, u64 *d_stats)
 {
     if (!n) return EULER_OK;
-    wide_count_keys_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>((const K128 *)d_keys, n, keys, cnt, cap, d_stats);
+    u64 grid = (u64)ctx->num_sms * 8;
+    const u64 need = (n + 511) / 512;
+    if (grid > need) grid = need;
+    wide_count_keys_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>((const K128 *)d_keys, n, keys, cnt, cap, d_stats);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }

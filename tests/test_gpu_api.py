@@ -116,6 +116,27 @@ def test_graph_stage_from_an_lmer_table(ctx, g200_reads, l):
     assert ctx.pipeline_contigs() == c0
 
 
+def test_partition_driver_on_one_gpu(tmp_path, g200_reads):
+    """assembler.py with world = 1: FASTA + GFA from a FASTQ file in unitig mode, the Euler-mode
+    contigs of assemble2 in euler mode; the multi-GPU legs are checked by scripts/check_assembler.sh."""
+    import assembler
+    import eulercuda.eulercuda as ec
+    fq = tmp_path / "reads.fq"
+    fq.write_text("".join("@r%d\n%s\n+\n%s\n" % (i, r, "I" * len(r)) for i, r in enumerate(g200_reads)))
+    out = tmp_path / "contigs.fa"
+    assert assembler.main(["-i", str(fq), "-o", str(out), "-k", "9"]) == 0
+    got = [x for x in out.read_text().split("\n") if x and x[0] != ">"]
+    fx = _load("g200.json")
+    gold = {(c["k"], c["limit"]): c for c in fx["cases"]}
+    assert oracle.canonical_contigs(got) == oracle.canonical_contigs(gold[(9, 1)]["contigs"])
+    gfa = (tmp_path / "contigs.fa.gfa").read_text().splitlines()
+    assert gfa[0] == "H\tVN:Z:1.0" and sum(x.startswith("S\t") for x in gfa) == len(got)
+    out2 = tmp_path / "euler.fa"
+    assert assembler.main(["-i", str(fq), "-o", str(out2), "-k", "10", "--mode", "euler"]) == 0
+    got2 = [x for x in out2.read_text().split("\n") if x and x[0] != ">"]
+    assert got2 == ec.assemble2(10, buffer=g200_reads, mode="euler")
+
+
 def test_assemble_entry_points(tmp_path, g200_reads):
     import eulercuda as ec_pkg
     import eulercuda.eulercuda as ec
