@@ -223,10 +223,13 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ms, graph_ms, launches = 0.0, 0.0, 0
+    per_step = []   # the library's own CUDA-event time of each step (N = 1) / host wall time of each step (N > 1)
     t_wall0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
+        t_s = time.perf_counter()
         st, info = step()
+        per_step.append(st.ms_total if world == 1 else 1e3 * (time.perf_counter() - t_s))
         kern_ms += st.ms_count_kernel
         graph_ms += st.ms_graph
         launches += st.kernel_launches + (3 if world > 1 else 0)   # + mark_starts, count pass, scatter pass
@@ -346,7 +349,8 @@ def main():
                        "distinct_lmers": int(st.distinct_lmers), "distinct_kmers": int(st.distinct_kmers),
                        "edges": int(st.edge_count), "lmer_table_capacity": int(st.lmer_table_capacity),
                        "retries": int(st.retries)},
-            "stage_ms": {"count_kernel": kern_ms_max, "graph": graph_ms, "step_wall": wall_ms},
+            "stage_ms": {"count_kernel": kern_ms_max, "graph": graph_ms, "step_wall": wall_ms,
+                         "step_median": sorted(per_step)[len(per_step) // 2], "step_best": min(per_step)},
             "roofline": {"bound": "hbm", "kernel": ("count_compact_kernel" if l <= 32 else "wide_count_kernel") if world == 1 else
                          ("dist_count_keys_kernel" if l <= 32 else "wide_count_keys_kernel") + " (one launch per source rank)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
