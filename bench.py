@@ -344,6 +344,9 @@ def main():
                 "l2": "inputs (%d MB ASCII) + table (%d MB) exceed the 126 MB L2; the table is re-initialised every step"
                       % (R * L // 10 ** 6, st.lmer_table_capacity * 12 // 10 ** 6),
                 "distinct_hint": hint, "ids": "slot order (canonical-id sort not in the timed region)",
+                "timing": "CUDA events on the library's stream around the K steps" if world == 1 else
+                          "host clock around the K steps, barrier + device synchronize on both sides, max over ranks "
+                          "(every step synchronises with the host at the count exchange, so device events see the same interval)",
             },
             "counts": {"n_kmer_windows": int(st.n_kmer_windows), "n_lmer_windows": int(st.n_lmer_windows),
                        "distinct_lmers": int(st.distinct_lmers), "distinct_kmers": int(st.distinct_kmers),
