@@ -181,7 +181,6 @@ static bool use_merged_table()
     const char *e = getenv("EULER_B200_MERGED");
     return e && atoi(e) == 1;
 }
-static bool N_l_fits_merged(u64) { return true; }
 static u64 cap_for(u64 n) { return round_up((u64)((double)(n < 64 ? 64 : n) / table_load()) + 1, 1024); }
 
 // l in 33..64: the same stages over two-word keys (wide.cu).  Correctness-first: one thread per read,
@@ -318,7 +317,7 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
     u64 lt_cap = cap_for(est_l), vt_cap = cap_for(est_v);
     // packed count table: power-of-two bucket count, load factor in (0.375, 0.75]
     bool packed = !from_table && use_packed_table();
-    bool merged = !from_table && !packed && use_merged_table() && !table_hash_for(lt_cap, k).span_nb && N_l_fits_merged(B);
+    bool merged = !from_table && !packed && use_merged_table() && !table_hash_for(lt_cap, k).span_nb;
     if (merged) lt_cap = round_up(lt_cap / 3 * 4 + 4, 1024);   // three key slots per 4-word bucket
     u32 pk_b = 8;
     const u64 side_cap = 16384;
