@@ -281,6 +281,9 @@ __global__ void __launch_bounds__(PB, 4) dist_partition_kernel(const uint4 *__re
 // nothing is indexed dynamically (no local memory, no shared owner table).  The warp scan runs on
 // 16-bit fields; prefix sums ACROSS the fields of a word are one multiply by 0x0001000100010001.
 #define P8_FIELDS 0x0001000100010001ull
+#ifndef P8_MINB
+#define P8_MINB 4   // resident blocks per SM (128 registers); 5 and 6 spill
+#endif
 __device__ __forceinline__ u64 spread8to16(u32 x)
 {
     u64 t = x;
@@ -288,7 +291,7 @@ __device__ __forceinline__ u64 spread8to16(u32 x)
     return (t | (t << 8)) & 0x00FF00FF00FF00FFull;
 }
 template <bool SCATTER, int WK>
-__global__ void __launch_bounds__(PB, 4) dist_partition8_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
+__global__ void __launch_bounds__(PB, P8_MINB) dist_partition8_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
                                                                  const u32 *__restrict__ start_bits, u32 l, u32 nranks, u64 ntiles,
                                                                  u64 *__restrict__ counts, u64 *__restrict__ cursors,
                                                                  u64 *__restrict__ send, const u64 *__restrict__ seg_off, u64 seg_cap)
@@ -471,7 +474,7 @@ int dist_partition(euler_ctx *ctx, bool scatter, const void *d_buf, u64 n_bases,
     dist_partition8_kernel<S, WW><<<g8, PB, 0, ctx->stream>>>(b16, n_bases, d_bits, l, nranks, ntiles, d_counts, d_cursors, \
                                                               d_send, d_seg_off, seg_cap)
     if (nranks <= 8 && (WK == 20 || WK == 10)) {
-        u64 grid8 = (u64)ctx->num_sms * 4;
+        u64 grid8 = (u64)ctx->num_sms * P8_MINB;
         if (grid8 > need) grid8 = need;
         const unsigned g8 = (unsigned)grid8;
         if (scatter) { if (WK == 20) LAUNCH_P8(true, 20); else LAUNCH_P8(true, 10); }
