@@ -46,6 +46,23 @@ def torch_count_exchange(group=None, device="cuda"):
     return fn
 
 
+def global_id_bases(n_vertices, n_lmers, n_edges, group=None, device="cuda"):
+    """Global ids = local id + exclusive scan of the per-rank counts: one all_gather of three
+    integers.  Returns {"vertex_base", "lmer_base", "edge_base", "vertices", "lmers", "edges"} with the
+    bases of this rank and the totals over all ranks."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = torch.tensor([int(n_vertices), int(n_lmers), int(n_edges)], dtype=torch.int64, device=device)
+    rows = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(rows, mine, group=group)
+    table = torch.stack(rows).cpu().numpy()
+    base = table[:rank].sum(axis=0) if rank else np.zeros(3, np.int64)
+    tot = table.sum(axis=0)
+    return {"vertex_base": int(base[0]), "lmer_base": int(base[1]), "edge_base": int(base[2]),
+            "vertices": int(tot[0]), "lmers": int(tot[1]), "edges": int(tot[2])}
+
+
 _BUFFERS = {}
 
 

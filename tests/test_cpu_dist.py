@@ -31,7 +31,7 @@ def _worker(rank, world, port, q):
     import torch.distributed as dist
     import oracle
     from util import random_reads
-    from eulercuda.dist import plan_exchange, torch_count_exchange
+    from eulercuda.dist import plan_exchange, torch_count_exchange, global_id_bases
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -56,6 +56,10 @@ def _worker(rank, world, port, q):
         mine = np.array(sum((gathered[src][rank] for src in range(world)), []), dtype=np.uint64)
         assert [len(gathered[src][rank]) for src in range(world)] == recv_counts
         keys, cnt = np.unique(mine, return_counts=True)
+        ids = global_id_bases(10 + rank, 100 + 7 * rank, 1000 * (rank + 1), device="cpu")
+        assert ids["vertices"] == sum(10 + r for r in range(world)) and ids["edges"] == sum(1000 * (r + 1) for r in range(world))
+        assert ids["vertex_base"] == sum(10 + r for r in range(rank)) and ids["lmer_base"] == sum(100 + 7 * r for r in range(rank))
+        assert ids["edge_base"] == sum(1000 * (r + 1) for r in range(rank))
         q.put((rank, keys.tolist(), cnt.tolist()))
     finally:
         dist.destroy_process_group()
