@@ -177,6 +177,12 @@ typedef struct {
     float ms_count, ms_graph, ms_total;   /* CUDA-event times of the last run: table init + count | graph | both */
     float ms_count_kernel;                /* the fused encode+count kernel alone */
     uint32_t kernel_launches;             /* kernels of this library launched by the run */
+    /* bucketed path (path == 1): the partition pass is ms_count_kernel, the per-bucket build ms_build_kernel */
+    float ms_build_kernel;
+    uint32_t path;                        /* 0 = global-table path (round 1), 1 = minimizer-bucketed path */
+    uint32_t n_buckets;                   /* buckets of the last run */
+    uint32_t pad_;
+    uint64_t bucket_records;              /* largest number of 16-byte records in one bucket region */
 } euler_stats;
 
 #define EULER_RUN_EXPAND_EDGES 1u   /* also materialise ee[] / l[] / e[] (needs E < 2^32) */

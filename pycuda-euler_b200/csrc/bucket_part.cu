@@ -1,0 +1,127 @@
+// bucket_part.cu -- pass 1 of the bucketed hot path (bucket.cuh): one sweep over the ASCII reads that cuts
+// every read into minimizer runs and writes them, 2-bit packed, as 16-byte records into the bucket regions.
+// Replaces the encode half of eulercuda.readLmersKmersCuda (eulercuda.py:117-139: encode_lmer_device,
+// compute_kmer_device, compute_lmer_complement_device) -- no per-position key ever reaches memory.
+//
+// Tile geometry is the encoder's (encode.cuh): a warp covers 32 chunks of 16 bytes, lanes [0, ENC_HALO) only
+// supply left context.  Per lane: 16 m-mer scores (two funnel shifts + min + scramble each, no rolling
+// state), the 20 scores before them from the warp's shared-memory rows (stride 20 words: conflict-free 128-bit
+// accesses), a van Herk / Gil-Werman sliding minimum (~4 min per position), validity of all 16 k-mer / l-mer
+// windows from two 64-bit masks, then one record per minimizer run (1-3 per lane): a cursor atomic and one
+// 16-byte store.
+#include "bucket.cuh"
+#include "encode.cuh"
+#include "kernels.h"
+
+#define BP_BLOCK 128
+#define BP_WARPS (BP_BLOCK / 32)
+#define BP_ROW 20                       // words per lane row (16 scores + 4 pad)
+#define BP_ROWS 34                      // two rows of padding in front of lane 0
+#ifndef BP_MINB
+#define BP_MINB 5
+#endif
+
+template <int W>
+__global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
+                                                                           const u32 *__restrict__ start_bits, u32 l, BkGeom geom,
+                                                                           u32 my_rank, u32 rcap, uint4 *const *__restrict__ dst,
+                                                                           u32 *__restrict__ cursors, u64 ntiles, u64 *__restrict__ stats)
+{
+    __shared__ __align__(16) u32 s_rows[BP_WARPS][BP_ROWS * BP_ROW];
+    u32 *rows = s_rows[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    u32 *my_row = rows + (lane + 2) * BP_ROW;
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    const u32 k = l - 1, m = bk_m_of(k);
+    u32 nl_tot = 0, nk_tot = 0;
+    bool overflow = false;
+
+    for (u64 tile = warp; tile < ntiles; tile += nwarps) {
+        const long long chunk = (long long)(tile * ENC_ADV) - ENC_HALO + lane;
+        const Chunk c = load_chunk(buf16, chunk, n_bases, start_bits);
+        const u32 p1 = __shfl_up_sync(0xffffffffu, c.codes, 1), p2 = __shfl_up_sync(0xffffffffu, c.codes, 2);
+        const u32 v1 = __shfl_up_sync(0xffffffffu, c.vmask, 1), v2 = __shfl_up_sync(0xffffffffu, c.vmask, 2);
+        const u32 s1 = __shfl_up_sync(0xffffffffu, c.smask, 1), s2 = __shfl_up_sync(0xffffffffu, c.smask, 2);
+        u32 sa[36];
+        {
+            u32 sc[16];
+            bk_chunk_scores(lane >= 1 ? p1 : 0u, c.codes, m, sc);
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<uint4 *>(my_row + i) = make_uint4(sc[i], sc[i + 1], sc[i + 2], sc[i + 3]);
+#pragma unroll
+            for (int i = 0; i < 16; i++) sa[20 + i] = sc[i];
+        }
+        __syncwarp();
+        {   // the 20 scores before this chunk: the previous lane's row and the last four of the lane before it
+            const uint4 a = *reinterpret_cast<const uint4 *>(my_row - 2 * BP_ROW + 12);
+            sa[0] = a.x; sa[1] = a.y; sa[2] = a.z; sa[3] = a.w;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const uint4 b = *reinterpret_cast<const uint4 *>(my_row - BP_ROW + i);
+                sa[4 + i] = b.x; sa[5 + i] = b.y; sa[6 + i] = b.z; sa[7 + i] = b.w;
+            }
+        }
+        u32 win[16];
+        if constexpr (W > 0) bk_window_min<W>(sa, win);
+        else bk_window_min_any(sa, k - m + 1, win);
+        __syncwarp();   // every lane has read its neighbours' scores: the rows now carry the window minima
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<uint4 *>(my_row + i) = make_uint4(win[i], win[i + 1], win[i + 2], win[i + 3]);
+        __syncwarp();
+        if (lane >= ENC_HALO) {
+            const u64 vmw = ((u64)v2 << 48) | ((u64)v1 << 32) | ((u64)c.vmask << 16);
+            const u64 smw = ((u64)s2 << 48) | ((u64)s1 << 32) | ((u64)c.smask << 16);
+            const u64 VK = bk_valid_kmers(vmw, smw, k);
+            const u32 vk16 = bk_own16(VK), vl16 = bk_own16(bk_valid_lmers(VK, smw, k));
+            nk_tot += __popc(vk16);
+            nl_tot += __popc(vl16);
+            const u32 win_prev = my_row[-BP_ROW + 15];
+            bk_lane_pieces(p2, p1, c.codes, my_row, win_prev, bk_eq16(win, win_prev), vk16, vl16, k, geom, [&](u32 bucket, const BkRec &r) {
+                const u32 rank = geom.nranks > 1 ? bucket / geom.nb_per_rank : 0u;
+                const u32 lb = bucket - rank * geom.nb_per_rank;
+                const u32 pos = atomicAdd(cursors + bucket, 1u);
+                if (pos < rcap) {
+                    uint4 *region = dst[rank] + ((u64)lb * geom.nranks + my_rank) * rcap;
+                    region[pos] = make_uint4(r.hdr, r.d[0], r.d[1], r.d[2]);
+                } else {
+                    overflow = true;
+                }
+            });
+        }
+        __syncwarp();   // the rows are rewritten by the next tile
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        nl_tot += __shfl_xor_sync(0xffffffffu, nl_tot, o);
+        nk_tot += __shfl_xor_sync(0xffffffffu, nk_tot, o);
+    }
+    if (lane == 0) {
+        if (nl_tot) atomicAdd(stats + 0, (u64)nl_tot);
+        if (nk_tot) atomicAdd(stats + 1, (u64)nk_tot);
+    }
+    if (overflow) atomicOr((unsigned long long *)(stats + 2), (unsigned long long)BKT_FLAG_REGION);
+}
+
+int bkt_partition(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u32 nranks, u32 nb_per_rank, u32 my_rank,
+                  u32 rcap, uint4 *const *d_dst, u32 *d_cursors, u64 *d_stats)
+{
+    if (!n_bases) return EULER_OK;
+    const u64 nchunks = (n_bases + 15) / 16;
+    const u64 ntiles = (nchunks + ENC_ADV - 1) / ENC_ADV;
+    u64 grid = (u64)ctx->num_sms * BP_MINB;
+    const u64 need = (ntiles + BP_WARPS - 1) / BP_WARPS;
+    if (grid > need) grid = need;
+    const BkGeom geom = {nranks, nb_per_rank};
+    const u32 k = l - 1, W = k - bk_m_of(k) + 1;
+    const unsigned g = (unsigned)grid;
+#define LAUNCH_BP(WW)                                                                                                        \
+    bkt_partition_kernel<WW><<<g, BP_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, geom, my_rank, rcap, d_dst, \
+                                                              d_cursors, ntiles, d_stats)
+    if (W == 20) LAUNCH_BP(20);        // k = 31
+    else if (W == 10) LAUNCH_BP(10);   // k = 21
+    else LAUNCH_BP(0);
+#undef LAUNCH_BP
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}

@@ -155,3 +155,36 @@ int ingest_parse(euler_ctx *ctx, const unsigned char *d_file, u64 n, int fastq, 
                  u64 *nreads, u64 *nbases);
 // reads left resident by euler_ingest (pipeline.cu)
 int pipeline_resident_reads(euler_ctx *ctx, const void **d_buf, const u64 **d_off, u64 *nreads, u64 *n_bases);
+
+// ---- bucket_part.cu / bucket_build.cu (minimizer-bucketed hot path, bucket.cuh)
+// flags of stats[2] raised by the bucketed kernels
+#define BKT_FLAG_REGION 0x10ull     // a (bucket, source) record region overflowed: rerun with the capacity of stats[6]
+#define BKT_FLAG_TABLE 0x20ull      // a bucket's shared-memory table filled up: rerun with more buckets
+#define BKT_FLAG_OUTPUT 0x40ull     // the artefact arrays were too small: rerun with the totals of stats[3..5]
+#define BKT_FLAG_BOUNDARY 0x80ull   // the cross-bucket edge table filled up
+#define BKT_FLAG_INTERNAL 0x100ull  // a consistency check failed (pushed degree totals != looked-up degree slots)
+// pass 1: records of this rank's reads into the regions (local bucket, source rank) of every owner;
+// d_dst[r] = base of rank r's record area, d_cursors[nranks * nb_per_rank] (zeroed by the caller) counts per global bucket;
+// d_stats: [0] += N_l, [1] += N_k, [2] |= flags
+int bkt_partition(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u32 nranks, u32 nb_per_rank, u32 my_rank,
+                  u32 rcap, uint4 *const *d_dst, u32 *d_cursors, u64 *d_stats);
+// pass 2 over the nb local buckets
+struct BktBuild {
+    const void *records;   // region (b, src) at ((b * nranks + src) * rcap) records of 16 bytes
+    const u32 *counts;     // [nb * nranks]
+    u32 nb, nranks, rcap, l, log_capl, log_capv;
+    u64 *lkeys; u32 *lvals, *loffs, *ev1, *ev2; u64 ucap;
+    u64 *vkeys; u32 *lcount, *ecount, *lstart, *estart; euler_vertex *ev; u64 vcap;
+    void *state;           // bkt_state_bytes(nb)
+    u64 *bkeys; u32 *bvals; u64 bcap;   // cross-bucket edge table: bcap keys (power of two), 2 * bcap values
+    u64 *stats;            // [2] |= flags, [3] U_l, [4] V, [5] E, [6] max records in a region
+};
+int bkt_build(euler_ctx *ctx, const BktBuild &B);
+size_t bkt_state_bytes(u32 nb);
+size_t bkt_build_smem(u32 log_capl, u32 log_capv);
+// canonical-id post-processing of the bucketed build
+int bkt_iota(euler_ctx *ctx, u32 *v, u64 n);
+int bkt_invert_perm(euler_ctx *ctx, const u32 *perm, u64 n, u32 *inv);
+int bkt_gather_rows(euler_ctx *ctx, const u32 *perm, u64 n, const u32 *a_in, const u32 *b_in, u32 *a_out, u32 *b_out);
+int bkt_gather_edges(euler_ctx *ctx, const u32 *perm, u64 n, const u32 *newid, const u32 *lvals, const u32 *ev1, const u32 *ev2,
+                     u32 *lvals_out, u32 *ev1_out, u32 *ev2_out);

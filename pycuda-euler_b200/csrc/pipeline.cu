@@ -7,7 +7,9 @@
 #include "sort.cuh"
 #include "tmp.cuh"
 #include "wide.cuh"
+#include "bucket.cuh"
 #include <stdlib.h>
+#include <utility>
 
 struct LtTable {
     DevBuf b;
@@ -101,6 +103,14 @@ struct Pipeline {
     DevArr<u64> lkeys_hi, vkeys_hi;
     DevArr<unsigned char> tf;
     bool wide = false;
+    // bucketed hot path (bucket.cuh): record regions, per-bucket cursors, look-back state, cross-bucket edge table
+    DevBuf bk_records, bk_state;
+    DevArr<u32> bk_cursors, bk_bvals, bk_perm, bk_newid, bk_tmp32a, bk_tmp32b, bk_tmp32c, bk_rows_a, bk_rows_b;
+    DevArr<u64> bk_bkeys;
+    DevArr<uint4 *> bk_dst;
+    u32 bk_learned_rcap = 0, bk_learned_nb = 0;
+    u64 bk_learned_bases = 0, bk_learned_u = 0, bk_learned_v = 0;
+    u32 bk_learned_l = 0;
     euler_stats st = {};
 };
 
@@ -116,6 +126,8 @@ void pipeline_destroy(Pipeline *p)
     p->lev.free(); p->ent.free(); p->sort_k.free(); p->sort_v.free(); p->sort_hist.free();
     p->blk_keys.free(); p->blk_cur.free(); p->deg.free(); p->vt_bbase.free(); p->lt_merged.free(); p->tbl_keys.free(); p->tbl_cnt.free();
     p->wlt_keys.free(); p->wvt_keys.free(); p->wlt_cnt.free(); p->lkeys_hi.free(); p->vkeys_hi.free(); p->tf.free();
+    dev_free(p->bk_records); dev_free(p->bk_state); p->bk_cursors.free(); p->bk_bvals.free(); p->bk_perm.free(); p->bk_newid.free();
+    p->bk_tmp32a.free(); p->bk_tmp32b.free(); p->bk_tmp32c.free(); p->bk_rows_a.free(); p->bk_rows_b.free(); p->bk_bkeys.free(); p->bk_dst.free();
     delete p;
 }
 
@@ -292,12 +304,199 @@ static int pipeline_run_wide(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 
     return EULER_OK;
 }
 
+
+// ---- the bucketed hot path (bucket.cuh): partition pass + per-bucket shared-memory build ------------------------------
+// EULER_B200_BUCKETED=0 selects the round-1 global-table path below (also the fallback when a bucket does not fit
+// its shared-memory table, e.g. one minimizer shared by a huge number of distinct k-mers).
+static bool use_bucketed()
+{
+    const char *e = getenv("EULER_B200_BUCKETED");
+    return !(e && atoi(e) == 0);
+}
+static u32 env_u32(const char *name, u32 dflt)
+{
+    const char *e = getenv(name);
+    return e && atoi(e) > 0 ? (u32)atoi(e) : dflt;
+}
+static u64 pow2_at_least(u64 x)
+{
+    u64 p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+#define EULER_FALLBACK 1   // internal: take the global-table path instead
+
+static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 distinct_hint, euler_stats *stats)
+{
+    const u32 k = l - 1;
+    const u64 B = P->n_bases;
+    cudaStream_t s = ctx->stream;
+    if (B >= (1ull << 40)) return EULER_FALLBACK;
+    EULER_TRY(P->stats.reserve(ctx, 16));
+    EULER_TRY(P->start_bits.reserve(ctx, B / 32 + 2));
+
+    // geometry: buckets sized for a shared-memory table at ~45 % load
+    const u32 log_cap = env_u32("EULER_B200_BKT_LOGCAP", 11);
+    const bool learned = !distinct_hint && P->bk_learned_bases == B && P->bk_learned_l == l && P->bk_learned_nb;
+    u64 est_c = distinct_hint ? distinct_hint : (learned ? (P->bk_learned_u + 1) / 2 : (B ? B : 1));
+    const double per_bucket = 0.45 * (double)(1u << log_cap);
+    u64 nb64 = learned ? P->bk_learned_nb : (u64)((double)est_c * 1.06 / per_bucket) + 1;
+    if (const u32 f = env_u32("EULER_B200_BKT_NB", 0)) nb64 = f;
+    if (nb64 > (1ull << 24)) return EULER_FALLBACK;
+    u32 nb = (u32)nb64;
+    // records: one per minimizer run cut at 16-base chunk boundaries, plus the orphans
+    const u32 W = k - bk_m_of(k) + 1;
+    const double rec_per_base = 2.0 / (W + 1.0) + 1.0 / 16.0 + 0.01;
+    u32 rcap = learned && P->bk_learned_rcap ? P->bk_learned_rcap
+                                            : (u32)((double)B * rec_per_base / nb * 1.5) + 64;
+    // artefact capacities: known from a hint or the last run of this input, else a first build only counts
+    u64 ucap = distinct_hint ? 2 * est_c + est_c / 4 + 1024 : (learned ? P->bk_learned_u + P->bk_learned_u / 64 + 1024 : 0);
+    u64 vcap = distinct_hint ? 2 * est_c + est_c / 4 + 1024 : (learned ? P->bk_learned_v + P->bk_learned_v / 64 + 1024 : 0);
+    u64 bcap = pow2_at_least((distinct_hint || learned ? est_c / 6 : est_c / 16) + 1024);
+
+    u64 h[8] = {0};
+    u32 retries = 0, launches = 0;
+    bool need_part = true;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    EULER_TRY(enc_mark_starts(ctx, P->d_off, P->nreads, B, P->start_bits.ptr()));
+    launches++;
+    while (true) {
+        if ((u64)nb * rcap * 16 > (48ull << 30)) return EULER_FALLBACK;
+        EULER_TRY(dev_reserve(ctx, P->bk_records, (size_t)nb * rcap * 16 + 16));
+        EULER_TRY(P->bk_cursors.reserve(ctx, nb));
+        EULER_TRY(dev_reserve(ctx, P->bk_state, bkt_state_bytes(nb)));
+        EULER_TRY(P->bk_bkeys.reserve(ctx, bcap)); EULER_TRY(P->bk_bvals.reserve(ctx, 2 * bcap));
+        EULER_TRY(P->bk_dst.reserve(ctx, 16));
+        EULER_TRY(P->lkeys.reserve(ctx, ucap)); EULER_TRY(P->lvals.reserve(ctx, ucap)); EULER_TRY(P->loffs.reserve(ctx, ucap));
+        EULER_TRY(P->ev1.reserve(ctx, ucap)); EULER_TRY(P->ev2.reserve(ctx, ucap));
+        EULER_TRY(P->vkeys.reserve(ctx, vcap));
+        EULER_TRY(P->lcount.reserve(ctx, 4 * vcap + 4)); EULER_TRY(P->ecount.reserve(ctx, 4 * vcap + 4));
+        EULER_TRY(P->lstart.reserve(ctx, 4 * vcap + 4)); EULER_TRY(P->estart.reserve(ctx, 4 * vcap + 4));
+        EULER_TRY(P->ev.reserve(ctx, vcap));
+        if (need_part) {
+            uint4 *self = (uint4 *)P->bk_records.p;
+            CUDA_TRY(ctx, cudaMemcpyAsync(P->bk_dst.ptr(), &self, sizeof(self), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 16 * sizeof(u64), s));
+            CUDA_TRY(ctx, cudaMemsetAsync(P->bk_cursors.ptr(), 0, (size_t)nb * sizeof(u32), s));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
+            EULER_TRY(bkt_partition(ctx, P->d_buf, B, P->start_bits.ptr(), l, 1, nb, 0, rcap, P->bk_dst.ptr(), P->bk_cursors.ptr(),
+                                    P->stats.ptr()));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+            launches++;
+            need_part = false;
+        } else {
+            CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr() + 2, 0, 5 * sizeof(u64), s));   // flags, totals, max region
+        }
+        BktBuild bb;
+        bb.records = P->bk_records.p; bb.counts = P->bk_cursors.ptr(); bb.nb = nb; bb.nranks = 1; bb.rcap = rcap; bb.l = l;
+        bb.log_capl = log_cap; bb.log_capv = log_cap;
+        bb.lkeys = P->lkeys.ptr(); bb.lvals = P->lvals.ptr(); bb.loffs = P->loffs.ptr(); bb.ev1 = P->ev1.ptr(); bb.ev2 = P->ev2.ptr(); bb.ucap = ucap;
+        bb.vkeys = P->vkeys.ptr(); bb.lcount = P->lcount.ptr(); bb.ecount = P->ecount.ptr(); bb.lstart = P->lstart.ptr();
+        bb.estart = P->estart.ptr(); bb.ev = P->ev.ptr(); bb.vcap = vcap;
+        bb.state = P->bk_state.p; bb.bkeys = P->bk_bkeys.ptr(); bb.bvals = P->bk_bvals.ptr(); bb.bcap = bcap; bb.stats = P->stats.ptr();
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], s));
+        EULER_TRY(bkt_build(ctx, bb));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+        launches += 2;
+        EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 8));   // the only host round trip of a steady-state step
+        const u64 fl = h[2];
+        if (fl & BKT_FLAG_INTERNAL) return euler_fail(ctx, EULER_ERR_STATE, "internal: bucketed build consistency check failed (flags %llx)", fl);
+        if (!(fl & (BKT_FLAG_REGION | BKT_FLAG_TABLE | BKT_FLAG_OUTPUT | BKT_FLAG_BOUNDARY))) break;
+        if (++retries > 8) return EULER_FALLBACK;
+        if (fl & BKT_FLAG_REGION) {   // stats[6] = the largest region
+            rcap = (u32)(h[6] + h[6] / 8 + 16);
+            need_part = true;
+        } else if (fl & BKT_FLAG_TABLE) {
+            if (nb >= (1u << 22) || retries > 6) return EULER_FALLBACK;
+            nb *= 4;
+            rcap = rcap / 4 + rcap / 8 + 64;
+            need_part = true;
+        } else {
+            if (fl & BKT_FLAG_OUTPUT) { ucap = h[3] + h[3] / 64 + 1024; vcap = h[4] + h[4] / 64 + 1024; }
+            if (fl & BKT_FLAG_BOUNDARY) bcap *= 4;
+        }
+    }
+    const u64 N_l = h[0], N_k = h[1], U_l = h[3], V = h[4], E = h[5];
+    if (V >= 0x3fffffffull || N_l >= 0x7fffffffull)
+        return euler_fail(ctx, EULER_ERR_RANGE, "graph exceeds u32 ids (U_l=%llu V=%llu E=%llu)", U_l, V, E);
+    if (E != 2 * N_l) return euler_fail(ctx, EULER_ERR_STATE, "internal: edge total %llu != 2 N_l %llu", E, 2 * N_l);
+    P->U_l = U_l; P->V = V; P->E = E;
+
+    if (flags & EULER_RUN_CANONICAL_IDS) {
+        // ids = rank in ascending key order (B14): sort the keys with their bucket-order index as payload, gather the rest
+        const u64 nmax = U_l > V ? U_l : V;
+        const u32 nblocks = (u32)((nmax + RS_TILE - 1) / RS_TILE);
+        EULER_TRY(P->sort_k.reserve(ctx, nmax)); EULER_TRY(P->sort_v.reserve(ctx, nmax));
+        EULER_TRY(P->sort_hist.reserve(ctx, (u64)256 * (nblocks ? nblocks : 1)));
+        EULER_TRY(P->bk_perm.reserve(ctx, nmax)); EULER_TRY(P->bk_newid.reserve(ctx, V));
+        EULER_TRY(P->bk_rows_a.reserve(ctx, 4 * V + 4)); EULER_TRY(P->bk_rows_b.reserve(ctx, 4 * V + 4));
+        EULER_TRY(P->bk_tmp32a.reserve(ctx, U_l)); EULER_TRY(P->bk_tmp32b.reserve(ctx, U_l)); EULER_TRY(P->bk_tmp32c.reserve(ctx, U_l));
+        EULER_TRY(bkt_iota(ctx, P->bk_perm.ptr(), V));
+        EULER_TRY(radix_sort_pairs(ctx, P->vkeys.ptr(), P->bk_perm.ptr(), V, 2 * (int)k, P->sort_k.ptr(), P->sort_v.ptr(), P->sort_hist.ptr()));
+        EULER_TRY(bkt_invert_perm(ctx, P->bk_perm.ptr(), V, P->bk_newid.ptr()));
+        EULER_TRY(bkt_gather_rows(ctx, P->bk_perm.ptr(), V, P->lcount.ptr(), P->ecount.ptr(), P->bk_rows_a.ptr(), P->bk_rows_b.ptr()));
+        std::swap(P->lcount, P->bk_rows_a);
+        std::swap(P->ecount, P->bk_rows_b);
+        EULER_TRY(bkt_iota(ctx, P->bk_perm.ptr(), U_l));
+        EULER_TRY(radix_sort_pairs(ctx, P->lkeys.ptr(), P->bk_perm.ptr(), U_l, 2 * (int)l, P->sort_k.ptr(), P->sort_v.ptr(), P->sort_hist.ptr()));
+        EULER_TRY(bkt_gather_edges(ctx, P->bk_perm.ptr(), U_l, P->bk_newid.ptr(), P->lvals.ptr(), P->ev1.ptr(), P->ev2.ptr(),
+                                   P->bk_tmp32a.ptr(), P->bk_tmp32b.ptr(), P->bk_tmp32c.ptr()));
+        std::swap(P->lvals, P->bk_tmp32a);
+        std::swap(P->ev1, P->bk_tmp32b);
+        std::swap(P->ev2, P->bk_tmp32c);
+        EULER_TRY(P->loffs.reserve(ctx, U_l));
+        EULER_TRY(P->lstart.reserve(ctx, 4 * V + 4)); EULER_TRY(P->estart.reserve(ctx, 4 * V + 4)); EULER_TRY(P->ev.reserve(ctx, V));
+        EULER_TRY(scan_exclusive(ctx, ScanInU32{P->lvals.ptr()}, U_l, P->loffs.ptr(), (u64 *)nullptr));
+        EULER_TRY(graph_vertices_fused(ctx, P->lcount.ptr(), P->ecount.ptr(), P->vkeys.ptr(), V, P->lstart.ptr(), P->estart.ptr(), P->ev.ptr()));
+        launches += 3 * ((2 * l + 7) / 8) + 3 * ((2 * k + 7) / 8) + 8;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], s));
+    if (flags & EULER_RUN_EXPAND_EDGES) {
+        launches += 1;
+        EULER_TRY(P->ee.reserve(ctx, E)); EULER_TRY(P->lev.reserve(ctx, E)); EULER_TRY(P->ent.reserve(ctx, E));
+        EULER_TRY(graph_setup_edges(ctx, P->lkeys.ptr(), P->lvals.ptr(), P->loffs.ptr(), U_l, l, P->ev1.ptr(), P->ev2.ptr(),
+                                    P->lstart.ptr(), P->estart.ptr(), (u32)E, P->ee.ptr(), P->lev.ptr(), P->ent.ptr()));
+        P->expanded = true;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    P->have_graph = true;
+    P->learned_bases = B;
+    P->learned_lc = (U_l + 1) / 2 + 16; P->learned_vc = (V + 1) / 2 + 16;
+    P->bk_learned_bases = B; P->bk_learned_l = l; P->bk_learned_nb = nb; P->bk_learned_u = U_l; P->bk_learned_v = V;
+    P->bk_learned_rcap = (u32)(h[6] + h[6] / 8 + 16);
+    // a hint that was far off: size the buckets from what was counted
+    {
+        const u64 want = (u64)((double)((U_l + 1) / 2) * 1.06 / per_bucket) + 1;
+        if (!env_u32("EULER_B200_BKT_NB", 0) && (want * 2 < nb || want > (u64)nb * 2)) { P->bk_learned_nb = (u32)want; P->bk_learned_rcap = 0; }
+    }
+    euler_stats &st = P->st;
+    st.n_kmer_windows = N_k; st.n_lmer_windows = N_l; st.distinct_lmers = U_l; st.distinct_kmers = V; st.edge_count = E;
+    st.lmer_table_capacity = (u64)nb << log_cap; st.kmer_table_capacity = (u64)nb << log_cap; st.retries = retries;
+    cudaEventElapsedTime(&st.ms_count, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&st.ms_graph, ctx->ev[1], ctx->ev[6]);
+    cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[6]);
+    cudaEventElapsedTime(&st.ms_count_kernel, ctx->ev[4], ctx->ev[1]);
+    cudaEventElapsedTime(&st.ms_build_kernel, ctx->ev[5], ctx->ev[2]);
+    st.kernel_launches = launches;
+    st.path = 1; st.n_buckets = nb; st.bucket_records = h[6];
+    if (stats) *stats = st;
+    return EULER_OK;
+}
+
 static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 distinct_hint, euler_stats *stats)
 {
     if (l < 2 || l > 64) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,64]", l);
     if (l > 32) return pipeline_run_wide(ctx, P, l, flags, distinct_hint, stats);
     P->wide = false;
     P->l = l; P->flags = flags; P->have_graph = false; P->expanded = false; P->text_valid = false;
+    memset(&P->st, 0, sizeof(P->st));
+    P->st.n_reads = P->nreads; P->st.n_bases = P->n_bases;
+    if (!P->from_table && use_bucketed()) {
+        const int rc = pipeline_run_bucketed(ctx, P, l, flags, distinct_hint, stats);
+        if (rc != EULER_FALLBACK) return rc;
+        P->have_graph = false; P->expanded = false;
+    }
     const u32 k = l - 1;
     const u64 B = P->n_bases;
     cudaStream_t s = ctx->stream;

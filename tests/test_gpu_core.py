@@ -237,9 +237,10 @@ def test_pipeline_device_resident_synthetic(ctx):
     assert np.array_equal(ctx.download(N.ART_LMER_VALUES), g.lvals)
 
 
-@pytest.mark.parametrize("knob", ["EULER_B200_MINHASH", "EULER_B200_PACKED", "EULER_B200_COHASH", "EULER_B200_MERGED"])
+@pytest.mark.parametrize("knob", ["EULER_B200_GLOBAL_TABLE", "EULER_B200_MINHASH", "EULER_B200_PACKED", "EULER_B200_COHASH", "EULER_B200_MERGED"])
 def test_opt_in_table_variants_give_the_same_graph(knob):
-    """EULER_B200_MINHASH=1 (minimizer-ordered homes; rolling-minimum kernels for l = 32 / 22, the
+    """The round-1 global-table path (EULER_B200_BUCKETED=0, also the fallback of the bucketed path) and its variants:
+    EULER_B200_MINHASH=1 (minimizer-ordered homes; rolling-minimum kernels for l = 32 / 22, the
     brute-force one otherwise), EULER_B200_PACKED=1 (packed quotient count table, count-wrap side
     table) and EULER_B200_COHASH=1 (l-mer table hashed by the canonical prefix k-mer) must not change
     any artefact.  The knobs are read once per process, so this runs in a
@@ -267,6 +268,6 @@ for l in (32, 22, 27, 12):
     assert np.array_equal(lk[o], g.lk_lo) and np.array_equal(ctx.download(N.ART_LMER_VALUES)[o], g.lvals)
 print("ok")
 ''' % (root, os.path.join(root, "pycuda-euler_b200"), os.path.join(root, "tests"))
-    env = dict(os.environ, **{knob: "1"})
+    env = dict(os.environ, **{knob: "1", "EULER_B200_BUCKETED": "0"})
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
