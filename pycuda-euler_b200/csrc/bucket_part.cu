@@ -125,3 +125,32 @@ int bkt_partition(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_b
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
+
+// ---- multi-GPU: publish this rank's region counts in every owner's area -----------------------------------------
+// counts of owner d live behind its records: counts[lb * nranks + src]
+__global__ void __launch_bounds__(256) bkt_push_counts_kernel(const u32 *__restrict__ cursors, uint4 *const *__restrict__ dst, u64 rec_bytes,
+                                                              u32 nbpr, u32 nranks, u32 my_rank, u64 *__restrict__ max_out)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 c = 0;
+    if (i < (u64)nbpr * nranks) {
+        const u32 d = (u32)(i / nbpr), lb = (u32)(i - (u64)d * nbpr);
+        c = cursors[i];
+        u32 *counts = (u32 *)((char *)dst[d] + rec_bytes);
+        counts[(u64)lb * nranks + my_rank] = c;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const u32 t = __shfl_xor_sync(0xffffffffu, c, o);
+        c = t > c ? t : c;
+    }
+    if ((threadIdx.x & 31) == 0 && c) atomicMax((unsigned long long *)max_out, (unsigned long long)c);
+}
+
+int bkt_push_counts(euler_ctx *ctx, const u32 *d_cursors, uint4 *const *d_dst, u64 rec_bytes, u32 nbpr, u32 nranks, u32 my_rank, u64 *d_max)
+{
+    const u64 n = (u64)nbpr * nranks;
+    bkt_push_counts_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_cursors, d_dst, rec_bytes, nbpr, nranks, my_rank, d_max);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}

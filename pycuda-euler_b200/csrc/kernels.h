@@ -188,3 +188,4 @@ int bkt_invert_perm(euler_ctx *ctx, const u32 *perm, u64 n, u32 *inv);
 int bkt_gather_rows(euler_ctx *ctx, const u32 *perm, u64 n, const u32 *a_in, const u32 *b_in, u32 *a_out, u32 *b_out);
 int bkt_gather_edges(euler_ctx *ctx, const u32 *perm, u64 n, const u32 *newid, const u32 *lvals, const u32 *ev1, const u32 *ev2,
                      u32 *lvals_out, u32 *ev1_out, u32 *ev2_out);
+int bkt_push_counts(euler_ctx *ctx, const u32 *d_cursors, uint4 *const *d_dst, u64 rec_bytes, u32 nbpr, u32 nranks, u32 my_rank, u64 *d_max);

@@ -111,6 +111,10 @@ struct Pipeline {
     u32 bk_learned_rcap = 0, bk_learned_nb = 0;
     u64 bk_learned_bases = 0, bk_learned_u = 0, bk_learned_v = 0;
     u32 bk_learned_l = 0;
+    void *bk_area[2] = {nullptr, nullptr};   // peer-visible bucket areas of the multi-GPU form (plain cudaMalloc)
+    u64 bk_area_bytes[2] = {0, 0};
+    u64 bk_dist_key = 0;
+    float bk_scatter_ms = 0;
     euler_stats st = {};
 };
 
@@ -126,6 +130,7 @@ void pipeline_destroy(Pipeline *p)
     p->lev.free(); p->ent.free(); p->sort_k.free(); p->sort_v.free(); p->sort_hist.free();
     p->blk_keys.free(); p->blk_cur.free(); p->deg.free(); p->vt_bbase.free(); p->lt_merged.free(); p->tbl_keys.free(); p->tbl_cnt.free();
     p->wlt_keys.free(); p->wvt_keys.free(); p->wlt_cnt.free(); p->lkeys_hi.free(); p->vkeys_hi.free(); p->tf.free();
+    for (int i = 0; i < 2; i++) if (p->bk_area[i]) cudaFree(p->bk_area[i]);
     dev_free(p->bk_records); dev_free(p->bk_state); p->bk_cursors.free(); p->bk_bvals.free(); p->bk_perm.free(); p->bk_newid.free();
     p->bk_tmp32a.free(); p->bk_tmp32b.free(); p->bk_tmp32c.free(); p->bk_rows_a.free(); p->bk_rows_b.free(); p->bk_bkeys.free(); p->bk_dst.free();
     delete p;
@@ -1328,6 +1333,156 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
     cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[2]);
     cudaEventElapsedTime(&st.ms_count_kernel, ctx->ev[4], ctx->ev[1]);
     st.kernel_launches = launches;
+    if (stats) *stats = st;
+    return EULER_OK;
+}
+
+// ---- multi-GPU form of the bucketed path -----------------------------------------------------------------------
+// Every rank owns nb_per_rank buckets; the region of (local bucket, source rank) lives in the OWNER's "area"
+// (records followed by the per-region record counts), published through a CUDA IPC handle.  Pass 1 on every
+// rank stores its records straight into the owners' areas over NVLink and then its region counts; after a
+// barrier, pass 2 runs on the local area.  No key ever crosses the fabric: a 16-byte record carries ~7 l-mers.
+static size_t bkt_area_record_bytes(u32 nbpr, u32 nranks, u32 rcap) { return (size_t)nbpr * nranks * rcap * 16; }
+
+int euler_bkt_area_bytes(uint32_t nb_per_rank, uint32_t nranks, uint32_t rcap, uint64_t *bytes)
+{
+    if (!bytes) return EULER_ERR_ARG;
+    *bytes = bkt_area_record_bytes(nb_per_rank, nranks, rcap) + (size_t)nb_per_rank * nranks * 4 + 256;
+    return EULER_OK;
+}
+
+// which in {0, 1}: two areas per context so that a rank may scatter step i+1 while a peer still builds step i
+int euler_bkt_area_alloc(euler_ctx *ctx, int which, uint32_t nb_per_rank, uint32_t nranks, uint32_t rcap, void **dptr,
+                         unsigned char *handle64)
+{
+    if (!ctx || !dptr || which < 0 || which > 1) return EULER_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Pipeline *P = get_pipe(ctx);
+    uint64_t need = 0;
+    euler_bkt_area_bytes(nb_per_rank, nranks, rcap, &need);
+    if (P->bk_area[which] && P->bk_area_bytes[which] < need) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(P->bk_area[which]);
+        P->bk_area[which] = nullptr;
+    }
+    if (!P->bk_area[which]) {
+        // plain cudaMalloc: IPC handles cannot be taken from stream-ordered pool memory
+        cudaError_t e = cudaMalloc(&P->bk_area[which], need);
+        if (e != cudaSuccess) return euler_fail(ctx, EULER_ERR_NOMEM, "cudaMalloc(bucket area %llu bytes): %s", (u64)need, cudaGetErrorString(e));
+        P->bk_area_bytes[which] = need;
+    }
+    if (handle64) {
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, P->bk_area[which]));
+        memcpy(handle64, &h, 64);
+    }
+    *dptr = P->bk_area[which];
+    return EULER_OK;
+}
+
+// out[0] N_l, out[1] N_k of this rank's reads, out[2] flags (BKT_FLAG_REGION = a region overflowed), out[3] largest region
+int euler_bkt_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads, uint64_t n_bases, uint32_t l,
+                      uint32_t my_rank, uint32_t nranks, uint32_t nb_per_rank, uint32_t rcap, void *const *dst_areas, uint64_t *out)
+{
+    if (!ctx || !out || !dst_areas) return EULER_ERR_ARG;
+    if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
+    if (nranks < 1 || nranks > 16 || my_rank >= nranks || !nb_per_rank) return euler_fail(ctx, EULER_ERR_ARG, "bad rank / geometry");
+    if (((uintptr_t)d_buf & 15) != 0) return euler_fail(ctx, EULER_ERR_ARG, "d_buf must be 16-byte aligned");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Pipeline *P = get_pipe(ctx);
+    cudaStream_t s = ctx->stream;
+    const u32 NB = nranks * nb_per_rank;
+    EULER_TRY(P->stats.reserve(ctx, 64));
+    EULER_TRY(P->start_bits.reserve(ctx, n_bases / 32 + 2));
+    EULER_TRY(P->bk_cursors.reserve(ctx, NB));
+    EULER_TRY(P->bk_dst.reserve(ctx, 16));
+    uint4 *h_dst[16];
+    for (u32 d = 0; d < nranks; d++) h_dst[d] = (uint4 *)dst_areas[d];
+    CUDA_TRY(ctx, cudaMemcpyAsync(P->bk_dst.ptr(), h_dst, nranks * sizeof(uint4 *), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr() + 40, 0, 8 * sizeof(u64), s));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->bk_cursors.ptr(), 0, (size_t)NB * sizeof(u32), s));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    EULER_TRY(enc_mark_starts(ctx, (const u64 *)d_read_off, nreads, n_bases, P->start_bits.ptr()));
+    EULER_TRY(bkt_partition(ctx, d_buf, n_bases, P->start_bits.ptr(), l, nranks, nb_per_rank, my_rank, rcap, P->bk_dst.ptr(),
+                            P->bk_cursors.ptr(), P->stats.ptr() + 40));
+    EULER_TRY(bkt_push_counts(ctx, P->bk_cursors.ptr(), P->bk_dst.ptr(), bkt_area_record_bytes(nb_per_rank, nranks, rcap), nb_per_rank,
+                              nranks, my_rank, P->stats.ptr() + 46));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+    u64 h[8];
+    EULER_TRY(read_u64s(ctx, P->stats.ptr() + 40, h, 8));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[3] = h[6];
+    cudaEventElapsedTime(&P->bk_scatter_ms, ctx->ev[0], ctx->ev[1]);
+    return EULER_OK;
+}
+
+int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_rank, uint32_t nranks, uint32_t nb_per_rank,
+                    uint32_t rcap, uint64_t distinct_hint, euler_stats *stats)
+{
+    if (!ctx || !d_area) return EULER_ERR_ARG;
+    if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
+    if (nranks < 1 || nranks > 16 || my_rank >= nranks || !nb_per_rank) return euler_fail(ctx, EULER_ERR_ARG, "bad rank / geometry");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Pipeline *P = get_pipe(ctx);
+    cudaStream_t s = ctx->stream;
+    P->wide = false; P->l = l; P->flags = 0; P->have_graph = false; P->expanded = false; P->text_valid = false;
+    memset(&P->st, 0, sizeof(P->st));
+    EULER_TRY(P->stats.reserve(ctx, 64));
+    const u32 nb = nb_per_rank;
+    const u32 log_cap = env_u32("EULER_B200_BKT_LOGCAP", 11);
+    const u64 key = ((u64)nb << 32) ^ ((u64)nranks << 8) ^ l;   // what the learned capacities belong to
+    const bool learned = !distinct_hint && P->bk_dist_key == key && P->bk_learned_u;
+    const u64 est_c = distinct_hint ? distinct_hint : (learned ? (P->bk_learned_u + 1) / 2 : 0);
+    u64 ucap = est_c ? (distinct_hint ? 2 * est_c + est_c / 4 : P->bk_learned_u + P->bk_learned_u / 32) + 1024 : 0;
+    u64 vcap = est_c ? (distinct_hint ? 2 * est_c + est_c / 4 : P->bk_learned_v + P->bk_learned_v / 32) + 1024 : 0;
+    u64 bcap = pow2_at_least((est_c ? est_c / 6 : (u64)nb * 64) + 1024);
+    u64 h[8] = {0};
+    u32 retries = 0, launches = 0;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    while (true) {
+        EULER_TRY(dev_reserve(ctx, P->bk_state, bkt_state_bytes(nb)));
+        EULER_TRY(P->bk_bkeys.reserve(ctx, bcap)); EULER_TRY(P->bk_bvals.reserve(ctx, 2 * bcap));
+        EULER_TRY(P->lkeys.reserve(ctx, ucap)); EULER_TRY(P->lvals.reserve(ctx, ucap)); EULER_TRY(P->loffs.reserve(ctx, ucap));
+        EULER_TRY(P->ev1.reserve(ctx, ucap)); EULER_TRY(P->ev2.reserve(ctx, ucap));
+        EULER_TRY(P->vkeys.reserve(ctx, vcap));
+        EULER_TRY(P->lcount.reserve(ctx, 4 * vcap + 4)); EULER_TRY(P->ecount.reserve(ctx, 4 * vcap + 4));
+        EULER_TRY(P->lstart.reserve(ctx, 4 * vcap + 4)); EULER_TRY(P->estart.reserve(ctx, 4 * vcap + 4));
+        EULER_TRY(P->ev.reserve(ctx, vcap));
+        CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 8 * sizeof(u64), s));
+        BktBuild bb;
+        bb.records = d_area; bb.counts = (const u32 *)((const char *)d_area + bkt_area_record_bytes(nb, nranks, rcap));
+        bb.nb = nb; bb.nranks = nranks; bb.rcap = rcap; bb.l = l; bb.log_capl = log_cap; bb.log_capv = log_cap;
+        bb.lkeys = P->lkeys.ptr(); bb.lvals = P->lvals.ptr(); bb.loffs = P->loffs.ptr(); bb.ev1 = P->ev1.ptr(); bb.ev2 = P->ev2.ptr(); bb.ucap = ucap;
+        bb.vkeys = P->vkeys.ptr(); bb.lcount = P->lcount.ptr(); bb.ecount = P->ecount.ptr(); bb.lstart = P->lstart.ptr();
+        bb.estart = P->estart.ptr(); bb.ev = P->ev.ptr(); bb.vcap = vcap;
+        bb.state = P->bk_state.p; bb.bkeys = P->bk_bkeys.ptr(); bb.bvals = P->bk_bvals.ptr(); bb.bcap = bcap; bb.stats = P->stats.ptr();
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], s));
+        EULER_TRY(bkt_build(ctx, bb));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
+        launches += 2;
+        EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 8));
+        const u64 fl = h[2];
+        if (fl & BKT_FLAG_INTERNAL) return euler_fail(ctx, EULER_ERR_STATE, "internal: bucketed build consistency check failed (flags %llx)", fl);
+        if (fl & BKT_FLAG_TABLE)
+            return euler_fail(ctx, EULER_ERR_OVERFLOW, "a bucket does not fit its shared-memory table: partition again with more buckets per rank");
+        if (!(fl & (BKT_FLAG_OUTPUT | BKT_FLAG_BOUNDARY))) break;
+        if (++retries > 6) return euler_fail(ctx, EULER_ERR_OVERFLOW, "bucketed build: capacities did not settle");
+        if (fl & BKT_FLAG_OUTPUT) { ucap = h[3] + h[3] / 64 + 1024; vcap = h[4] + h[4] / 64 + 1024; }
+        if (fl & BKT_FLAG_BOUNDARY) bcap *= 4;
+    }
+    const u64 U_l = h[3], V = h[4], E = h[5];
+    if (V >= 0x3fffffffull || U_l >= 0xffffffffull) return euler_fail(ctx, EULER_ERR_RANGE, "graph exceeds u32 ids (U_l=%llu V=%llu)", U_l, V);
+    P->U_l = U_l; P->V = V; P->E = E;
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    P->have_graph = true;
+    P->bk_dist_key = key; P->bk_learned_u = U_l; P->bk_learned_v = V;
+    euler_stats &st = P->st;
+    st.distinct_lmers = U_l; st.distinct_kmers = V; st.edge_count = E;
+    st.lmer_table_capacity = (u64)nb << log_cap; st.kmer_table_capacity = (u64)nb << log_cap; st.retries = retries;
+    st.ms_count = P->bk_scatter_ms;
+    cudaEventElapsedTime(&st.ms_graph, ctx->ev[0], ctx->ev[2]);
+    st.ms_total = st.ms_graph;
+    cudaEventElapsedTime(&st.ms_build_kernel, ctx->ev[5], ctx->ev[2]);
+    st.kernel_launches = launches; st.path = 1; st.n_buckets = nb; st.bucket_records = h[6];
     if (stats) *stats = st;
     return EULER_OK;
 }

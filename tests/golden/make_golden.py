@@ -11,6 +11,11 @@ Fixtures
                     limit in {0,1}: build() table and all_contigs() output.
   synth_small.json  600 seeded random reads (with N's and ragged lengths) from a 3 kbp genome,
                     k in {15,16,31}: same outputs.
+  graph_pins.json   the de Bruijn GRAPH artefacts as a pure function of the reference's own build(reads, l, 0)
+                    (:25-42) and fw / bw (:16-23) for the same two read sets: the vertex set, per-vertex
+                    lcount[4] / ecount[4] (multiplicity of the l-mer v+x / x+v) and the edge multiset
+                    (l-mer, multiplicity).  Pins the degree arrays and edge lists of the oracle and of the GPU
+                    path independently of the oracle's own restatement of pydebruijn.py.
 """
 import hashlib
 import json
@@ -55,6 +60,16 @@ def run_case(ra, reads, k, limit):
     }
 
 
+def graph_case(ra, reads, l):
+    """vertices / degree slots / edges of the l-mer graph from the reference's build(), fw() and bw() alone"""
+    d = ra.build(reads, l, 0)
+    verts = sorted({x[:-1] for x in d} | {x[1:] for x in d})
+    # fw('A' + v) yields v + x, bw(v + 'A') yields x + v  (x over 'ACGT')
+    lcount = [[d.get(km, 0) for km in ra.fw("A" + v)] for v in verts]
+    ecount = [[d.get(km, 0) for km in ra.bw(v + "A")] for v in verts]
+    return {"l": l, "vertices": verts, "lcount": lcount, "ecount": ecount, "edges": sorted([x, c] for x, c in d.items())}
+
+
 def read_fasta_lines(path):
     out = []
     with open(path) as f:
@@ -93,6 +108,14 @@ def main():
              "cases": [run_case(ra, sreads, k, lim) for k in (15, 16, 31) for lim in (0, 1)]}
     with open(os.path.join(HERE, "synth_small.json"), "w") as f:
         json.dump(synth, f, indent=0)
+    pins = {"source": "referenceAssembler.build(reads, l, 0) + fw/bw, see make_golden.py",
+            "g200": [graph_case(ra, reads, l) for l in (10, 18)],
+            "synth_small": [graph_case(ra, sreads, l) for l in (16, 32)]}
+    with open(os.path.join(HERE, "graph_pins.json"), "w") as f:
+        json.dump(pins, f, separators=(",", ":"))
+    for name in ("g200", "synth_small"):
+        for c in pins[name]:
+            print("graph", name, c["l"], len(c["vertices"]), len(c["edges"]), sum(m for _, m in c["edges"]))
     for name, fx in (("g200", g200), ("synth_small", synth)):
         for c in fx["cases"]:
             print(name, c["k"], c["limit"], len(c["kmers"]), c["kmer_sha"], len(c["contigs"]), c["contig_sha"])

@@ -121,10 +121,34 @@ def test_readers(tmp_path, g200_reads):
 
 
 def test_bench_reference_arm_runs_on_cpu():
-    """`bench.py --impl reference` (the oracle port on host cores) prints one JSON line."""
+    """`bench.py --impl reference` prints one JSON line: the UNMODIFIED reference's build() (source in this container,
+    the bytecode of oracle/build_ref.py on the GPU box) under multiprocessing.Pool, else the oracle port."""
     import json
+    from oracle import ref_loader
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                                   "--warmup", "0", "--workload", "small_smoke"], text=True)
+                                   "--warmup", "0", "--workload", "small_smoke", "--ref-genome", "20000"], text=True)
     line = json.loads(out.strip().splitlines()[-1])
-    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
-    assert line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["impl"] == "reference" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_loader.kind() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_reference_bytecode_is_the_reference():
+    """oracle/build_ref.py byte-compiles the unmodified reference module; loaded sourceless it gives the golden tables."""
+    import importlib.machinery
+    import importlib.util
+    import json
+    import types
+    from oracle import build_ref
+    pyc = build_ref.build()
+    if pyc is None:
+        pytest.skip("neither /root/reference nor oracle/_ref/ is present")
+    sys.modules.setdefault("dask", types.SimpleNamespace(delayed=lambda f=None, **kw: f))
+    loader = importlib.machinery.SourcelessFileLoader("ref_pyc_check", pyc)
+    mod = importlib.util.module_from_spec(importlib.util.spec_from_loader("ref_pyc_check", loader))
+    loader.exec_module(mod)
+    with open(os.path.join(ROOT, "tests", "golden", "g200.json")) as f:
+        fx = json.load(f)
+    case = next(c for c in fx["cases"] if c["k"] == 9 and c["limit"] == 1)
+    d = mod.build(fx["reads"], 9, 1)
+    assert sorted([km, c] for km, c in d.items()) == case["kmers"]

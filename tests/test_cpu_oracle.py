@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import oracle
-from util import random_reads
+from util import check_graph_against_pins, random_reads
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -148,3 +148,14 @@ def test_synthetic_generator_is_deterministic_and_sliceable():
     clean = oracle.synth_reads(50000, 100, err_ppm=0, first=0, count=300)
     frac = (a != clean).mean()
     assert 0.005 < frac < 0.015                    # ~1 % substitutions
+
+
+@pytest.mark.parametrize("name", ["g200", "synth_small"])
+def test_oracle_graph_equals_the_reference_derived_pins(name):
+    """Degree arrays, vertex set and edge lists of the oracle's D1-D6 restatement against pins derived from the
+    unmodified reference's build(reads, l, 0) + fw / bw (tests/golden/graph_pins.json, make_golden.py)."""
+    reads = _load("g200.json" if name == "g200" else "synth_small.json")["reads"]
+    buf, off = oracle.pack_reads(reads)
+    for pin in _load("graph_pins.json")[name]:
+        g = oracle.graph_build(buf, off, pin["l"], expand=False)
+        check_graph_against_pins(pin, g.vk_lo, g.lcount, g.ecount, g.lk_lo, g.lvals, g.ev1, g.ev2, oracle.decode_key)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
-from util import random_reads
+from util import check_graph_against_pins, random_reads
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -93,7 +93,7 @@ def test_graph_stage_from_an_lmer_table(ctx, g200_reads, l):
     """euler_pipeline_run_lmers: the graph stage fed with a count table (what the multi-GPU driver joins on one
     rank) gives the artefacts and contigs of the run on the reads themselves."""
     import _native as N
-    from util import random_reads
+    from util import check_graph_against_pins, random_reads
     reads = g200_reads if l <= 18 else random_reads(9, 300, genome_len=3000)
     buf, off = oracle.pack_reads(reads)
     flags = N.RUN_EXPAND_EDGES | N.RUN_CANONICAL_IDS
@@ -421,3 +421,17 @@ def test_device_ingestion_matches_the_reference_readers(ctx, tmp_path, g200_read
     b, o = oracle.pack_reads(g200_reads)
     ref, _ = oracle.euler_contigs(b, o, 12)
     assert ec.assemble2(12, infile=str(fa), mode="euler") == ref
+
+
+@pytest.mark.parametrize("name", ["g200", "synth_small"])
+def test_graph_equals_the_reference_derived_pins(ctx, name):
+    """The GPU path's vertex set, degree arrays, edge multiset and edge end points against pins derived from the
+    unmodified reference's build(reads, l, 0) + fw / bw (tests/golden/graph_pins.json) -- independent of the oracle."""
+    import _native as N
+    reads = _load("g200.json" if name == "g200" else "synth_small.json")["reads"]
+    buf, off = oracle.pack_reads(reads)
+    for pin in _load("graph_pins.json")[name]:
+        ctx.run_host(buf, off, pin["l"], N.RUN_CANONICAL_IDS)
+        check_graph_against_pins(pin, ctx.download(N.ART_KMER_KEYS), ctx.download(N.ART_LCOUNT), ctx.download(N.ART_ECOUNT),
+                                 ctx.download(N.ART_LMER_KEYS), ctx.download(N.ART_LMER_VALUES), ctx.download(N.ART_EDGE_V1),
+                                 ctx.download(N.ART_EDGE_V2), oracle.decode_key)

@@ -28,3 +28,18 @@ def random_reads(seed, n, genome_len=4000, lens=(20, 35, 64, 100, 100, 150), n_f
 def lower_some(reads, seed, frac=0.3):
     rng = random.Random(seed)
     return [r.lower() if rng.random() < frac else r for r in reads]
+
+
+def check_graph_against_pins(pin, vkeys, lcount, ecount, lkeys, lvals, ev1, ev2, decode_key):
+    """Compare graph artefacts (ids = rank in ascending key order) with a case of tests/golden/graph_pins.json,
+    which make_golden.py derived from the UNMODIFIED reference's build(reads, l, 0) and fw / bw alone:
+    vertex set, per-vertex lcount[4] / ecount[4], edge multiset and the (prefix, suffix) vertex of every edge."""
+    l = pin["l"]
+    verts = [decode_key(int(v), 0, l - 1) for v in vkeys]
+    assert verts == pin["vertices"]
+    assert np.asarray(lcount, np.uint32).reshape(-1, 4).tolist() == pin["lcount"]
+    assert np.asarray(ecount, np.uint32).reshape(-1, 4).tolist() == pin["ecount"]
+    edges = [[decode_key(int(x), 0, l), int(m)] for x, m in zip(lkeys, lvals)]
+    assert edges == pin["edges"]
+    for (x, _), a, b in zip(edges, ev1, ev2):
+        assert verts[int(a)] == x[:-1] and verts[int(b)] == x[1:]
