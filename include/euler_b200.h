@@ -306,9 +306,11 @@ int euler_bkt_area_alloc(euler_ctx *ctx, int which, uint32_t nb_per_rank, uint32
                          unsigned char *handle64);
 /* out[0] forward l-mer windows, out[1] forward k-mer windows of this rank's reads, out[2] flags (0x10: a region
  * overflowed -- partition again with the capacity of out[3]), out[3] records in the largest region */
+/* d_out != NULL: asynchronous form, the four words are left in device memory (u64[4]) on the ctx stream and `out`
+ * may be NULL -- e.g. as the payload of the collective that doubles as the barrier of step 3 */
 int euler_bkt_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads, uint64_t n_bases,
                       uint32_t l, uint32_t my_rank, uint32_t nranks, uint32_t nb_per_rank, uint32_t rcap,
-                      void *const *dst_areas, uint64_t *out);
+                      void *const *dst_areas, uint64_t *out, void *d_out);
 int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_rank, uint32_t nranks,
                     uint32_t nb_per_rank, uint32_t rcap, uint64_t distinct_hint, euler_stats *stats);
 

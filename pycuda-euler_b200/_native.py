@@ -115,7 +115,7 @@ def load():
         "euler_dist_build_regions": [vp, vp, u64, vp, u32, u32, u32, u64, vp],
         "euler_bkt_area_bytes": [u32, u32, u32, vp],
         "euler_bkt_area_alloc": [vp, i32, u32, u32, u32, vp, vp],
-        "euler_bkt_scatter": [vp, vp, vp, u64, u64, u32, u32, u32, u32, u32, vp, vp],
+        "euler_bkt_scatter": [vp, vp, vp, u64, u64, u32, u32, u32, u32, u32, vp, vp, vp],
         "euler_bkt_build": [vp, vp, u32, u32, u32, u32, u32, u64, vp],
         "euler_compat_phase1": [vp, vp, u64, u32, vp, vp],
         "euler_compat_copy_to_bucket": [vp, vp, vp, vp, u64, vp, u32, vp, vp],
@@ -162,6 +162,16 @@ class Context:
         self.device = device
 
     def close(self):
+        # peer mappings of the multi-GPU exchanges live on the context (eulercuda/dist.py) and end with it
+        for name in ("_bucket_exchange", "_peer_exchange"):
+            ex = getattr(self, name, None)
+            if ex is not None and hasattr(ex, "close"):
+                try:
+                    ex.close()
+                except Exception:
+                    pass
+            if hasattr(self, name):
+                setattr(self, name, None)
         if getattr(self, "h", None):
             self.lib.euler_ctx_destroy(self.h)
             self.h = None
@@ -603,13 +613,15 @@ class Context:
         self.check(self.lib.euler_bkt_area_alloc(self.h, int(which), int(nb_per_rank), int(nranks), int(rcap), C.byref(p), handle))
         return p.value, bytes(handle)
 
-    def bkt_scatter(self, d_buf, d_off, nreads, n_bases, l, rank, nranks, nb_per_rank, rcap, dst_areas):
-        """-> uint64[4]: forward l-mer windows, forward k-mer windows, flags (0x10 = a region overflowed), largest region"""
+    def bkt_scatter(self, d_buf, d_off, nreads, n_bases, l, rank, nranks, nb_per_rank, rcap, dst_areas, d_out=None):
+        """-> uint64[4]: forward l-mer windows, forward k-mer windows, flags (0x10 = a region overflowed), largest region.
+        d_out (device pointer to 4 x u64): asynchronous form, the words stay on the device and None is returned."""
         out = np.zeros(4, np.uint64)
         arr = (C.c_void_p * nranks)(*[C.c_void_p(int(x)) for x in dst_areas])
         self.check(self.lib.euler_bkt_scatter(self.h, C.c_void_p(int(d_buf)), C.c_void_p(int(d_off)), int(nreads), int(n_bases),
-                                              int(l), int(rank), int(nranks), int(nb_per_rank), int(rcap), arr, _p(out)))
-        return out
+                                              int(l), int(rank), int(nranks), int(nb_per_rank), int(rcap), arr,
+                                              None if d_out else _p(out), C.c_void_p(int(d_out)) if d_out else None))
+        return None if d_out else out
 
     def bkt_build(self, d_area, l, rank, nranks, nb_per_rank, rcap, distinct_hint=0):
         st = Stats()

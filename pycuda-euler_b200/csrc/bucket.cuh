@@ -208,37 +208,57 @@ BK_HD bk_u32 bk_eq16(const bk_u32 (&win)[16], bk_u32 win_prev)
     for (int i = 0; i < 16; i++) eq16 |= (win[i] == (i ? win[i - 1] : win_prev) ? 1u : 0u) << i;
     return eq16;
 }
+// The records of ONE piece [s, e] (positions of the lane's chunk): the piece itself and, for a piece that starts the
+// chunk right after a k-mer of another bucket, the orphan single-l-mer record for that bucket.
+//   w_s = minimizer score at s, w_before = at s - 1 (the previous chunk's last position when s = 0),
+//   w_after = at e + 1 (ignored when e = 15)
+template <typename Emit>
+BK_HD void bk_piece_records(bk_u32 c2, bk_u32 c1, bk_u32 c0, bk_u32 s, bk_u32 e, bk_u32 w_s, bk_u32 w_before, bk_u32 w_after,
+                            bk_u32 vl16, bk_u32 k, BkGeom g, Emit emit)
+{
+    const bk_u32 b = bk_bucket_of(w_s, g);
+    bk_u32 flags = 0, lf = 0, rf = 0;
+    if ((vl16 >> s) & 1u) {   // the l-mer ending at s exists: it is this piece's first l-mer
+        lf = 1;
+        const bk_u32 bp = bk_bucket_of(w_before, g);
+        if (bp != b) {
+            flags |= BK_HDR_LFF;
+            if (s == 0)   // the previous chunk's piece could not look ahead: ship the l-mer to its bucket from here
+                emit(bp, bk_make_record(c2, c1, c0, 32u - k, k + 1u, BK_HDR_RFF));
+        }
+    }
+    if (e < 15u && ((vl16 >> (e + 1u)) & 1u)) {   // the l-mer ending at e+1: ours as well when its suffix vertex is foreign
+        if (bk_bucket_of(w_after, g) != b) {
+            rf = 1;
+            flags |= BK_HDR_RFF;
+        }
+    }
+    if (e - s + lf + rf == 0) return;   // a lone k-mer with no l-mer around it is no vertex of the graph
+    const bk_u32 q0 = 32u + s - (k - 1u) - lf, q1 = 32u + e + rf;
+    emit(b, bk_make_record(c2, c1, c0, q0, q1 - q0 + 1u, flags));
+}
+
+// piece boundaries of a lane: bit i of `starts` / `ends` = a piece starts / ends at position i (the j-th start pairs
+// with the j-th end).  A piece = consecutive valid k-mers of one read with the same minimizer score, inside the chunk.
+BK_HD void bk_piece_masks(bk_u32 eq16, bk_u32 vk16, bk_u32 vl16, bk_u32 &starts, bk_u32 &ends)
+{
+    const bk_u32 cont = vl16 & eq16 & 0xfffeu;   // position i continues the piece of i-1: same read, same minimizer (never across the lane start)
+    starts = vk16 & ~cont;
+    ends = vk16 & ~(cont >> 1);
+}
+
 template <typename Emit>
 BK_HD void bk_lane_pieces(bk_u32 c2, bk_u32 c1, bk_u32 c0, const bk_u32 *win, bk_u32 win_prev, bk_u32 eq16, bk_u32 vk16,
                           bk_u32 vl16, bk_u32 k, BkGeom g, Emit emit)
 {
     if (!vk16) return;
-    const bk_u32 cont = vl16 & eq16 & 0xfffeu;   // position i continues the piece of i-1: same read, same minimizer (never across the lane start)
-    bk_u32 starts = vk16 & ~cont, ends = vk16 & ~(cont >> 1);
+    bk_u32 starts, ends;
+    bk_piece_masks(eq16, vk16, vl16, starts, ends);
     while (starts) {
         const bk_u32 s = (bk_u32)bk_ffs(starts) - 1u, e = (bk_u32)bk_ffs(ends) - 1u;
         starts &= starts - 1u;
         ends &= ends - 1u;
-        const bk_u32 b = bk_bucket_of(win[s], g);
-        bk_u32 flags = 0, lf = 0, rf = 0;
-        if ((vl16 >> s) & 1u) {   // the l-mer ending at s exists: it is this piece's first l-mer
-            lf = 1;
-            const bk_u32 bp = bk_bucket_of(s ? win[s - 1] : win_prev, g);
-            if (bp != b) {
-                flags |= BK_HDR_LFF;
-                if (s == 0)   // the previous chunk's piece could not look ahead: ship the l-mer to its bucket from here
-                    emit(bp, bk_make_record(c2, c1, c0, 32u - k, k + 1u, BK_HDR_RFF));
-            }
-        }
-        if (e < 15u && ((vl16 >> (e + 1u)) & 1u)) {   // the l-mer ending at e+1: ours as well when its suffix vertex is foreign
-            if (bk_bucket_of(win[e + 1u], g) != b) {
-                rf = 1;
-                flags |= BK_HDR_RFF;
-            }
-        }
-        if (e - s + lf + rf == 0) continue;   // a lone k-mer with no l-mer around it is no vertex of the graph
-        const bk_u32 q0 = 32u + s - (k - 1u) - lf, q1 = 32u + e + rf;
-        emit(b, bk_make_record(c2, c1, c0, q0, q1 - q0 + 1u, flags));
+        bk_piece_records(c2, c1, c0, s, e, win[s], s ? win[s - 1] : win_prev, e < 15u ? win[e + 1u] : 0u, vl16, k, g, emit);
     }
 }
 

@@ -7,8 +7,9 @@
 // supply left context.  Per lane: 16 m-mer scores (two funnel shifts + min + scramble each, no rolling
 // state), the 20 scores before them from the warp's shared-memory rows (stride 20 words: conflict-free 128-bit
 // accesses), a van Herk / Gil-Werman sliding minimum (~4 min per position), validity of all 16 k-mer / l-mer
-// windows from two 64-bit masks, then one record per minimizer run (1-3 per lane): a cursor atomic and one
-// 16-byte store.
+// windows from two 64-bit masks and the piece boundaries (bit masks).  The tile's pieces are then listed in shared
+// memory and handled one per lane per round -- every lane busy, 32 cursor atomics in flight -- each giving one
+// 16-byte record: a cursor atomic and one 16-byte store.
 #include "bucket.cuh"
 #include "encode.cuh"
 #include "kernels.h"
@@ -18,7 +19,7 @@
 #define BP_ROW 20                       // words per lane row (16 scores + 4 pad)
 #define BP_ROWS 34                      // two rows of padding in front of lane 0
 #ifndef BP_MINB
-#define BP_MINB 5
+#define BP_MINB 8
 #endif
 
 template <int W>
@@ -27,8 +28,12 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const 
                                                                            u32 my_rank, u32 rcap, uint4 *const *__restrict__ dst,
                                                                            u32 *__restrict__ cursors, u64 ntiles, u64 *__restrict__ stats)
 {
-    __shared__ __align__(16) u32 s_rows[BP_WARPS][BP_ROWS * BP_ROW];
-    u32 *rows = s_rows[threadIdx.x >> 5];
+    __shared__ __align__(16) u32 s_rows[BP_WARPS][BP_ROWS * BP_ROW];   // per lane: 16 m-mer scores, then 16 window minima
+    __shared__ u32 s_codes[BP_WARPS][34];                              // 2-bit codes of every lane's chunk (two pad entries in front)
+    __shared__ u32 s_vl[BP_WARPS][32];                                 // valid l-mer windows of every lane
+    __shared__ unsigned short s_desc[BP_WARPS][ENC_ADV * 16];          // the tile's pieces: lane << 8 | end << 4 | start
+    const int wib = threadIdx.x >> 5;
+    u32 *rows = s_rows[wib];
     const int lane = threadIdx.x & 31;
     u32 *my_row = rows + (lane + 2) * BP_ROW;
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -36,11 +41,12 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const 
     const u32 k = l - 1, m = bk_m_of(k);
     u32 nl_tot = 0, nk_tot = 0;
     bool overflow = false;
+    if (lane < 2) s_codes[wib][lane] = 0;
 
     for (u64 tile = warp; tile < ntiles; tile += nwarps) {
         const long long chunk = (long long)(tile * ENC_ADV) - ENC_HALO + lane;
         const Chunk c = load_chunk(buf16, chunk, n_bases, start_bits);
-        const u32 p1 = __shfl_up_sync(0xffffffffu, c.codes, 1), p2 = __shfl_up_sync(0xffffffffu, c.codes, 2);
+        const u32 p1 = __shfl_up_sync(0xffffffffu, c.codes, 1);
         const u32 v1 = __shfl_up_sync(0xffffffffu, c.vmask, 1), v2 = __shfl_up_sync(0xffffffffu, c.vmask, 2);
         const u32 s1 = __shfl_up_sync(0xffffffffu, c.smask, 1), s2 = __shfl_up_sync(0xffffffffu, c.smask, 2);
         u32 sa[36];
@@ -52,6 +58,7 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const 
 #pragma unroll
             for (int i = 0; i < 16; i++) sa[20 + i] = sc[i];
         }
+        s_codes[wib][lane + 2] = c.codes;
         __syncwarp();
         {   // the 20 scores before this chunk: the previous lane's row and the last four of the lane before it
             const uint4 a = *reinterpret_cast<const uint4 *>(my_row - 2 * BP_ROW + 12);
@@ -69,25 +76,53 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const 
 #pragma unroll
         for (int i = 0; i < 16; i += 4) *reinterpret_cast<uint4 *>(my_row + i) = make_uint4(win[i], win[i + 1], win[i + 2], win[i + 3]);
         __syncwarp();
+        // ---- piece boundaries of this lane, listed for the whole warp ---------------------------------------------------
+        u32 starts = 0, ends = 0, vl16 = 0;
         if (lane >= ENC_HALO) {
             const u64 vmw = ((u64)v2 << 48) | ((u64)v1 << 32) | ((u64)c.vmask << 16);
             const u64 smw = ((u64)s2 << 48) | ((u64)s1 << 32) | ((u64)c.smask << 16);
             const u64 VK = bk_valid_kmers(vmw, smw, k);
-            const u32 vk16 = bk_own16(VK), vl16 = bk_own16(bk_valid_lmers(VK, smw, k));
+            const u32 vk16 = bk_own16(VK);
+            vl16 = bk_own16(bk_valid_lmers(VK, smw, k));
             nk_tot += __popc(vk16);
             nl_tot += __popc(vl16);
-            const u32 win_prev = my_row[-BP_ROW + 15];
-            bk_lane_pieces(p2, p1, c.codes, my_row, win_prev, bk_eq16(win, win_prev), vk16, vl16, k, geom, [&](u32 bucket, const BkRec &r) {
-                const u32 rank = geom.nranks > 1 ? bucket / geom.nb_per_rank : 0u;
-                const u32 lb = bucket - rank * geom.nb_per_rank;
-                const u32 pos = atomicAdd(cursors + bucket, 1u);
-                if (pos < rcap) {
-                    uint4 *region = dst[rank] + ((u64)lb * geom.nranks + my_rank) * rcap;
-                    region[pos] = make_uint4(r.hdr, r.d[0], r.d[1], r.d[2]);
-                } else {
-                    overflow = true;
-                }
-            });
+            bk_piece_masks(bk_eq16(win, my_row[-BP_ROW + 15]), vk16, vl16, starts, ends);
+        }
+        s_vl[wib][lane] = vl16;
+        const u32 np = __popc(starts);
+        u32 inc = np;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const u32 total = __shfl_sync(0xffffffffu, inc, 31);
+        u32 at = inc - np;
+        while (starts) {
+            const u32 s = (u32)__ffs(starts) - 1u, e = (u32)__ffs(ends) - 1u;
+            starts &= starts - 1u;
+            ends &= ends - 1u;
+            s_desc[wib][at++] = (unsigned short)((lane << 8) | (e << 4) | s);
+        }
+        __syncwarp();
+        // ---- one piece per lane per round: record(s), cursor atomic, 16-byte store -------------------------------------------
+        for (u32 t = lane; t < total; t += 32) {
+            const u32 d = s_desc[wib][t];
+            const u32 L = d >> 8, e = (d >> 4) & 15u, s = d & 15u;
+            const u32 *row = rows + (L + 2) * BP_ROW;
+            const u32 w_s = row[s], w_before = s ? row[s - 1] : row[-BP_ROW + 15], w_after = e < 15u ? row[e + 1] : 0u;
+            bk_piece_records(s_codes[wib][L], s_codes[wib][L + 1], s_codes[wib][L + 2], s, e, w_s, w_before, w_after, s_vl[wib][L], k, geom,
+                             [&](u32 bucket, const BkRec &r) {
+                                 const u32 rank = geom.nranks > 1 ? bucket / geom.nb_per_rank : 0u;
+                                 const u32 lb = bucket - rank * geom.nb_per_rank;
+                                 const u32 pos = atomicAdd(cursors + bucket, 1u);
+                                 if (pos < rcap) {
+                                     uint4 *region = dst[rank] + ((u64)lb * geom.nranks + my_rank) * rcap;
+                                     region[pos] = make_uint4(r.hdr, r.d[0], r.d[1], r.d[2]);
+                                 } else {
+                                     overflow = true;
+                                 }
+                             });
         }
         __syncwarp();   // the rows are rewritten by the next tile
     }

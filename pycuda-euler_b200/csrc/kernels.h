@@ -172,7 +172,7 @@ int bkt_partition(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_b
 struct BktBuild {
     const void *records;   // region (b, src) at ((b * nranks + src) * rcap) records of 16 bytes
     const u32 *counts;     // [nb * nranks]
-    u32 nb, nranks, rcap, l, log_capl, log_capv;
+    u32 nb, nranks, rcap, l, cap;   // cap: slots of each per-bucket shared-memory table (l-mers, vertices), a multiple of 256
     u64 *lkeys; u32 *lvals, *loffs, *ev1, *ev2; u64 ucap;
     u64 *vkeys; u32 *lcount, *ecount, *lstart, *estart; euler_vertex *ev; u64 vcap;
     void *state;           // bkt_state_bytes(nb)
@@ -181,7 +181,7 @@ struct BktBuild {
 };
 int bkt_build(euler_ctx *ctx, const BktBuild &B);
 size_t bkt_state_bytes(u32 nb);
-size_t bkt_build_smem(u32 log_capl, u32 log_capv);
+size_t bkt_build_smem(u32 cap);
 // canonical-id post-processing of the bucketed build
 int bkt_iota(euler_ctx *ctx, u32 *v, u64 n);
 int bkt_invert_perm(euler_ctx *ctx, const u32 *perm, u64 n, u32 *inv);

@@ -330,6 +330,7 @@ static u64 pow2_at_least(u64 x)
     return p;
 }
 #define EULER_FALLBACK 1   // internal: take the global-table path instead
+#define BKT_MAX_CAP 7936u   // 28 B per slot: the largest per-bucket table that fits one block's shared memory
 
 static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 distinct_hint, euler_stats *stats)
 {
@@ -341,10 +342,10 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
     EULER_TRY(P->start_bits.reserve(ctx, B / 32 + 2));
 
     // geometry: buckets sized for a shared-memory table at ~45 % load
-    const u32 log_cap = env_u32("EULER_B200_BKT_LOGCAP", 11);
+    const u32 cap = (env_u32("EULER_B200_BKT_CAP", 1792) + 255u) / 256u * 256u;   // 28 B per slot: 4 resident blocks per SM
     const bool learned = !distinct_hint && P->bk_learned_bases == B && P->bk_learned_l == l && P->bk_learned_nb;
     u64 est_c = distinct_hint ? distinct_hint : (learned ? (P->bk_learned_u + 1) / 2 : (B ? B : 1));
-    const double per_bucket = 0.45 * (double)(1u << log_cap);
+    const double per_bucket = 0.45 * (double)cap;
     u64 nb64 = learned ? P->bk_learned_nb : (u64)((double)est_c * 1.06 / per_bucket) + 1;
     if (const u32 f = env_u32("EULER_B200_BKT_NB", 0)) nb64 = f;
     if (nb64 > (1ull << 24)) return EULER_FALLBACK;
@@ -394,7 +395,7 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
         }
         BktBuild bb;
         bb.records = P->bk_records.p; bb.counts = P->bk_cursors.ptr(); bb.nb = nb; bb.nranks = 1; bb.rcap = rcap; bb.l = l;
-        bb.log_capl = log_cap; bb.log_capv = log_cap;
+        bb.cap = cap;
         bb.lkeys = P->lkeys.ptr(); bb.lvals = P->lvals.ptr(); bb.loffs = P->loffs.ptr(); bb.ev1 = P->ev1.ptr(); bb.ev2 = P->ev2.ptr(); bb.ucap = ucap;
         bb.vkeys = P->vkeys.ptr(); bb.lcount = P->lcount.ptr(); bb.ecount = P->ecount.ptr(); bb.lstart = P->lstart.ptr();
         bb.estart = P->estart.ptr(); bb.ev = P->ev.ptr(); bb.vcap = vcap;
@@ -413,7 +414,7 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
             need_part = true;
         } else if (fl & BKT_FLAG_TABLE) {
             if (nb >= (1u << 22) || retries > 6) return EULER_FALLBACK;
-            nb *= 4;
+            nb *= 4;   // far more distinct l-mers than estimated: partition again into more buckets
             rcap = rcap / 4 + rcap / 8 + 64;
             need_part = true;
         } else {
@@ -477,7 +478,7 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
     }
     euler_stats &st = P->st;
     st.n_kmer_windows = N_k; st.n_lmer_windows = N_l; st.distinct_lmers = U_l; st.distinct_kmers = V; st.edge_count = E;
-    st.lmer_table_capacity = (u64)nb << log_cap; st.kmer_table_capacity = (u64)nb << log_cap; st.retries = retries;
+    st.lmer_table_capacity = (u64)nb * cap; st.kmer_table_capacity = (u64)nb * cap; st.retries = retries;
     cudaEventElapsedTime(&st.ms_count, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&st.ms_graph, ctx->ev[1], ctx->ev[6]);
     cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[6]);
@@ -1382,9 +1383,10 @@ int euler_bkt_area_alloc(euler_ctx *ctx, int which, uint32_t nb_per_rank, uint32
 
 // out[0] N_l, out[1] N_k of this rank's reads, out[2] flags (BKT_FLAG_REGION = a region overflowed), out[3] largest region
 int euler_bkt_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads, uint64_t n_bases, uint32_t l,
-                      uint32_t my_rank, uint32_t nranks, uint32_t nb_per_rank, uint32_t rcap, void *const *dst_areas, uint64_t *out)
+                      uint32_t my_rank, uint32_t nranks, uint32_t nb_per_rank, uint32_t rcap, void *const *dst_areas, uint64_t *out,
+                      void *d_out)
 {
-    if (!ctx || !out || !dst_areas) return EULER_ERR_ARG;
+    if (!ctx || (!out && !d_out) || !dst_areas) return EULER_ERR_ARG;
     if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
     if (nranks < 1 || nranks > 16 || my_rank >= nranks || !nb_per_rank) return euler_fail(ctx, EULER_ERR_ARG, "bad rank / geometry");
     if (((uintptr_t)d_buf & 15) != 0) return euler_fail(ctx, EULER_ERR_ARG, "d_buf must be 16-byte aligned");
@@ -1408,6 +1410,12 @@ int euler_bkt_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off,
     EULER_TRY(bkt_push_counts(ctx, P->bk_cursors.ptr(), P->bk_dst.ptr(), bkt_area_record_bytes(nb_per_rank, nranks, rcap), nb_per_rank,
                               nranks, my_rank, P->stats.ptr() + 46));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
+    if (d_out) {   // asynchronous form: the four words stay on the device (e.g. as the payload of the caller's collective)
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_out, P->stats.ptr() + 40, 3 * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync((u64 *)d_out + 3, P->stats.ptr() + 46, sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        P->bk_scatter_ms = -1.f;   // read from the events by the build call, after the stream has been synchronised
+        return EULER_OK;
+    }
     u64 h[8];
     EULER_TRY(read_u64s(ctx, P->stats.ptr() + 40, h, 8));
     out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[3] = h[6];
@@ -1428,7 +1436,6 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
     memset(&P->st, 0, sizeof(P->st));
     EULER_TRY(P->stats.reserve(ctx, 64));
     const u32 nb = nb_per_rank;
-    const u32 log_cap = env_u32("EULER_B200_BKT_LOGCAP", 11);
     const u64 key = ((u64)nb << 32) ^ ((u64)nranks << 8) ^ l;   // what the learned capacities belong to
     const bool learned = !distinct_hint && P->bk_dist_key == key && P->bk_learned_u;
     const u64 est_c = distinct_hint ? distinct_hint : (learned ? (P->bk_learned_u + 1) / 2 : 0);
@@ -1437,7 +1444,11 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
     u64 bcap = pow2_at_least((est_c ? est_c / 6 : (u64)nb * 64) + 1024);
     u64 h[8] = {0};
     u32 retries = 0, launches = 0;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
+    u32 cap = (env_u32("EULER_B200_BKT_CAP", 1792) + 255u) / 256u * 256u;
+    if (P->bk_scatter_ms < 0.f) {   // asynchronous scatter: its events have completed by now (the caller synchronised on the exchange)
+        if (cudaEventElapsedTime(&P->bk_scatter_ms, ctx->ev[0], ctx->ev[1]) != cudaSuccess) { P->bk_scatter_ms = 0.f; cudaGetLastError(); }
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[7], s));
     while (true) {
         EULER_TRY(dev_reserve(ctx, P->bk_state, bkt_state_bytes(nb)));
         EULER_TRY(P->bk_bkeys.reserve(ctx, bcap)); EULER_TRY(P->bk_bvals.reserve(ctx, 2 * bcap));
@@ -1450,7 +1461,7 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
         CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 8 * sizeof(u64), s));
         BktBuild bb;
         bb.records = d_area; bb.counts = (const u32 *)((const char *)d_area + bkt_area_record_bytes(nb, nranks, rcap));
-        bb.nb = nb; bb.nranks = nranks; bb.rcap = rcap; bb.l = l; bb.log_capl = log_cap; bb.log_capv = log_cap;
+        bb.nb = nb; bb.nranks = nranks; bb.rcap = rcap; bb.l = l; bb.cap = cap;
         bb.lkeys = P->lkeys.ptr(); bb.lvals = P->lvals.ptr(); bb.loffs = P->loffs.ptr(); bb.ev1 = P->ev1.ptr(); bb.ev2 = P->ev2.ptr(); bb.ucap = ucap;
         bb.vkeys = P->vkeys.ptr(); bb.lcount = P->lcount.ptr(); bb.ecount = P->ecount.ptr(); bb.lstart = P->lstart.ptr();
         bb.estart = P->estart.ptr(); bb.ev = P->ev.ptr(); bb.vcap = vcap;
@@ -1462,11 +1473,12 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
         EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 8));
         const u64 fl = h[2];
         if (fl & BKT_FLAG_INTERNAL) return euler_fail(ctx, EULER_ERR_STATE, "internal: bucketed build consistency check failed (flags %llx)", fl);
-        if (fl & BKT_FLAG_TABLE)
+        if ((fl & BKT_FLAG_TABLE) && cap * 2 > BKT_MAX_CAP)
             return euler_fail(ctx, EULER_ERR_OVERFLOW, "a bucket does not fit its shared-memory table: partition again with more buckets per rank");
-        if (!(fl & (BKT_FLAG_OUTPUT | BKT_FLAG_BOUNDARY))) break;
+        if (!(fl & (BKT_FLAG_TABLE | BKT_FLAG_OUTPUT | BKT_FLAG_BOUNDARY))) break;
         if (++retries > 6) return euler_fail(ctx, EULER_ERR_OVERFLOW, "bucketed build: capacities did not settle");
-        if (fl & BKT_FLAG_OUTPUT) { ucap = h[3] + h[3] / 64 + 1024; vcap = h[4] + h[4] / 64 + 1024; }
+        if (fl & BKT_FLAG_TABLE) cap *= 2;   // a local decision (no re-partition across ranks): larger tables, fewer resident blocks
+        else if (fl & BKT_FLAG_OUTPUT) { ucap = h[3] + h[3] / 64 + 1024; vcap = h[4] + h[4] / 64 + 1024; }
         if (fl & BKT_FLAG_BOUNDARY) bcap *= 4;
     }
     const u64 U_l = h[3], V = h[4], E = h[5];
@@ -1477,9 +1489,9 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
     P->bk_dist_key = key; P->bk_learned_u = U_l; P->bk_learned_v = V;
     euler_stats &st = P->st;
     st.distinct_lmers = U_l; st.distinct_kmers = V; st.edge_count = E;
-    st.lmer_table_capacity = (u64)nb << log_cap; st.kmer_table_capacity = (u64)nb << log_cap; st.retries = retries;
+    st.lmer_table_capacity = (u64)nb * cap; st.kmer_table_capacity = (u64)nb * cap; st.retries = retries;
     st.ms_count = P->bk_scatter_ms;
-    cudaEventElapsedTime(&st.ms_graph, ctx->ev[0], ctx->ev[2]);
+    cudaEventElapsedTime(&st.ms_graph, ctx->ev[7], ctx->ev[2]);
     st.ms_total = st.ms_graph;
     cudaEventElapsedTime(&st.ms_build_kernel, ctx->ev[5], ctx->ev[2]);
     st.kernel_launches = launches; st.path = 1; st.n_buckets = nb; st.bucket_records = h[6];

@@ -95,19 +95,31 @@ class PeerExchange:
         # counting.  Nobody can be two steps ahead -- the next count exchange needs everyone.
         self.nbuf = 1 if os.environ.get("EULER_B200_PEER_DOUBLE", "1") == "0" else 2
         self.phase = 0
-        self.base_ptr, handle = ctx.dist_recv_alloc(self.seg_cap * world * self.nbuf)
+        self.bases, self.base_ptr, handle, err = [], None, None, None
+        try:
+            self.base_ptr, handle = ctx.dist_recv_alloc(self.seg_cap * world * self.nbuf)
+        except Exception as e:    # still take part in every collective below: a rank that left early would hang the others
+            err = e
         self.local_ptr = self.base_ptr
-        handles = [None] * world
-        dist.all_gather_object(handles, handle, group=group)
-        self.bases = []
-        for d in range(world):
-            self.bases.append(self.base_ptr if d == rank else ctx.dist_peer_open(handles[d]))
-        self.next_step()
+        table = [None] * world
+        dist.all_gather_object(table, (handle, err is None), group=group)
+        if err is None and all(t[1] for t in table):
+            try:
+                for d in range(world):
+                    self.bases.append(self.base_ptr if d == rank else ctx.dist_peer_open(table[d][0]))
+            except Exception as e:
+                err = e
+        else:
+            err = err or RuntimeError("a peer could not allocate its receive buffer")
+        if err is not None:
+            self.close()
+            raise err
+        self.next_step(first=True)
 
-    def next_step(self):
+    def next_step(self, first=False):
         """switch to the other receive buffer (every rank calls this once per exchange, in lock step)"""
         import torch.distributed as dist
-        if self.nbuf == 1:
+        if self.nbuf == 1 and not first:
             dist.barrier(group=self.group)     # single buffer: wait until every rank has consumed the last step
         shift = 8 * self.seg_cap * self.world * (self.phase % self.nbuf)
         self.phase += 1
@@ -125,34 +137,40 @@ class PeerExchange:
         self.bases = []
 
 
-_PEER = {}
-
-
 def _peer_exchange(ctx, rank, world, seg_cap, group):
-    """The exchange object of (ctx, world), created collectively on first use.  It is never re-created by
-    one rank alone (that would dead-lock the handshake): a rank that needs more than the agreed capacity
-    reports the overflow through the count exchange, every rank takes the exact-size fallback for that
-    step and drops the object (`_drop_peer_exchange`), and the next step agrees on a larger one."""
-    key = (id(ctx), world)
-    px = _PEER.get(key)
+    """The key-exchange object of this context, created collectively on first use and kept ON the context (a new
+    Context can never inherit mappings of a freed buffer).  The transport is agreed collectively: every rank reports
+    whether its allocation and IPC opens succeeded, and if any failed all of them close their mappings and use NCCL.
+    A rank that needs more than the agreed capacity reports the overflow through the count exchange, every rank takes
+    the exact-size fallback for that step and drops the object (`_drop_peer_exchange`), and the next step agrees on a
+    larger one (the cached capacity is in 8-byte words, so a change of key width re-agrees as well)."""
+    import torch.distributed as dist
+    px = getattr(ctx, "_peer_exchange", None)
+    if px is not None and px is not False and (px.world != world or px.seg_cap < seg_cap):
+        px.close()
+        px = None
     if px is None:
+        err = None
         try:
-            px = PeerExchange(ctx, rank, world, max(int(seg_cap), _PEER_MIN.get(key, 0)), group)
-        except Exception as e:          # no peer access on this box: fall back to NCCL all_to_all
-            px = e
-        _PEER[key] = px
-    return None if isinstance(px, Exception) else px
-
-
-_PEER_MIN = {}
+            px = PeerExchange(ctx, rank, world, max(int(seg_cap), getattr(ctx, "_peer_min", 0)), group)
+        except Exception as e:          # no peer access from this rank: everyone must fall back together
+            err, px = e, None
+        oks = [None] * world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            if px is not None:
+                px.close()
+            px = False                  # remembered: NCCL all_to_all from now on
+        ctx._peer_exchange = px
+    return px if px else None
 
 
 def _drop_peer_exchange(ctx, world):
-    key = (id(ctx), world)
-    px = _PEER.pop(key, None)
-    if isinstance(px, PeerExchange):
-        _PEER_MIN[key] = int(px.seg_cap * 1.5)
+    px = getattr(ctx, "_peer_exchange", None)
+    if px:
+        ctx._peer_min = int(px.seg_cap * 1.5)
         px.close()
+    ctx._peer_exchange = None
 
 
 def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint=0, group=None, slack=1.25,
@@ -168,6 +186,10 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
     import torch
     import torch.distributed as dist
     dev = d_reads.device
+    if world > 1 and l <= 32 and use_peer and os.environ.get("EULER_B200_DIST_KEYS", "0") != "1":
+        res = build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint, group)
+        if res is not None:
+            return res
     kw = 2 if l > 32 else 1          # 8-byte words per key (128-bit keys above l = 32, csrc/wide_dist.cu)
     t0 = time.perf_counter()
     if world == 1 and kw == 2:
@@ -253,6 +275,178 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
             "phase_ms": {"partition": 1e3 * (t1 - t0), "count_exchange": 1e3 * (t2 - t1), "all_to_all": 1e3 * (t3 - t2),
                          "build": 1e3 * (t4 - t3)}}
     return st, info
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The minimizer-bucketed form (csrc/bucket.cuh): what crosses NVLink is the reads cut into 2-bit packed minimizer
+# runs (16-byte records of up to 17 l-mers), stored by the partition kernel straight into the owners' bucket
+# regions; the owner then builds every bucket in shared memory.  Used for l <= 32.
+BKT_CAP = 1792   # slots of a per-bucket shared-memory table (csrc/pipeline.cu default)
+
+
+def plan_buckets(n_bases, l, world, distinct_hint=0, cap=None):
+    """(buckets per rank, records per (bucket, source) region) for shards of at most n_bases bases per rank.
+    distinct_hint = expected distinct canonical l-mers PER RANK (0 = unknown: every window distinct)."""
+    cap = cap or int(os.environ.get("EULER_B200_BKT_CAP", BKT_CAP))
+    k = l - 1
+    w = k - min(k, 12) + 1
+    rec_per_base = 2.0 / (w + 1.0) + 1.0 / 16.0 + 0.01
+    est = int(distinct_hint) or max(int(n_bases), 1)
+    nbpr = int(est * 1.06 / (0.45 * cap)) + 1
+    rcap = int(n_bases * rec_per_base / (world * nbpr) * 1.5) + 64
+    return nbpr, rcap
+
+
+class BucketExchange:
+    """Geometry agreed by all ranks, two peer-visible receive areas per rank (step parity: a rank may scatter step
+    i+1 while a peer still builds step i; nobody can be two steps ahead, the flag exchange needs everyone) and the
+    peers' areas opened through CUDA IPC.  Created collectively; `ok` is the COLLECTIVE outcome, so either every rank
+    uses the object or none does."""
+
+    def __init__(self, ctx, rank, world, nb_per_rank, rcap, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        props = [None] * world
+        dist.all_gather_object(props, (int(nb_per_rank), int(rcap)), group=group)
+        self.nb_per_rank = max(p[0] for p in props)
+        self.rcap = max(p[1] for p in props)
+        self.phase = 0
+        self.local, self.areas, self.opened = [None, None], [None, None], []
+        handles, err = [None, None], None
+        try:
+            for which in (0, 1):
+                self.local[which], handles[which] = ctx.bkt_area_alloc(which, self.nb_per_rank, world, self.rcap)
+        except Exception as e:   # reported to everyone below
+            err = e
+        table = [None] * world
+        dist.all_gather_object(table, (handles, err is None), group=group)
+        if all(t[1] for t in table):
+            try:
+                for which in (0, 1):
+                    ptrs = []
+                    for d in range(world):
+                        if d == rank:
+                            ptrs.append(self.local[which])
+                        else:
+                            ptr = ctx.dist_peer_open(table[d][0][which])
+                            self.opened.append(ptr)
+                            ptrs.append(ptr)
+                    self.areas[which] = ptrs
+            except Exception as e:
+                err = e
+        oks = [None] * world
+        dist.all_gather_object(oks, err is None, group=group)
+        self.ok = all(oks)
+        self.error = err
+        if not self.ok:
+            self.close()
+
+    def close(self):
+        for ptr in self.opened:
+            try:
+                self.ctx.dist_peer_close(ptr)
+            except Exception:
+                pass
+        self.opened = []
+
+
+def _bucket_exchange(ctx, rank, world, nbpr, rcap, group):
+    """the exchange object kept ON the context (closed with it), re-created collectively when the geometry grows"""
+    bx = getattr(ctx, "_bucket_exchange", None)
+    if bx is not None and bx.world == world and bx.ok:
+        return bx
+    bx = BucketExchange(ctx, rank, world, nbpr, rcap, group)
+    ctx._bucket_exchange = bx
+    return bx
+
+
+def build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint=0, group=None, _retry=0):
+    """One step of the bucketed multi-GPU path on this rank.  d_reads / d_off: CUDA tensors.  The caller's current
+    torch stream must be the ctx stream (collectives and kernels are ordered on it).  Returns (stats, info), or None
+    when the ranks have no peer access to each other (the caller then takes the key exchange)."""
+    import time
+    import torch
+    import torch.distributed as dist
+    dev = d_reads.device
+    t0 = time.perf_counter()
+    bx = getattr(ctx, "_bucket_exchange", None)
+    if bx is None or bx.world != world:
+        nbpr, rcap = plan_buckets(n_bases, l, world, distinct_hint)
+        bx = _bucket_exchange(ctx, rank, world, nbpr, rcap, group)
+    if not bx.ok:
+        return None
+    which = bx.phase & 1
+    bx.phase += 1
+    words = _buffer("bkt_words", 8, dev)
+    ctx.bkt_scatter(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, rank, world, bx.nb_per_rank, bx.rcap, bx.areas[which],
+                    d_out=words.data_ptr())
+    # flags + largest region + wanted geometry: MAX over ranks.  The collective is also the barrier after which every
+    # rank's peer stores are complete (each rank's scatter precedes its contribution on its stream).
+    want = getattr(ctx, "_bucket_want", 0)
+    msg = torch.stack([words[2], words[3], torch.tensor(want, dtype=torch.int64, device=dev)])
+    dist.all_reduce(msg, op=dist.ReduceOp.MAX, group=group)
+    host = torch.cat([words[:2], msg]).cpu().numpy()   # the one host round trip between scatter and build
+    t1 = time.perf_counter()
+    n_l, n_k, flags, max_region, want_all = (int(x) for x in host)
+    if (flags & 0x10) or (want_all and (want_all > 2 * bx.nb_per_rank or 2 * want_all < bx.nb_per_rank)):
+        # collective knowledge (everyone sees the same reduced words): re-plan and redo this step
+        if _retry >= 3:
+            raise RuntimeError("bucketed exchange: the region capacity did not settle")
+        nbpr = want_all if want_all else bx.nb_per_rank
+        rcap = int(max_region * bx.nb_per_rank / nbpr * 1.25) + 64
+        bx.close()
+        bx.ok = False
+        ctx._bucket_exchange = None
+        ctx._bucket_want = 0
+        bx = _bucket_exchange(ctx, rank, world, nbpr, rcap, group)
+        if not bx.ok:
+            return None
+        return build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint, group, _retry + 1)
+    st = ctx.bkt_build(bx.local[which], l, rank, world, bx.nb_per_rank, bx.rcap, distinct_hint)
+    t2 = time.perf_counter()
+    # geometry for the next steps from what was counted (reported at the next exchange, adopted by all ranks together)
+    cap = int(os.environ.get("EULER_B200_BKT_CAP", BKT_CAP))
+    ctx._bucket_want = int((st.distinct_lmers + 1) // 2 * 1.06 / (0.45 * cap)) + 1
+    rec_bytes = 16
+    info = {"n_lmer_windows": n_l, "n_kmer_windows": n_k, "sent_keys": 0, "recv_keys": 0,
+            "exchange_bytes": int(rec_bytes * max_region * bx.nb_per_rank * (world - 1)),   # upper bound: largest region x regions
+            "exact_fallback": False, "transport": "16-byte minimizer-run records stored into the owners' bucket regions over NVLink (CUDA IPC)",
+            "geometry": {"nb_per_rank": bx.nb_per_rank, "rcap": bx.rcap, "max_region": max_region},
+            "phase_ms": {"partition+exchange": 1e3 * (t1 - t0), "build": 1e3 * (t2 - t1), "scatter_kernel": float(st.ms_count),
+                         "build_kernel": float(st.ms_build_kernel)}}
+    return st, info
+
+
+def emulate_partitioned_bucketed(ctx, shards, l, world, nb_per_rank=None, rcap=None):
+    """Single-process emulation of `world` ranks on one GPU (tests) through the entry points the production path
+    uses (euler_bkt_scatter with one area per destination, euler_bkt_build per area).  Same return value as
+    emulate_partitioned."""
+    import torch
+    import _native as N
+    n_max = max(int(off[-1]) for _, off in shards) if shards else 0
+    a, b = plan_buckets(max(n_max, 1), l, world)
+    nbpr, rcap = nb_per_rank or a, rcap or b
+    nbytes = nbpr * world * rcap * 16 + nbpr * world * 4 + 256
+    areas = [torch.zeros(nbytes // 8 + 1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    ptrs = [t.data_ptr() for t in areas]
+    windows = []
+    for r, (buf, off) in enumerate(shards):
+        d_buf = torch.from_numpy(np.ascontiguousarray(buf)).cuda() if len(buf) else torch.zeros(16, dtype=torch.uint8, device="cuda")
+        d_off = torch.from_numpy(np.ascontiguousarray(off).astype(np.int64)).cuda()
+        out = ctx.bkt_scatter(d_buf.data_ptr(), d_off.data_ptr(), len(off) - 1, int(off[-1]), l, r, world, nbpr, rcap, ptrs)
+        assert not (int(out[2]) & 0x10), "region overflow in the emulation: raise rcap"
+        windows.append((int(out[0]), int(out[1])))
+    ctx.sync()
+    res = []
+    for d in range(world):
+        st = ctx.bkt_build(ptrs[d], l, d, world, nbpr, rcap, 0)
+        names = ("LMER_KEYS", "LMER_VALUES", "LMER_OFFSETS", "KMER_KEYS", "LCOUNT", "ECOUNT", "LSTART", "ESTART", "EV", "EDGE_V1", "EDGE_V2")
+        art = {name: ctx.download(getattr(N, "ART_" + name)) for name in names}
+        art["stats"] = st.as_dict()
+        art["recv_keys"] = 0
+        res.append(art)
+    return res, windows
 
 
 def emulate_partitioned(ctx, shards, l, world):

@@ -79,15 +79,15 @@ d_off = torch.arange(R + 1, dtype=torch.int64, device="cuda") * L
 ctx.sync()
 for mode in ("1", "0"):
     os.environ["EULER_B200_BUCKETED"] = mode
-    for logcap in ((11, 12, 10) if mode == "1" else (0,)):
+    for logcap in ((1792, 2048, 1280, 1024, 2560) if mode == "1" else (0,)):
         if logcap:
-            os.environ["EULER_B200_BKT_LOGCAP"] = str(logcap)
-        for hint in (G, 0):
+            os.environ["EULER_B200_BKT_CAP"] = str(logcap)
+        for hint in (G,):
             ts = []
             for it in range(6):
                 t0 = time.perf_counter()
                 st = ctx.run_dev(d_reads.data_ptr(), d_off.data_ptr(), R, R * L, l, 0, hint)
                 ts.append(1e3 * (time.perf_counter() - t0))
-            print("bucketed=%s logcap=%d hint=%d: path=%d nb=%d retries=%d maxrec=%d U=%d V=%d E=%d | ms total %.3f part %.3f build %.3f count %.3f graph %.3f | wall %s"
+            print("bucketed=%s cap=%d hint=%d: path=%d nb=%d retries=%d maxrec=%d U=%d V=%d E=%d | ms total %.3f part %.3f build %.3f count %.3f graph %.3f | wall %s"
                   % (mode, logcap, hint, st.path, st.n_buckets, st.retries, st.bucket_records, st.distinct_lmers, st.distinct_kmers, st.edge_count,
                      st.ms_total, st.ms_count_kernel, st.ms_build_kernel, st.ms_count, st.ms_graph, " ".join("%.2f" % t for t in ts)))

@@ -125,3 +125,85 @@ def test_assembler_driver_splits_files_at_record_boundaries():
     assert b"".join(fa[a:b] for a, b in rs) == fa and all(fa[a:a + 1] in (b">", b"A", b"") for a, _ in rs)
     assert split_records(b"", 3, 1) == [(0, 0)] * 3
     assert detect_format("x.fq", b"") == 2 and detect_format("x.fasta", b"") == 1 and detect_format("x.txt", b"@r") == 2
+
+
+class _FakeCtx:
+    """stands in for _native.Context in the transport handshakes (no GPU): allocation / IPC opens succeed or fail on demand"""
+
+    def __init__(self, rank, fail_alloc=False, fail_open=False):
+        self.rank, self.fail_alloc, self.fail_open, self.closed = rank, fail_alloc, fail_open, []
+
+    def bkt_area_alloc(self, which, nbpr, world, rcap):
+        if self.fail_alloc:
+            raise RuntimeError("out of memory (injected)")
+        return 0x1000 * (self.rank + 1) + which, bytes([self.rank, which]) * 32
+
+    def dist_recv_alloc(self, nkeys):
+        if self.fail_alloc:
+            raise RuntimeError("out of memory (injected)")
+        return 0x2000 * (self.rank + 1), bytes([self.rank]) * 64
+
+    def dist_peer_open(self, handle):
+        if self.fail_open:
+            raise RuntimeError("no peer access (injected)")
+        return 0x9000 + handle[0] * 16 + (handle[1] if handle[1] < 2 else 0)
+
+    def dist_peer_close(self, ptr):
+        self.closed.append(ptr)
+
+
+def _handshake_worker(rank, world, port, q, mode):
+    sys.path.insert(0, os.path.join(ROOT, "pycuda-euler_b200"))
+    import torch.distributed as dist
+    from eulercuda.dist import BucketExchange, _peer_exchange
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = {}
+        # one rank fails (allocation or IPC open): EVERY rank must see the exchange as unusable and nobody may hang
+        ctx = _FakeCtx(rank, fail_alloc=(mode == "alloc" and rank == 1), fail_open=(mode == "open" and rank == 0))
+        bx = BucketExchange(ctx, rank, world, 10 + rank, 100 - rank)
+        out["bucket_ok"] = bx.ok
+        out["geometry"] = (bx.nb_per_rank, bx.rcap)
+        px = _peer_exchange(ctx, rank, world, 64 + 2 * rank, None)
+        out["peer"] = px is not None
+        out["peer_again"] = _peer_exchange(ctx, rank, world, 64, None) is not None   # remembered, no second handshake
+        if px is not None:
+            out["seg_cap"] = px.seg_cap
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode,port", [("ok", 29621), ("alloc", 29622), ("open", 29623)])
+def test_transport_is_agreed_collectively(mode, port):
+    """a rank whose allocation / IPC open fails must not leave the others on the peer path (different
+    collectives -> hang or a silently wrong table).  Both exchanges report success collectively."""
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_handshake_worker, args=(r, world, port, q, mode)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        assert res[r]["bucket_ok"] == (mode == "ok")
+        assert res[r]["peer"] == (mode == "ok") and res[r]["peer_again"] == res[r]["peer"]
+        assert res[r]["geometry"] == (11, 100)          # the maximum of the proposals, the same on every rank
+    if mode == "ok":
+        assert res[0]["seg_cap"] == res[1]["seg_cap"] == 66
+
+
+def test_plan_buckets_pure():
+    sys.path.insert(0, os.path.join(ROOT, "pycuda-euler_b200"))
+    from eulercuda.dist import plan_buckets
+    nb1, rc1 = plan_buckets(138_000_000, 32, 1, 4_600_000, cap=1792)
+    assert 5000 < nb1 < 7000 and rc1 * nb1 * 16 < 2 * 10 ** 9
+    nb8, rc8 = plan_buckets(138_000_000, 32, 8, 5_290_000, cap=1792)
+    assert rc8 < rc1 and nb8 >= nb1
+    assert plan_buckets(0, 10, 2) == (1, 64)

@@ -32,16 +32,22 @@ def canon_np(x, k):
     return np.array([min(int(v), oracle.revcomp(int(v), k)) for v in x], dtype=np.uint64)
 
 
+@pytest.mark.parametrize("impl", ["records", "keys"])   # records: the bucketed form (csrc/bucket.cuh); keys: the round-1 key exchange
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 @pytest.mark.parametrize("l", [12, 22, 32])   # 22 and 32 use the rolling-minimizer kernels, 12 the generic one
-def test_partitioned_graph_equals_oracle(ctx, world, l):
-    from eulercuda.dist import emulate_partitioned
+def test_partitioned_graph_equals_oracle(ctx, world, l, impl):
+    from eulercuda.dist import emulate_partitioned, emulate_partitioned_bucketed
     reads = random_reads(21, 600, genome_len=5000) + ["A" * 70, "ACGT" * 12]
     k = l - 1
     shards = []
     for r in range(world):
-        shards.append(oracle.pack_reads(reads[r::world]))
-    parts, windows = emulate_partitioned(ctx, shards, l, world)
+        shards.append(oracle.pack_reads(reads[r::world] if world < 8 else reads[r * 97 % len(reads)::world]))
+    if world == 8:   # uneven shards (one rank has nothing): region counts of an idle source must read as zero
+        shards = [oracle.pack_reads(reads[r::7]) for r in range(7)] + [oracle.pack_reads([])]
+    if impl == "records":
+        parts, windows = emulate_partitioned_bucketed(ctx, shards, l, world, nb_per_rank=5 if world != 3 else None)
+    else:
+        parts, windows = emulate_partitioned(ctx, shards, l, world)
     buf, off = oracle.pack_reads(reads)
     g = oracle.graph_build(buf, off, l, expand=False)
     assert sum(w[0] for w in windows) * 2 == g.ne
