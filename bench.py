@@ -162,7 +162,8 @@ def cpu_rate(wl, G1, procs, want="auto"):
     fn = (lambda G: reference_build_seconds(wl, G, procs)) if use_ref else (lambda G: port_build_seconds(wl, G))
     t1, n1, _ = fn(G1)
     t2, n2, _ = fn(2 * G1)
-    slope = (n2 - n1) / max(t2 - t1, 1e-9)
+    # slope between the two sizes; a sample too small to separate them (timer noise) falls back to the larger sample's raw rate
+    slope = (n2 - n1) / (t2 - t1) if t2 > 1.25 * t1 else n2 / t2
     return {"value": slope, "unit": UNIT, "cores": procs if use_ref else int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)),
             "kind": "reference" if use_ref else "port",
             "sample": "%d x data sets of %d bp and %d bp genomes from the workload's generator (%d / %d k-mer windows, %.2f s / %.2f s); "
@@ -204,6 +205,176 @@ def run_reference(args, wl, rank, world):
     print(json.dumps(line))
 
 
+def roofline_record(st, ms_part, ms_build, ms_step, l, workload, world):
+    """The dominant kernel against the measured HBM peak.  Algorithmic bytes:
+    A = B + N_l (w+8) + U_l (w+16) + U_k (2w+84).  The partition kernel reads every base once (B); the per-bucket
+    build kernel does the table touches and writes every artefact (the other three terms)."""
+    peak, peak_src = measured_peak_gbs()
+    w = 16 if l > 32 else 8
+    B, Nl, Ul, Uk = st.n_bases, st.n_lmer_windows, st.distinct_lmers, st.distinct_kmers
+    a_part, a_build = B, Nl * (w + 8) + Ul * (w + 16) + Uk * (2 * w + 84)
+    a_path = a_part + a_build
+    if st.path == 1:
+        name, a_kernel, t = ("bkt_build_kernel", a_build, ms_build) if ms_build >= ms_part else ("bkt_partition_kernel", a_part, ms_part)
+    else:   # round-1 global-table path: the fused encode + count kernel (first two terms)
+        name, a_kernel, t = ("count_compact_kernel" if l <= 32 else "wide_count_tiled_kernel"), B + Nl * (w + 8), ms_part
+    achieved = a_kernel / (t * 1e-3) / 1e9 if t > 0 else 0.0
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")
+    if os.path.exists(tfile) and world == 1:
+        try:
+            with open(tfile) as f:
+                rec = json.load(f).get(name)
+            if rec and rec.get("workload") == workload:   # only for the kernel and workload the capture was taken on
+                traffic = rec.get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": a_kernel,
+            "path_algorithmic_bytes": a_path, "path_frac": a_path / (ms_step * 1e-3) / 1e9 / peak,
+            "kernels_ms": {"bkt_partition_kernel": ms_part, "bkt_build_kernel": ms_build} if st.path == 1 else {"count_kernel": ms_part}}
+
+
+class Runner:
+    """One rank of the benchmark: device buffers of a workload and the step function (single GPU: the resident
+    pipeline; N > 1: the partitioned path of eulercuda/dist.py)."""
+
+    def __init__(self, ctx, stream, rank, world, dist):
+        self.ctx, self.stream, self.rank, self.world, self.dist = ctx, stream, rank, world, dist
+
+    def barrier(self):
+        import torch
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def load(self, wl, strong, hint_mode="genome"):
+        import torch
+        L = wl["L"]
+        world, rank = self.world, self.rank
+        self.wl, self.l = wl, wl["k"] + 1
+        self.G = wl["G"] if (strong or world == 1) else wl["G"] * world
+        R_all = -(-wl["G"] * wl["cov"] // L)
+        self.R = -(-R_all // world) if strong else R_all
+        first = rank * self.R
+        self.d_reads = torch.empty(self.R * L, dtype=torch.uint8, device="cuda")
+        self.ctx.synth_reads_dev(self.d_reads.data_ptr(), self.G, L, wl["err_ppm"], first, self.R)
+        self.d_off = torch.arange(self.R + 1, dtype=torch.int64, device="cuda") * L
+        self.ctx.sync()
+        torch.cuda.synchronize()
+        # a user knows the genome size: error-free reads have ~G distinct canonical l-mers, of which a rank holds
+        # ~1.15 / world (l-mers at bucket borders are held twice).  With sequencing errors nothing is known: 0.
+        if wl["err_ppm"] == 0 and hint_mode == "genome":
+            self.hint = wl["G"] if world == 1 else int(self.G / world * 1.15)
+        else:
+            self.hint = 0
+
+    def step(self, hint=None):
+        import torch
+        hint = self.hint if hint is None else hint
+        n_bases = self.R * self.wl["L"]
+        if self.world == 1:
+            return self.ctx.run_dev(self.d_reads.data_ptr(), self.d_off.data_ptr(), self.R, n_bases, self.l, 0, hint), None
+        from eulercuda.dist import build_partitioned
+        with torch.cuda.stream(self.stream):
+            return build_partitioned(self.ctx, self.d_reads, self.d_off, self.R, n_bases, self.l, self.rank, self.world, hint)
+
+    def measure(self, steps, warmup, hint=None):
+        """-> dict: ms per step (CUDA events on the ctx stream around the K steps, max over ranks), stage times, counts"""
+        import torch
+        st = info = None
+        for _ in range(warmup):
+            st, info = self.step(hint)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        part_ms = build_ms = graph_ms = 0.0
+        launches, per_step = 0, []
+        t0 = time.perf_counter()
+        e0.record(self.stream)
+        for _ in range(steps):
+            t_s = time.perf_counter()
+            st, info = self.step(hint)
+            per_step.append(st.ms_total if self.world == 1 else 1e3 * (time.perf_counter() - t_s))
+            part_ms += st.ms_count_kernel if self.world == 1 else st.ms_count
+            build_ms += st.ms_build_kernel
+            graph_ms += st.ms_graph
+            launches += st.kernel_launches + (3 if self.world > 1 else 0)   # + mark_starts, partition, push_counts
+        e1.record(self.stream)
+        self.barrier()
+        wall = 1e3 * (time.perf_counter() - t0) / steps
+        ms = e0.elapsed_time(e1) / steps
+        if self.world > 1:
+            st.n_kmer_windows, st.n_lmer_windows, st.n_bases = info["n_kmer_windows"], info["n_lmer_windows"], self.R * self.wl["L"]
+        vals = torch.tensor([ms, part_ms / steps, build_ms / steps, wall], dtype=torch.float64, device="cuda")
+        tot = torch.tensor([float(st.n_kmer_windows), float(launches)], dtype=torch.float64, device="cuda")
+        if self.dist is not None:
+            self.dist.all_reduce(vals, op=self.dist.ReduceOp.MAX)
+            self.dist.all_reduce(tot, op=self.dist.ReduceOp.SUM)
+        ms_max, part_max, build_max, wall_max = (float(x) for x in vals.tolist())
+        nk_total, launches_total = (float(x) for x in tot.tolist())
+        return {"st": st, "info": info, "ms": ms_max, "part_ms": part_max, "build_ms": build_max, "graph_ms": graph_ms / steps,
+                "wall_ms": wall_max, "per_step": per_step, "nk_total": nk_total, "launches": int(launches_total)}
+
+    def free(self):
+        self.d_reads = self.d_off = None
+
+
+def parity_check_partitioned(runner):
+    """N > 1: the PRODUCTION partitioned path (peer stores + per-rank build, uneven shards) against the single-GPU
+    pipeline on the same reads, before anything is timed: sum of multiplicities, number of distinct both-strand
+    l-mers, number of vertices and a checksum sum(key * multiplicity) mod 2^64 over the per-rank edge tables must
+    equal the single-GPU values (every both-strand l-mer is homed on exactly one rank)."""
+    import numpy as np
+    import torch
+    import _native as N
+    from eulercuda.dist import build_partitioned
+    ctx, rank, world, dist = runner.ctx, runner.rank, runner.world, runner.dist
+    wl = dict(WORKLOADS["small_smoke"])
+    L, l = wl["L"], wl["k"] + 1
+    R_all = wl["G"] * wl["cov"] // L
+    # uneven shards: rank r takes a slice proportional to r + 1
+    cuts = [R_all * (r * (r + 1) // 2) // (world * (world + 1) // 2) for r in range(world + 1)]
+    lo, hi = cuts[rank], cuts[rank + 1]
+    n = hi - lo
+    d_reads = torch.empty(max(n, 1) * L, dtype=torch.uint8, device="cuda")
+    if n:
+        ctx.synth_reads_dev(d_reads.data_ptr(), wl["G"], L, wl["err_ppm"], lo, n)
+    d_off = torch.arange(n + 1, dtype=torch.int64, device="cuda") * L
+    ctx.sync()
+
+    def table_sums():
+        lk = ctx.download(N.ART_LMER_KEYS)
+        lv = ctx.download(N.ART_LMER_VALUES).astype(np.uint64)
+        return [int(lv.sum()), int(lk.size), int(ctx.download(N.ART_KMER_KEYS).size), int((lk * lv).sum(dtype=np.uint64))]
+
+    res = {"ok": False}
+    try:
+        with torch.cuda.stream(runner.stream):
+            for _ in range(2):   # twice: the second step runs on the other receive area with learned capacities
+                st, info = build_partitioned(ctx, d_reads, d_off, n, n * L, l, rank, world, 0)
+        mine = table_sums()
+        t = torch.tensor([x & 0x7fffffffffffffff for x in mine[:3]] + [mine[3] & 0xffffffff, mine[3] >> 32], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        got = t.tolist()
+        chk = (got[3] + (got[4] << 32)) & 0xffffffffffffffff
+        if rank == 0:
+            d_all = torch.empty(R_all * L, dtype=torch.uint8, device="cuda")
+            ctx.synth_reads_dev(d_all.data_ptr(), wl["G"], L, wl["err_ppm"], 0, R_all)
+            d_off_all = torch.arange(R_all + 1, dtype=torch.int64, device="cuda") * L
+            ctx.sync()
+            ctx.run_dev(d_all.data_ptr(), d_off_all.data_ptr(), R_all, R_all * L, l, 0, 0)
+            want = table_sums()
+            res = {"ok": got[:3] == want[:3] and chk == want[3], "path": info["transport"], "workload": "small_smoke, shards ~ rank + 1",
+                   "edges": got[0], "distinct_lmers": got[1], "vertices": got[2], "checksum": "%016x" % chk,
+                   "single_gpu": {"edges": want[0], "distinct_lmers": want[1], "vertices": want[2], "checksum": "%016x" % want[3]}}
+    except Exception as e:   # reported, and fatal below
+        res = {"ok": False, "error": "%s: %s" % (type(e).__name__, e)}
+    flag = torch.tensor([1 if (rank != 0 or res["ok"]) and "error" not in res else 0], dtype=torch.int64, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["ok"] = bool(flag.item())
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -218,6 +389,7 @@ def main():
     ap.add_argument("--ref-genome", type=int, default=0, help="--impl reference: genome size of the smaller of the two samples")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra BASELINE configs (configs[2..4]) reported under `extra`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -227,13 +399,11 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.k:
         wl["k"] = args.k
-    wl["R"] = -(-wl["G"] * wl["cov"] // wl["L"])
 
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
         return
 
-    import numpy as np
     import torch
     import _native as N
 
@@ -249,70 +419,34 @@ def main():
     ctx = N.Context(local_rank)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
+    runner = Runner(ctx, stream, rank, world, dist)
+
+    parity = parity_check_partitioned(runner) if world > 1 else None
+    if parity is not None and not parity["ok"]:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "n_gpus": world, "parity_check": parity, "error": "the partitioned path disagrees with the single-GPU pipeline"}))
+        dist.barrier()
+        dist.destroy_process_group()
+        raise SystemExit(3)
 
     L, k, l = wl["L"], wl["k"], wl["k"] + 1
-    # Weak scaling: the genome (= the k-mer space) grows with the GPU count, every rank encodes its own
-    # R reads of the shared data set and owns 1/world of the k-mer space (hash partition, one all-to-all).
     strong = args.scaling == "strong" and world > 1
-    G = wl["G"] if strong else wl["G"] * world
-    R = -(-wl["R"] // world) if strong else wl["R"]
-    first = rank * R
-    d_reads = torch.empty(R * L, dtype=torch.uint8, device="cuda")
-    ctx.synth_reads_dev(d_reads.data_ptr(), G, L, wl["err_ppm"], first, R)
-    d_off = torch.arange(R + 1, dtype=torch.int64, device="cuda") * L
-    ctx.sync()
-    torch.cuda.synchronize()
-    # a user knows the genome size; per rank ~2/world of the canonical l-mers are incident to owned vertices
-    if wl["err_ppm"] == 0:
-        hint = wl["G"] if world == 1 else int((G / world) * 1.15)   # ~1.05 copies with minimizer ownership
-    else:
-        hint = 0
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    if world > 1:
-        from eulercuda.dist import build_partitioned
-
-    def step():
-        if world == 1:
-            return ctx.run_dev(d_reads.data_ptr(), d_off.data_ptr(), R, R * L, l, 0, hint), None
-        return build_partitioned(ctx, d_reads, d_off, R, R * L, l, rank, world, hint)
-
-    st = None
-    for _ in range(args.warmup):
-        st, info = step()
+    runner.load(wl, strong)
+    R, G, hint = runner.R, runner.G, runner.hint
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms, graph_ms, launches = 0.0, 0.0, 0
-    per_step = []   # the library's own CUDA-event time of each step (N = 1) / host wall time of each step (N > 1)
-    t_wall0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(args.steps):
-        t_s = time.perf_counter()
-        st, info = step()
-        per_step.append(st.ms_total if world == 1 else 1e3 * (time.perf_counter() - t_s))
-        kern_ms += st.ms_count_kernel
-        graph_ms += st.ms_graph
-        launches += st.kernel_launches + (3 if world > 1 else 0)   # + mark_starts, count pass, scatter pass
-    e1.record(stream)
-    barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t_wall0) / args.steps
-    # the partitioned step synchronises the host around the collective: wall clock is the honest time there
-    ms = e0.elapsed_time(e1) / args.steps if world == 1 else wall_ms
+    m = runner.measure(args.steps, args.warmup)
     clocks = sampler.result()
-    kern_ms /= args.steps
-    graph_ms /= args.steps
-    if world > 1:
-        st.n_kmer_windows, st.n_lmer_windows, st.n_bases = info["n_kmer_windows"], info["n_lmer_windows"], R * L
+    st, info, ms_max = m["st"], m["info"], m["ms"]
+    nohint = None
+    if world == 1 and hint:   # the same steady state without the genome-size hint (capacities learned from the previous run)
+        m0 = runner.measure(max(3, args.steps // 4), 2, hint=0)
+        nohint = {"ms_per_step": m0["ms"], "value": m0["nk_total"] / (m0["ms"] * 1e-3)}
 
     # ---- e2e: host buffers through the reference-facing C-ABI call, copies inside the timed region
     e2e = None
     if not args.no_e2e and world == 1:
+        d_reads, d_off = runner.d_reads, runner.d_off
         h_reads = torch.empty(R * L, dtype=torch.uint8, pin_memory=True)
         h_reads.copy_(d_reads)
         h_off = torch.empty(R + 1, dtype=torch.int64, pin_memory=True)
@@ -333,14 +467,15 @@ def main():
 
         for _ in range(2):
             e2e_step()
-        barrier()
+        runner.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
         d2h = 0
         for _ in range(args.steps):
             s2, d2h = e2e_step()
         e1.record(stream)
-        barrier()
+        runner.barrier()
         e2e_wall = 1e3 * (time.perf_counter() - t0) / args.steps
         serial_ms = max(e0.elapsed_time(e1) / args.steps, e2e_wall)  # the call returns synchronously: wall is the truth
         # Two contexts (two streams, two host threads) alternate steps, so the PCIe copies of one step
@@ -360,7 +495,7 @@ def main():
             except Exception as exc:   # surfaced below: a failed step must not look like a fast one
                 errs.append(exc)
 
-        barrier()
+        runner.barrier()
         th = [threading.Thread(target=worker, args=(ctx, h_out)), threading.Thread(target=worker, args=(ctx_b, h_out_b))]
         t0 = time.perf_counter()
         for t in th:
@@ -374,75 +509,99 @@ def main():
         ctx_b.close()
         e2e = {"ms": min(serial_ms, piped_ms), "serial_ms": serial_ms, "piped_ms": piped_ms, "h2d": int(R * L + (R + 1) * 8),
                "d2h": int(d2h)}
-
-    # ---- reduce over ranks
-    nk_local = float(st.n_kmer_windows)
-    vals = torch.tensor([ms, e2e["ms"] if e2e else 0.0, kern_ms], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([nk_local, float(launches)], dtype=torch.float64, device="cuda")
+        del h_reads, h_off, h_out, h_out_b
+    e2e_t = torch.tensor([e2e["ms"] if e2e else 0.0], dtype=torch.float64, device="cuda")
     if dist is not None:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_max, e2e_ms_max, kern_ms_max = [float(x) for x in vals.tolist()]
-    nk_total, launches_total = [float(x) for x in tot.tolist()]
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms_max = float(e2e_t.item())
+
+    # ---- the other BASELINE configs, reported under `extra` (every rank takes part; rank 0 prints)
+    extra = []
+    if not args.no_extra and args.workload == DEFAULT_WORKLOAD and args.scaling == "weak" and not args.k:
+        plan = []
+        if world == 1:
+            # configs[3] per-GPU share: 1/8 of the 1 Gbp genome at 30x on ONE GPU, the N = 1 point of the ">= 6x at 8 GPUs" target
+            plan.append(("1Gbp_150bp_30x_k31", dict(WORKLOADS["1Gbp_150bp_30x_k31"], G=125_000_000), False, "1/8 of configs[3] (125 Mbp, 150 bp, 30x) on one GPU"))
+        if world >= 2:
+            plan.append(("100Mbp_150bp_40x_1pct_k31", dict(WORKLOADS["100Mbp_150bp_40x_1pct_k31"]), True, "configs[2], strong scaling"))
+        if world == 8:
+            plan.append(("1Gbp_150bp_30x_k31", dict(WORKLOADS["1Gbp_150bp_30x_k31"]), True, "configs[3], strong scaling"))
+        for name, xwl, xstrong, note in plan:
+            rec = {"workload": name, "note": note, "n_gpus": world, "scaling": "strong" if xstrong else "single"}
+            try:
+                runner.free()
+                torch.cuda.empty_cache()
+                runner.load(xwl, xstrong)
+                xs = ClockSampler(local_rank)
+                xs.start()
+                xm = runner.measure(3, 2)
+                rec.update({"value": xm["nk_total"] / (xm["ms"] * 1e-3), "unit": UNIT, "ms_per_step": xm["ms"], "steps": 3, "warmup": 2,
+                            "genome_bp": xwl["G"], "read_len": xwl["L"], "coverage": xwl["cov"], "err_ppm": xwl["err_ppm"], "k": xwl["k"],
+                            "counts": {"n_kmer_windows": int(xm["nk_total"]), "distinct_lmers_rank0": int(xm["st"].distinct_lmers),
+                                       "distinct_kmers_rank0": int(xm["st"].distinct_kmers), "edges_rank0": int(xm["st"].edge_count)},
+                            "roofline": roofline_record(xm["st"], xm["part_ms"], xm["build_ms"], xm["ms"], xwl["k"] + 1, name, world),
+                            "clocks": xs.result()})
+                if xm["info"]:
+                    rec["dist"] = {kk: xm["info"][kk] for kk in ("exchange_bytes", "transport", "phase_ms", "geometry") if kk in xm["info"]}
+            except Exception as e:
+                rec["error"] = "%s: %s" % (type(e).__name__, e)
+            extra.append(rec)
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        a_kernel, a_path = algorithmic_bytes(st, 16 if l > 32 else 8)
-        achieved = a_kernel / (kern_ms_max * 1e-3) / 1e9
-        traffic = None
-        tfile = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
-        if os.path.exists(tfile) and args.workload == DEFAULT_WORKLOAD:
-            try:
-                with open(tfile) as f:
-                    traffic = json.load(f).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        roof = roofline_record(st, m["part_ms"], m["build_ms"], ms_max, l, args.workload, world)
+        per_step = m["per_step"]
         line = {
-            "metric": METRIC, "value": nk_total / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": m["nk_total"] / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": "u64" if l <= 32 else "u128", "data": "synthetic",
             "config": {
                 "workload": args.workload, "genome_bp": wl["G"], "read_len": L, "coverage": wl["cov"], "err_ppm": wl["err_ppm"],
                 "k": k, "reads_per_gpu": R, "bases_per_gpu": R * L,
                 "parallelism": "1 GPU" if world == 1 else
-                "%d GPUs: reads sharded, k-mer space partitioned by the minimizer of each vertex, one exchange of canonical l-mer keys (see dist.transport)" % world,
+                "%d GPUs: reads sharded, k-mer space partitioned by the minimizer of each vertex, one exchange (see dist.transport)" % world,
                 "genome_bp_total": G,
-                "l2": "inputs (%d MB ASCII) + table (%d MB) exceed the 126 MB L2; the table is re-initialised every step"
-                      % (R * L // 10 ** 6, st.lmer_table_capacity * 12 // 10 ** 6),
-                "distinct_hint": hint, "ids": "slot order (canonical-id sort not in the timed region)",
-                "timing": "CUDA events on the library's stream around the K steps" if world == 1 else
-                          "host clock around the K steps, barrier + device synchronize on both sides, max over ranks "
-                          "(every step synchronises with the host at the count exchange, so device events see the same interval)",
+                "l2": "inputs (%d MB ASCII) and the record regions written / re-read every step exceed the 126 MB L2" % (R * L // 10 ** 6),
+                "distinct_hint": hint, "ids": "bucket order (canonical-id sort not in the timed region)",
+                "path": "minimizer-bucketed (partition pass + per-bucket shared-memory build)" if st.path == 1 else "global table (round 1)",
+                "buckets": int(st.n_buckets),
+                "timing": "CUDA events on the library's stream around the K steps, max over ranks",
             },
             "counts": {"n_kmer_windows": int(st.n_kmer_windows), "n_lmer_windows": int(st.n_lmer_windows),
                        "distinct_lmers": int(st.distinct_lmers), "distinct_kmers": int(st.distinct_kmers),
-                       "edges": int(st.edge_count), "lmer_table_capacity": int(st.lmer_table_capacity),
-                       "retries": int(st.retries)},
-            "stage_ms": {"count_kernel": kern_ms_max, "graph": graph_ms, "step_wall": wall_ms,
+                       "edges": int(st.edge_count), "retries": int(st.retries)},
+            "stage_ms": {"partition_kernel": m["part_ms"], "build_kernel": m["build_ms"], "step_wall": m["wall_ms"],
                          "step_median": sorted(per_step)[len(per_step) // 2], "step_best": min(per_step)},
-            "roofline": {"bound": "hbm", "kernel": ("count_compact_kernel" if l <= 32 else "wide_count_kernel") if world == 1 else
-                         ("dist_count_keys_kernel" if l <= 32 else "wide_count_keys_kernel") + " (one launch per source rank)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": a_kernel,
-                         "path_algorithmic_bytes": a_path,
-                         "path_frac": a_path / (ms_max * 1e-3) / 1e9 / peak},
+            "roofline": roof,
             "clocks": clocks,
-            "gpu_launches": int(launches_total),
+            "gpu_launches": m["launches"],
         }
+        if nohint:
+            line["no_hint"] = nohint
+        if parity is not None:
+            line["parity_check"] = parity
         if world > 1 and info:
-            line["dist"] = {k: info[k] for k in ("sent_keys", "recv_keys", "exchange_bytes", "exact_fallback", "transport", "phase_ms")}
+            line["dist"] = {kk: info[kk] for kk in ("exchange_bytes", "exact_fallback", "transport", "phase_ms", "geometry") if kk in info}
         if e2e:
-            line["e2e"] = {"value": nk_total / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
+            line["e2e"] = {"value": m["nk_total"] / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                            "api": "euler_pipeline_run_host + euler_pipeline_download (compressed graph)",
                            "serial_ms_per_step": e2e["serial_ms"], "pipelined_ms_per_step": e2e["piped_ms"],
                            "pipelining": "2 contexts on 2 host threads alternate steps (copies of one overlap the kernels of the other); "
                                          "serial_ms_per_step is one context, one step at a time"}
+        if extra:
+            line["extra"] = extra
         if world == 1 and not args.no_cpu:
-            nsample = min(R, 200_000)
-            rate, dt, nk_s, _ = cpu_port_rate(wl, nsample)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": "first %d reads of the workload (%d k-mer windows), %.2f s" % (nsample, nk_s, dt)}
+            # the reference arm in a child process (no fork of a process that holds a CUDA context)
+            try:
+                import subprocess
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                                      "--workload", args.workload] + (["--k", str(args.k)] if args.k else []),
+                                     capture_output=True, text=True, timeout=600)
+                ref = json.loads(out.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = dict(ref["cpu_baseline"], code=ref["config"]["code"])
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "unavailable",
+                                        "sample": "reference arm failed: %s" % e}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

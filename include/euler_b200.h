@@ -19,7 +19,9 @@
  *   - 2-bit code: A=0 C=1 G=2 T=3 (case-insensitive), MSB-first (pyencode.py:42,64-71).  Any other
  *     byte ends the current window run (referenceAssembler.py:29); windows never cross a read
  *     boundary.  k-mer = vertex = (l-1)-mer, l-mer = edge (eulercuda.py:554 -> :450).
- *   - ids are u32, E (= sum of multiplicities) must be < 2^32 on one GPU (the reference's own limit).
+ *   - ids are u32 (vertices < 2^30, distinct l-mers < 2^32).  E (= sum of multiplicities) is reported as 64 bits; past
+ *     2^32 the compressed graph stays exact, the reference's `unsigned int` offsets are kept modulo 2^32 and the expanded
+ *     edge arrays (EULER_RUN_EXPAND_EDGES) are refused -- the reference's own limit.
  */
 #ifndef EULER_B200_H
 #define EULER_B200_H

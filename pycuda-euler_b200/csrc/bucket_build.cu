@@ -12,27 +12,41 @@
 //   B  insert the owned end vertices of every distinct l-mer into a second shared-memory table and add the
 //      multiplicity to the vertex's leaving / entering total;
 //   C  totals of (edge records, vertices, edge multiplicities) over the slots;
-//   D  decoupled look-back over the buckets in ticket order (buckets are taken largest first, so a bucket's
-//      predecessors are done when it gets here): global bases;
+//   D  decoupled look-back over the buckets in the order in which they finish counting (the output ticket is taken
+//      when a bucket's totals are ready, so no bucket ever waits for another one's work): global bases;
 //   E  vertex artefacts (the eight degree slots of a vertex are eight lookups in the bucket's own l-mer table)
 //      and edge artefacts, written in slot order with warp-row scans: consecutive lanes write consecutive ids.
-//      The suffix vertex of an edge whose suffix lives in another bucket is published / resolved through a
-//      small global table keyed by the canonical l-mer (bkt_fixup_kernel).
+//      The suffix vertex of an edge whose suffix lives in another bucket is resolved afterwards by two light passes
+//      over the records through a small global table keyed by the canonical l-mer (bkt_boundary_publish_kernel,
+//      bkt_fixup_kernel).
 #include "bucket.cuh"
 #include "kernels.h"
 
 #define BB_THREADS 256
 #define BB_WARPS (BB_THREADS / 32)
+#ifndef BB_STEPS
 #define BB_STEPS 2   // l-mers a lane rolls between two refills
+#endif
 #ifndef BB_MINB
 #define BB_MINB 4
 #endif
-#define BB_BINS 1024
+// -DBKT_TIMING: thread 0 of every block adds the clock cycles of each phase to stats[16 + phase] (development aid)
+#ifdef BKT_TIMING
+#define BB_TICK(i)                                                                      \
+    do {                                                                                \
+        if (threadIdx.x == 0) {                                                         \
+            const long long now_ = clock64();                                           \
+            atomicAdd((unsigned long long *)(a.stats + 16 + (i)), (unsigned long long)(now_ - tick_)); \
+            tick_ = now_;                                                               \
+        }                                                                               \
+    } while (0)
+#else
+#define BB_TICK(i) do { } while (0)
+#endif
 
 struct BkBuildArgs {
     const uint4 *records;
     const u32 *counts;   // [nb * nranks] records in region (bucket, source rank)
-    const u32 *order;    // ticket -> bucket (largest first)
     u32 nb, nranks, rcap, l;
     u32 cap;             // slots of each shared-memory table (a multiple of 256)
     u64 *lkeys; u32 *lvals, *loffs, *ev1, *ev2; u64 ucap;
@@ -42,13 +56,15 @@ struct BkBuildArgs {
     u64 *stats;
 };
 
-// home bucket (4 slots) of a key in a shared-memory table of nbk buckets
-__device__ __forceinline__ u32 bb_home(u64 key, u32 nbk)
+// home slot of a key in a shared-memory table of `cap` slots (linear probing, one key per slot: in shared memory a probe
+// is one 8-byte load, and the 32-byte buckets that pay off against DRAM sectors only cost compares and bank conflicts)
+__device__ __forceinline__ u32 bb_home(u64 key, u32 cap)
 {
     u32 h = (u32)key * 0x9E3779B1u + (u32)(key >> 32) * 0x85EBCA77u;
     h ^= h >> 15;
     h *= 0x2C1B3C6Du;
-    return __umulhi(h, nbk);
+    h ^= h >> 13;
+    return __umulhi(h, cap);
 }
 __device__ __forceinline__ u32 ld_vol_u32(const u32 *p)
 {
@@ -65,43 +81,40 @@ __device__ __forceinline__ u64 ld_vol_u64(const u64 *p)
 __device__ __forceinline__ void st_vol_u32(u32 *p, u32 v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_vol_u64(u64 *p, u64 v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 
-// Slots of a bucket fill in order and are never freed, so the first EMPTY slot ends a search.
+// Slots are never freed, so the first EMPTY slot ends a search.  One exit per function: with early returns the compiler
+// duplicated the caller's tail per return point and the warp ran it once per group of lanes.
 // insert: returns the slot, 0xffffffff when the table is full; first = this call claimed the slot.
-__device__ __forceinline__ u32 sm_insert(u64 *keys, u32 nbk, u64 key, bool &first)
+__device__ __forceinline__ u32 sm_insert(u64 *keys, u32 cap, u64 key, bool &first)
 {
-    u32 hb = bb_home(key, nbk);
+    u32 h = bb_home(key, cap), slot = 0xffffffffu;
     first = false;
-    for (u32 probe = 0; probe < nbk; probe++) {
-        u64 *bk = keys + 4u * hb;
-        const ulonglong2 q0 = *reinterpret_cast<const ulonglong2 *>(bk), q1 = *reinterpret_cast<const ulonglong2 *>(bk + 2);
-        if (q0.x == key) return 4u * hb;
-        if (q0.y == key) return 4u * hb + 1u;
-        if (q1.x == key) return 4u * hb + 2u;
-        if (q1.y == key) return 4u * hb + 3u;
-        u32 fe = q0.x == EULER_EMPTY_KEY ? 0u : (q0.y == EULER_EMPTY_KEY ? 1u : (q1.x == EULER_EMPTY_KEY ? 2u : (q1.y == EULER_EMPTY_KEY ? 3u : 4u)));
-        for (; fe < 4u; fe++) {   // claim the first empty slot; a slot lost to another key sends us to the next one
-            const u64 old = atomicCAS(bk + fe, EULER_EMPTY_KEY, key);
-            if (old == EULER_EMPTY_KEY) { first = true; return 4u * hb + fe; }
-            if (old == key) return 4u * hb + fe;
+    for (u32 probe = 0; probe < cap; probe++) {
+        u64 cur = keys[h];
+        if (cur == EULER_EMPTY_KEY) {
+            cur = atomicCAS(keys + h, EULER_EMPTY_KEY, key);
+            first = cur == EULER_EMPTY_KEY;
+            if (first) cur = key;
         }
-        hb = hb + 1u == nbk ? 0u : hb + 1u;
+        if (cur == key) {
+            slot = h;
+            break;
+        }
+        h = h + 1u == cap ? 0u : h + 1u;
     }
-    return 0xffffffffu;
+    return slot;
 }
-__device__ __forceinline__ u32 sm_find(const u64 *keys, u32 nbk, u64 key)
+__device__ __forceinline__ u32 sm_find(const u64 *keys, u32 cap, u64 key)
 {
-    u32 hb = bb_home(key, nbk);
-    for (u32 probe = 0; probe < nbk; probe++) {
-        const u64 *bk = keys + 4u * hb;
-        const ulonglong2 q0 = *reinterpret_cast<const ulonglong2 *>(bk), q1 = *reinterpret_cast<const ulonglong2 *>(bk + 2);
-        if (q0.x == key) return 4u * hb;
-        if (q0.y == key) return 4u * hb + 1u;
-        if (q1.x == key) return 4u * hb + 2u;
-        if (q1.y == key) return 4u * hb + 3u;
-        if (q0.x == EULER_EMPTY_KEY || q0.y == EULER_EMPTY_KEY || q1.x == EULER_EMPTY_KEY || q1.y == EULER_EMPTY_KEY) return 0xffffffffu;
-        hb = hb + 1u == nbk ? 0u : hb + 1u;
+    u32 h = bb_home(key, cap), slot = 0xffffffffu;
+    for (u32 probe = 0; probe < cap; probe++) {
+        const u64 cur = keys[h];
+        if (cur == key || cur == EULER_EMPTY_KEY) {
+            slot = cur == key ? h : 0xffffffffu;
+            break;
+        }
+        h = h + 1u == cap ? 0u : h + 1u;
     }
-    return 0xffffffffu;
+    return slot;
 }
 
 __device__ __forceinline__ u32 warp_incl_u32(u32 v, int lane)
@@ -129,13 +142,11 @@ __device__ __forceinline__ u64 warp_sum_u64(u64 v)
     return v;
 }
 
-// both-strand multiplicity of the l-mer x in the bucket's table (0 when absent)
-__device__ __forceinline__ u32 bb_bs_count(const u64 *lt_keys, const u32 *lt_cnt, u32 nbk, u64 x, u32 l)
+// both-strand multiplicity of the l-mer x (reverse complement r) in the bucket's table (0 when absent)
+__device__ __forceinline__ u32 bb_bs_count(const u64 *lt_keys, const u32 *lt_cnt, u32 cap, u64 x, u64 r)
 {
-    const u64 r = bk_revcomp(x, l);
-    const u32 slot = sm_find(lt_keys, nbk, x < r ? x : r);
-    if (slot == 0xffffffffu) return 0u;
-    const u32 n = lt_cnt[slot] & 0x3fffffffu;
+    const u32 slot = sm_find(lt_keys, cap, x < r ? x : r);
+    const u32 n = slot == 0xffffffffu ? 0u : (lt_cnt[slot] & 0x3fffffffu);
     return x == r ? 2u * n : n;
 }
 
@@ -156,21 +167,54 @@ __device__ __forceinline__ LtSlot bb_lt_slot(const u64 *lt_keys, const u32 *lt_c
     s.n = w & 0x3fffffffu;
     s.own_p = (w >> 30) & 1u;
     s.own_s = (w >> 31) & 1u;
-    s.pal = s.c == bk_revcomp(s.c, l);
+    s.pal = !(l & 1u) && s.c == bk_revcomp(s.c, l);   // only an even length can be its own reverse complement
     if (s.pal) { s.recs = s.own_p ? 1u : 0u; s.edges = s.own_p ? 2ull * s.n : 0ull; }
     else { s.recs = (s.own_p ? 1u : 0u) + (s.own_s ? 1u : 0u); s.edges = (u64)s.n * s.recs; }
     return s;
 }
 
+// Per-warp work queue in shared memory (64 entries of 16 bytes).  The per-slot phases walk table slots that are ~45 %
+// occupied, and the count phase has a rare slow path; instead of letting the idle lanes ride along, a lane with work
+// pushes it and the warp pops 32 entries at a time: every lane busy on the expensive code.
+struct WarpQueue {
+    ulonglong2 *q;   // this warp's 64 entries
+    u32 n;           // warp-uniform
+    __device__ __forceinline__ void push(bool pred, ulonglong2 v, unsigned lt_mask)
+    {
+        const unsigned m = __ballot_sync(0xffffffffu, pred);
+        if (pred) q[n + __popc(m & lt_mask)] = v;
+        n += __popc(m);
+        __syncwarp();
+    }
+    // pops 32 entries (the caller checked n >= 32)
+    __device__ __forceinline__ ulonglong2 pop32(int lane)
+    {
+        n -= 32u;
+        const ulonglong2 v = q[n + lane];
+        __syncwarp();
+        return v;
+    }
+    // the rest at the end: valid for lanes < old n
+    __device__ __forceinline__ ulonglong2 rest(int lane, bool &valid)
+    {
+        valid = (u32)lane < n;
+        const ulonglong2 v = valid ? q[lane] : make_ulonglong2(0, 0);
+        n = 0;
+        __syncwarp();
+        return v;
+    }
+};
+
 __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const BkBuildArgs a)
 {
     extern __shared__ __align__(16) unsigned char bb_smem[];
-    const u32 cap = a.cap, nbk = cap / 4;
+    const u32 cap = a.cap;
     u64 *lt_keys = (u64 *)bb_smem;
     u64 *vt_keys = lt_keys + cap;
     u32 *lt_cnt = (u32 *)(vt_keys + cap);
     u32 *vt_a = lt_cnt + cap;   // leaving total of the canonical strand, later the vertex id
     u32 *vt_b = vt_a + cap;     // entering total of the canonical strand
+    __shared__ ulonglong2 s_queue[BB_WARPS][64];
     __shared__ u64 s_wtot[BB_WARPS][4];
     __shared__ u64 s_base[2];
     __shared__ u32 s_bucket, s_fail;
@@ -180,24 +224,37 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
     const u32 l = a.l, k = l - 1;
     const u64 lmask = l >= 32 ? ~0ull : ((1ull << (2 * l)) - 1ull), kmask = lmask >> 2;
     const u32 top = 2 * (l - 1);
+    WarpQueue wq;
+    wq.q = s_queue[warp];
+    wq.n = 0;
 
-    if (tid == 0) { s_bucket = atomicAdd(a.ticket, 1u); s_fail = 0; }
+#ifdef BKT_TIMING
+    long long tick_ = clock64();
+#endif
+    if (tid == 0) { s_bucket = atomicAdd(a.ticket, 1u); s_fail = 0; }   // which bucket this block builds
     {
         const ulonglong2 e2 = make_ulonglong2(EULER_EMPTY_KEY, EULER_EMPTY_KEY);
-        for (u32 i = tid; i < cap; i += BB_THREADS) {   // lt_keys and vt_keys are adjacent: 2 * cap keys = cap pairs
-            reinterpret_cast<ulonglong2 *>(lt_keys)[i] = e2;
-        }
+        for (u32 i = tid; i < cap; i += BB_THREADS) reinterpret_cast<ulonglong2 *>(lt_keys)[i] = e2;   // lt_keys and vt_keys are adjacent
         const uint4 z = make_uint4(0, 0, 0, 0);
         for (u32 i = tid; i < 3 * cap / 4; i += BB_THREADS) reinterpret_cast<uint4 *>(lt_cnt)[i] = z;
     }
     __syncthreads();
-    const u32 ticket = s_bucket;
-    if (ticket >= a.nb) return;   // never: the grid is nb blocks
-    const u32 b = a.order ? a.order[ticket] : ticket;
+    const u32 b = s_bucket;
+    if (b >= a.nb) return;   // never: the grid is nb blocks
 
+    BB_TICK(0);
     // ---- A: count the l-mers of the bucket's records ---------------------------------------------------------
     bool fail = false;
     u32 max_region = 0;
+    // slow path of the count: a key that is not in its home bucket yet (first occurrence, or its home was full)
+    auto count_slow = [&](ulonglong2 e, bool valid) {
+        if (valid) {
+            bool first;
+            const u32 slot = sm_insert(lt_keys, cap, e.x, first);
+            if (slot == 0xffffffffu) fail = true;
+            else atomicAdd(lt_cnt + slot, first ? (1u | ((u32)e.y << 30)) : 1u);
+        }
+    };
     for (u32 src = 0; src < a.nranks; src++) {
         u32 cnt = a.counts[(u64)b * a.nranks + src];
         max_region = cnt > max_region ? cnt : max_region;
@@ -258,61 +315,83 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
             }
 #pragma unroll
             for (int st = 0; st < BB_STEPS; st++) {
-                if (left) {
+                const bool act = left != 0;
+                bool miss = false;
+                ulonglong2 e = make_ulonglong2(0, 0);
+                if (act) {
                     const u32 cc = (u32)(rem >> 62);
                     rem <<= 2;
                     f = ((f << 2) | cc) & lmask;
                     rc = (rc >> 2) | ((u64)(3u - cc) << top);
                     const bool flip = rc < f;
                     const u64 c = flip ? rc : f;
-                    // ownership of the end vertices, in the orientation the read spells
-                    const u32 own_pf = (firstl && (hdr & BK_HDR_LFF)) ? 0u : 1u;
-                    const u32 own_sf = (left == 1u && (hdr & BK_HDR_RFF)) ? 0u : 1u;
-                    const u32 own = flip ? (own_sf | (own_pf << 1)) : (own_pf | (own_sf << 1));   // bit 0: prefix(c), bit 1: suffix(c)
-                    bool first;
-                    const u32 slot = sm_insert(lt_keys, nbk, c, first);
-                    if (slot == 0xffffffffu) fail = true;
-                    else atomicAdd(lt_cnt + slot, first ? (1u | (own << 30)) : 1u);
+                    const u32 h = bb_home(c, cap);
+                    if (lt_keys[h] == c) {
+                        atomicAdd(lt_cnt + h, 1u);   // the common case: the key sits in its home slot
+                    } else {   // first occurrence, or displaced from its home: the slow path, with the ownership of the end
+                               // vertices in the orientation the read spells (bit 0: prefix(c), bit 1: suffix(c))
+                        const u32 own_pf = (firstl && (hdr & BK_HDR_LFF)) ? 0u : 1u;
+                        const u32 own_sf = (left == 1u && (hdr & BK_HDR_RFF)) ? 0u : 1u;
+                        e = make_ulonglong2(c, flip ? (own_sf | (own_pf << 1)) : (own_pf | (own_sf << 1)));
+                        miss = true;
+                    }
                     firstl = false;
                     left--;
                 }
+                wq.push(miss, e, lt_mask);
+                if (wq.n >= 32u) count_slow(wq.pop32(lane), true);
             }
         }
     }
+    {
+        bool valid;
+        const ulonglong2 e = wq.rest(lane, valid);
+        count_slow(e, valid);
+    }
     if (fail) s_fail = 1;
     __syncthreads();
+    BB_TICK(1);
 
     // per-slot passes: warp w owns slots [w * spw, (w + 1) * spw), a row = 32 consecutive slots
     const u32 spw = cap / BB_WARPS, rows = spw / 32u, wbase = warp * spw;
 
     // ---- B: owned end vertices of every distinct l-mer ---------------------------------------------------------
     if (!s_fail) {
-        for (u32 row = 0; row < rows; row++) {
-            const u32 slot = wbase + row * 32u + lane;
+        auto vertex_sides = [&](ulonglong2 e, bool valid) {
+            if (!valid) return;
+            const u32 slot = (u32)e.x;
             const u64 c = lt_keys[slot];
-            if (c == EULER_EMPTY_KEY) continue;
             const u32 w = lt_cnt[slot], n = w & 0x3fffffffu;
             const bool own_p = (w >> 30) & 1u, own_s = (w >> 31) & 1u;
-            const bool pal = c == bk_revcomp(c, l);
+            const bool pal = !(l & 1u) && c == bk_revcomp(c, l);
             const u32 m0 = pal ? 2u * n : n;
             bool first;
             if (own_p) {   // strand c leaves prefix(c) with m0
                 const u64 p = c >> 2, rp = bk_revcomp(p, k);
-                const u32 vs = sm_insert(vt_keys, nbk, p < rp ? p : rp, first);
+                const u32 vs = sm_insert(vt_keys, cap, p < rp ? p : rp, first);
                 if (vs == 0xffffffffu) fail = true;
                 else atomicAdd((p <= rp) ? vt_a + vs : vt_b + vs, m0);   // p is the canonical strand (or a palindrome): its leaving total
             }
             if (own_s && !pal) {   // strand c enters suffix(c) with n (a palindromic l-mer is covered by its prefix side)
                 const u64 s = c & kmask, rs = bk_revcomp(s, k);
-                const u32 vs = sm_insert(vt_keys, nbk, s < rs ? s : rs, first);
+                const u32 vs = sm_insert(vt_keys, cap, s < rs ? s : rs, first);
                 if (vs == 0xffffffffu) fail = true;
                 else if (s == rs) atomicAdd(vt_a + vs, n);            // palindromic vertex: one strand, leaving total == entering total
                 else atomicAdd((s < rs) ? vt_b + vs : vt_a + vs, n);   // canonical strand: entering; else the mirror = leaving of the canonical strand
             }
+        };
+        for (u32 row = 0; row < rows; row++) {
+            const u32 slot = wbase + row * 32u + lane;
+            wq.push(lt_keys[slot] != EULER_EMPTY_KEY, make_ulonglong2(slot, 0), lt_mask);
+            if (wq.n >= 32u) vertex_sides(wq.pop32(lane), true);
         }
+        bool valid;
+        const ulonglong2 e = wq.rest(lane, valid);
+        vertex_sides(e, valid);
         if (fail) s_fail = 1;
     }
     __syncthreads();
+    BB_TICK(2);
     const bool failed = s_fail != 0;
 
     // ---- C: totals per warp ----------------------------------------------------------------------------------------
@@ -326,7 +405,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
                 t_edges += s.edges;
                 const u64 v = vt_keys[slot];
                 if (v != EULER_EMPTY_KEY) {
-                    const bool palv = v == bk_revcomp(v, k);
+                    const bool palv = !(k & 1u) && v == bk_revcomp(v, k);
                     t_v += palv ? 1u : 2u;
                     t_w += palv ? (u64)vt_a[slot] : (u64)vt_a[slot] + vt_b[slot];
                 }
@@ -344,9 +423,16 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
         tot_rec += r0; tot_e += r1; tot_v += r2; tot_w += r3;
     }
     const u64 tot_uv = (tot_v << 32) | tot_rec;
+    BB_TICK(3);
 
-    // ---- D: look-back over the buckets (ticket order) --------------------------------------------------------------
+    // ---- D: look-back over the buckets, in the order in which they get HERE ------------------------------------------
+    // The output ticket is taken now, not at the start: every lower ticket belongs to a block that has already
+    // reached this point, so its totals are published (or are a few instructions away) and nobody ever waits for
+    // another block's counting.  The artefacts therefore come out in completion order of the buckets.
     if (warp == 0) {
+        u32 ticket = 0;
+        if (lane == 0) ticket = atomicAdd(a.ticket + 1, 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
         u64 pre_uv = 0, pre_e = 0;
         if (ticket == 0) {
             if (lane == 0) {
@@ -371,7 +457,8 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
                     u32 spins = 0;
                     do {
                         fl = ld_vol_u32(a.flag + idx);
-                        if (fl == 0u && ++spins > (1u << 26)) {   // a predecessor never published: give up instead of hanging the GPU
+                        if (fl == 0u) __nanosleep(64);   // leave the issue slots to the blocks that still have work
+                        if (fl == 0u && ++spins > (1u << 22)) {   // a predecessor never published: give up instead of hanging the GPU
                             atomicOr((unsigned long long *)(a.stats + 2), (unsigned long long)BKT_FLAG_INTERNAL);
                             fl = 3u;
                         }
@@ -417,6 +504,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
         }
     }
     __syncthreads();
+    BB_TICK(4);
     if (failed) return;
     const u64 ubase = s_base[0] & 0xffffffffull, vbase = s_base[0] >> 32, ebase = s_base[1];
     if (ubase + tot_rec > a.ucap || vbase + tot_v > a.vcap) {
@@ -426,32 +514,24 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
 
     // ---- E1: vertex artefacts -----------------------------------------------------------------------------------------
     {
-        u64 vcarry = vbase + off_v, wcarry = ebase + off_w;
         bool bad = false;
-        for (u32 row = 0; row < rows; row++) {
-            const u32 slot = wbase + row * 32u + lane;
-            const u64 v = vt_keys[slot];
-            const bool occ = v != EULER_EMPTY_KEY;
-            const u64 rv = occ ? bk_revcomp(v, k) : 0ull;
+        // entry: x = slot | vid << 32, y = wpos (the edge-offset prefix of the vertex)
+        auto vertex_out = [&](ulonglong2 e, bool valid) {
+            if (!valid) return;
+            const u32 slot = (u32)e.x & 0xffffu;
+            const u64 vid = e.x >> 32;
+            const u64 v = vt_keys[slot], rv = bk_revcomp(v, k);
             const bool palv = v == rv;
-            const u32 L0 = occ ? vt_a[slot] : 0u, E0 = occ ? vt_b[slot] : 0u;
-            const u32 nstr = occ ? (palv ? 1u : 2u) : 0u;
-            const u64 wsum = occ ? (palv ? (u64)L0 : (u64)L0 + E0) : 0ull;
-            const u32 vinc = warp_incl_u32(nstr, lane);
-            const u64 winc = warp_incl_u64(wsum, lane);
-            const u64 vid = vcarry + vinc - nstr, wpos = wcarry + winc - wsum;
-            vcarry += __shfl_sync(0xffffffffu, vinc, 31);
-            wcarry += __shfl_sync(0xffffffffu, winc, 31);
-            if (!occ) continue;
+            const u32 L0 = vt_a[slot], E0 = vt_b[slot];
             u32 lc[4], ec[4];
 #pragma unroll
-            for (u32 t = 0; t < 4; t++) {
-                lc[t] = bb_bs_count(lt_keys, lt_cnt, nbk, (v << 2) | t, l);
-                ec[t] = bb_bs_count(lt_keys, lt_cnt, nbk, ((u64)t << (2 * k)) | v, l);
+            for (u32 t = 0; t < 4; t++) {   // rc(v t) = comp(t) rc(v), rc(t v) = rc(v) comp(t): no bit reversal per neighbour
+                lc[t] = bb_bs_count(lt_keys, lt_cnt, cap, (v << 2) | t, ((u64)(3u - t) << (2 * k)) | rv);
+                ec[t] = bb_bs_count(lt_keys, lt_cnt, cap, ((u64)t << (2 * k)) | v, (rv << 2) | (3u - t));
             }
             const u32 ls = lc[0] + lc[1] + lc[2] + lc[3], es = ec[0] + ec[1] + ec[2] + ec[3];
             if (ls != L0 || es != (palv ? L0 : E0)) bad = true;
-            const u32 P = (u32)wpos;
+            const u32 P = (u32)e.y;
             vt_a[slot] = (u32)vid;   // the id of the canonical strand, for the edge pass
             a.vkeys[vid] = v;
             reinterpret_cast<uint4 *>(a.lcount)[vid] = make_uint4(lc[0], lc[1], lc[2], lc[3]);
@@ -472,38 +552,55 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
                 x.vid = rv; x.ep = PE; x.ecount = ls; x.lp = PL; x.lcount = es;
                 a.ev[id1] = x;
             }
+        };
+        u64 vcarry = vbase + off_v, wcarry = ebase + off_w;
+        for (u32 row = 0; row < rows; row++) {
+            const u32 slot = wbase + row * 32u + lane;
+            const u64 v = vt_keys[slot];
+            const bool occ = v != EULER_EMPTY_KEY;
+            const bool palv = occ && !(k & 1u) && v == bk_revcomp(v, k);
+            const u32 L0 = occ ? vt_a[slot] : 0u, E0 = occ ? vt_b[slot] : 0u;
+            const u32 nstr = occ ? (palv ? 1u : 2u) : 0u;
+            const u64 wsum = occ ? (palv ? (u64)L0 : (u64)L0 + E0) : 0ull;
+            const u32 vinc = warp_incl_u32(nstr, lane);
+            const u64 winc = warp_incl_u64(wsum, lane);
+            const u64 vid = vcarry + vinc - nstr, wpos = wcarry + winc - wsum;
+            vcarry += __shfl_sync(0xffffffffu, vinc, 31);
+            wcarry += __shfl_sync(0xffffffffu, winc, 31);
+            wq.push(occ, make_ulonglong2((u64)slot | (vid << 32), wpos), lt_mask);
+            if (wq.n >= 32u) vertex_out(wq.pop32(lane), true);
         }
+        bool valid;
+        const ulonglong2 e = wq.rest(lane, valid);
+        vertex_out(e, valid);
         if (bad) atomicOr((unsigned long long *)(a.stats + 2), (unsigned long long)BKT_FLAG_INTERNAL);
     }
     __syncthreads();
+    BB_TICK(5);
 
     // ---- E2: edge artefacts -------------------------------------------------------------------------------------------
     {
-        u64 rcarry = ubase + off_rec, ecarry = ebase + off_edges;
-        bool bfail = false;
-        for (u32 row = 0; row < rows; row++) {
-            const u32 slot = wbase + row * 32u + lane;
+        bool bfail = false;   // a vertex that phase B inserted is missing: cannot happen
+        // entry: x = slot | first record index << 32, y = first edge offset
+        auto edge_out = [&](ulonglong2 e, bool valid) {
+            if (!valid) return;
+            const u32 slot = (u32)e.x & 0xffffu;
+            u64 rec = e.x >> 32, eo = e.y;
             const LtSlot s = bb_lt_slot(lt_keys, lt_cnt, slot, l);
-            const u32 rinc = warp_incl_u32(s.recs, lane);
-            const u64 einc = warp_incl_u64(s.edges, lane);
-            u64 rec = rcarry + rinc - s.recs, eo = ecarry + einc - s.edges;
-            rcarry += __shfl_sync(0xffffffffu, rinc, 31);
-            ecarry += __shfl_sync(0xffffffffu, einc, 31);
-            if (!s.recs) continue;
             const u64 c = s.c, r = bk_revcomp(c, l);
             const u32 n = s.n, m0 = s.pal ? 2u * n : n;
-            const u64 p = c >> 2, sf = c & kmask, rp = bk_revcomp(p, k), rs = bk_revcomp(sf, k);
+            const u64 p = c >> 2, sf = c & kmask, rp = r & kmask, rs = r >> 2;   // rc(prefix c) = suffix(rc c), rc(suffix c) = prefix(rc c)
             u32 id_p = EULER_NO_ID, id_rp = EULER_NO_ID, id_s = EULER_NO_ID, id_rs = EULER_NO_ID;
             if (s.own_p) {
-                const u32 vs = sm_find(vt_keys, nbk, p < rp ? p : rp);
-                if (vs == 0xffffffffu) { bfail = true; continue; }   // cannot happen: inserted in B
+                const u32 vs = sm_find(vt_keys, cap, p < rp ? p : rp);
+                if (vs == 0xffffffffu) { bfail = true; return; }   // cannot happen: inserted in B
                 const u32 i0 = vt_a[vs];
                 id_p = p <= rp ? i0 : i0 + 1u;
                 id_rp = rp <= p ? i0 : i0 + 1u;
             }
             if (s.own_s) {
-                const u32 vs = sm_find(vt_keys, nbk, sf < rs ? sf : rs);
-                if (vs == 0xffffffffu) { bfail = true; continue; }
+                const u32 vs = sm_find(vt_keys, cap, sf < rs ? sf : rs);
+                if (vs == 0xffffffffu) { bfail = true; return; }
                 const u32 i0 = vt_a[vs];
                 id_s = sf <= rs ? i0 : i0 + 1u;
                 id_rs = rs <= sf ? i0 : i0 + 1u;
@@ -516,28 +613,67 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
             if (s.own_s && !s.pal) {   // strand rc(c) runs from rc(suffix c) to rc(prefix c)
                 a.lkeys[rec] = r; a.lvals[rec] = n; a.loffs[rec] = (u32)eo; a.ev1[rec] = id_rs; a.ev2[rec] = id_rp;
             }
-            if (s.own_p != s.own_s) {   // the other end vertex lives in another bucket: publish our side's id under the canonical l-mer
-                const u64 bmask = a.bcap - 1;
-                u64 h = ((c ^ (c >> 29)) * 0x9E3779B97F4A7C15ull >> 20) & bmask;
-                u32 probe = 0;
-                for (; probe < 4096; probe++) {
-                    const u64 cur = ld_vol_u64(a.bkeys + h);
-                    if (cur == c) break;
-                    if (cur == EULER_EMPTY_KEY) {
-                        const u64 old = atomicCAS((unsigned long long *)(a.bkeys + h), EULER_EMPTY_KEY, c);
-                        if (old == EULER_EMPTY_KEY || old == c) break;
-                    }
-                    h = (h + 1) & bmask;
-                }
-                if (probe == 4096) bfail = true;
-                else a.bvals[2 * h + (s.own_p ? 0 : 1)] = s.own_p ? id_rp : id_s;   // [0]: id(rc prefix) from the prefix owner, [1]: id(suffix) from the suffix owner
-            }
+        };
+        u64 rcarry = ubase + off_rec, ecarry = ebase + off_edges;
+        for (u32 row = 0; row < rows; row++) {
+            const u32 slot = wbase + row * 32u + lane;
+            const LtSlot s = bb_lt_slot(lt_keys, lt_cnt, slot, l);
+            const u32 rinc = warp_incl_u32(s.recs, lane);
+            const u64 einc = warp_incl_u64(s.edges, lane);
+            const u64 rec = rcarry + rinc - s.recs, eo = ecarry + einc - s.edges;
+            rcarry += __shfl_sync(0xffffffffu, rinc, 31);
+            ecarry += __shfl_sync(0xffffffffu, einc, 31);
+            wq.push(s.recs != 0, make_ulonglong2((u64)slot | (rec << 32), eo), lt_mask);
+            if (wq.n >= 32u) edge_out(wq.pop32(lane), true);
         }
-        if (bfail) atomicOr((unsigned long long *)(a.stats + 2), (unsigned long long)BKT_FLAG_BOUNDARY);
+        bool valid;
+        const ulonglong2 e = wq.rest(lane, valid);
+        edge_out(e, valid);
+        if (bfail) atomicOr((unsigned long long *)(a.stats + 2), (unsigned long long)BKT_FLAG_INTERNAL);
     }
+    __syncthreads();
+    BB_TICK(6);
 }
 
-// resolve the suffix vertex of the edges that cross buckets (ev2 == NO_ID after the build)
+// ---- edges that cross buckets ------------------------------------------------------------------------------------------
+// After the build, the record of strand x has ev2 == NO_ID when suffix(x) belongs to another bucket.  That bucket
+// holds the record of strand rc(x), whose ev1 is id(rc(suffix x)) -- the partner strand of the vertex we are
+// looking for -- and it is looking for the partner of OUR ev1.  Two passes over the records through a small global
+// table keyed by the canonical l-mer (value slot 0: id(rc prefix c), written from the record of strand c; slot 1:
+// id(suffix c), written from the record of strand rc(c)); no global atomic or dependent global access inside the
+// per-bucket kernel.  An l-mer whose other end lives on another RANK finds nothing and keeps NO_ID.
+__device__ __forceinline__ u64 bnd_hash(u64 c, u64 bmask) { return (((c ^ (c >> 29)) * 0x9E3779B97F4A7C15ull) >> 20) & bmask; }
+__global__ void __launch_bounds__(256) bkt_boundary_publish_kernel(const u64 *__restrict__ lkeys, const u32 *__restrict__ ev1,
+                                                                   const u32 *__restrict__ ev2, const u64 *__restrict__ d_u, u64 ucap, u32 l,
+                                                                   u64 *__restrict__ bkeys, u32 *__restrict__ bvals, u64 bcap, u64 *__restrict__ stats)
+{
+    const u64 n = *d_u < ucap ? *d_u : ucap;
+    const u64 bmask = bcap - 1;
+    const u32 k = l - 1;
+    bool bfail = false;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        if (ev2[i] != EULER_NO_ID) continue;
+        const u64 x = lkeys[i], r = bk_revcomp(x, l);
+        const u64 c = x < r ? x : r;
+        const u64 p = x >> 2, rp = bk_revcomp(p, k);
+        const u32 id = ev1[i];
+        const u32 partner = p < rp ? id + 1u : (p > rp ? id - 1u : id);   // id(rc(prefix x)): the two strands of a vertex have adjacent ids
+        u64 h = bnd_hash(c, bmask);
+        u32 probe = 0;
+        for (; probe < 4096; probe++) {
+            const u64 cur = bkeys[h];
+            if (cur == c) break;
+            if (cur == EULER_EMPTY_KEY) {
+                const u64 old = atomicCAS((unsigned long long *)(bkeys + h), EULER_EMPTY_KEY, c);
+                if (old == EULER_EMPTY_KEY || old == c) break;
+            }
+            h = (h + 1) & bmask;
+        }
+        if (probe == 4096) bfail = true;
+        else bvals[2 * h + (x == c ? 0 : 1)] = partner;
+    }
+    if (bfail) atomicOr((unsigned long long *)(stats + 2), (unsigned long long)BKT_FLAG_BOUNDARY);
+}
 __global__ void __launch_bounds__(256) bkt_fixup_kernel(const u64 *__restrict__ lkeys, u32 *__restrict__ ev2, const u64 *__restrict__ d_u,
                                                         u64 ucap, u32 l, const u64 *__restrict__ bkeys, const u32 *__restrict__ bvals,
                                                         u64 bcap)
@@ -548,7 +684,7 @@ __global__ void __launch_bounds__(256) bkt_fixup_kernel(const u64 *__restrict__ 
         if (ev2[i] != EULER_NO_ID) continue;
         const u64 x = lkeys[i], r = bk_revcomp(x, l);
         const u64 c = x < r ? x : r;
-        u64 h = ((c ^ (c >> 29)) * 0x9E3779B97F4A7C15ull >> 20) & bmask;
+        u64 h = bnd_hash(c, bmask);
         for (u32 probe = 0; probe < 4096; probe++) {
             const u64 cur = bkeys[h];
             if (cur == c) {
@@ -561,51 +697,7 @@ __global__ void __launch_bounds__(256) bkt_fixup_kernel(const u64 *__restrict__ 
     }
 }
 
-// ---- bucket order: largest first -----------------------------------------------------------------------------------
-// A bucket can pass the look-back only when every earlier ticket has published its totals, so tickets are handed
-// out in descending size: whoever waits, waits for buckets that started earlier AND are no smaller.  Sizes are
-// binned (BB_BINS classes of the record count), which is all the order has to be.
-__device__ __forceinline__ u32 bb_size_bin(const u32 *counts, u32 b, u32 nranks, u32 rcap)
-{
-    u64 total = 0;
-    for (u32 s = 0; s < nranks; s++) {
-        const u32 c = counts[(u64)b * nranks + s];
-        total += c < rcap ? c : rcap;
-    }
-    const u64 full = (u64)rcap * nranks;
-    const u32 bin = (u32)(total * (BB_BINS - 1) / (full ? full : 1));
-    return (BB_BINS - 1) - (bin > BB_BINS - 1 ? BB_BINS - 1 : bin);   // bin 0 = the largest buckets
-}
-__global__ void __launch_bounds__(256) bkt_size_hist_kernel(const u32 *__restrict__ counts, u32 nb, u32 nranks, u32 rcap, u32 *__restrict__ hist)
-{
-    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nb) atomicAdd(hist + bb_size_bin(counts, b, nranks, rcap), 1u);
-}
-__global__ void __launch_bounds__(256) bkt_order_kernel(const u32 *__restrict__ counts, u32 nb, u32 nranks, u32 rcap, const u32 *__restrict__ hist,
-                                                        u32 *__restrict__ fill, u32 *__restrict__ order)
-{
-    __shared__ u32 s_base[BB_BINS];
-    __shared__ u32 s_part[256];
-    // exclusive scan of the BB_BINS histogram, recomputed by every block (4 bins per thread)
-    const int tid = threadIdx.x;
-    u32 v[BB_BINS / 256], sum = 0;
-#pragma unroll
-    for (int i = 0; i < BB_BINS / 256; i++) { v[i] = hist[tid * (BB_BINS / 256) + i]; sum += v[i]; }
-    s_part[tid] = sum;
-    __syncthreads();
-    u32 off = 0;
-    for (int i = 0; i < tid; i++) off += s_part[i];
-#pragma unroll
-    for (int i = 0; i < BB_BINS / 256; i++) { s_base[tid * (BB_BINS / 256) + i] = off; off += v[i]; }
-    __syncthreads();
-    const u32 b = blockIdx.x * blockDim.x + tid;
-    if (b < nb) {
-        const u32 bin = bb_size_bin(counts, b, nranks, rcap);
-        order[s_base[bin] + atomicAdd(fill + bin, 1u)] = b;
-    }
-}
-
-size_t bkt_build_smem(u32 cap) { return (size_t)28 * cap; }
+size_t bkt_build_smem(u32 cap) { return (size_t)28 * cap; }   // two key arrays (8 B) + count + two vertex words (4 B)
 
 int bkt_build(euler_ctx *ctx, const BktBuild &B)
 {
@@ -618,21 +710,16 @@ int bkt_build(euler_ctx *ctx, const BktBuild &B)
         CUDA_TRY(ctx, cudaFuncSetAttribute(bkt_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    // state: flag u32[nb] | ticket u32 | hist u32[BINS] | fill u32[BINS] | (16-byte aligned) agg_uv, agg_e, inc_uv, inc_e u64[nb] | order u32[nb]
+    // state: flag u32[nb] | work ticket, output ticket u32[2] | (16-byte aligned) agg_uv, agg_e, inc_uv, inc_e u64[nb]
     u32 *flag = (u32 *)B.state;
     u32 *ticket = flag + B.nb;
-    u32 *hist = ticket + 1, *fill = hist + BB_BINS;
-    const size_t zero_bytes = ((size_t)B.nb + 1 + 2 * BB_BINS) * 4;
+    const size_t zero_bytes = ((size_t)B.nb + 2) * 4;
     u64 *w64 = (u64 *)((char *)B.state + (zero_bytes + 15) / 16 * 16);
-    u32 *order = (u32 *)(w64 + 4ull * B.nb);
     CUDA_TRY(ctx, cudaMemsetAsync(B.state, 0, zero_bytes, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(B.bkeys, 0xFF, B.bcap * 8, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(B.bvals, 0xFF, B.bcap * 8, ctx->stream));
-    bkt_size_hist_kernel<<<grid_for(B.nb, 256), 256, 0, ctx->stream>>>(B.counts, B.nb, B.nranks, B.rcap, hist);
-    bkt_order_kernel<<<grid_for(B.nb, 256), 256, 0, ctx->stream>>>(B.counts, B.nb, B.nranks, B.rcap, hist, fill, order);
-    CUDA_TRY(ctx, cudaGetLastError());
     BkBuildArgs a;
-    a.records = (const uint4 *)B.records; a.counts = B.counts; a.order = order; a.nb = B.nb; a.nranks = B.nranks; a.rcap = B.rcap; a.l = B.l;
+    a.records = (const uint4 *)B.records; a.counts = B.counts; a.nb = B.nb; a.nranks = B.nranks; a.rcap = B.rcap; a.l = B.l;
     a.cap = B.cap;
     a.lkeys = B.lkeys; a.lvals = B.lvals; a.loffs = B.loffs; a.ev1 = B.ev1; a.ev2 = B.ev2; a.ucap = B.ucap;
     a.vkeys = B.vkeys; a.lcount = B.lcount; a.ecount = B.ecount; a.lstart = B.lstart; a.estart = B.estart; a.ev = B.ev; a.vcap = B.vcap;
@@ -641,12 +728,13 @@ int bkt_build(euler_ctx *ctx, const BktBuild &B)
     bkt_build_kernel<<<B.nb, BB_THREADS, smem, ctx->stream>>>(a);
     CUDA_TRY(ctx, cudaGetLastError());
     const unsigned g = (unsigned)ctx->num_sms * 8;
+    bkt_boundary_publish_kernel<<<g, 256, 0, ctx->stream>>>(B.lkeys, B.ev1, B.ev2, B.stats + 3, B.ucap, B.l, B.bkeys, B.bvals, B.bcap, B.stats);
     bkt_fixup_kernel<<<g, 256, 0, ctx->stream>>>(B.lkeys, B.ev2, B.stats + 3, B.ucap, B.l, B.bkeys, B.bvals, B.bcap);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
 
-size_t bkt_state_bytes(u32 nb) { return (((size_t)nb + 1 + 2 * BB_BINS) * 4 + 15) / 16 * 16 + (size_t)nb * 32 + (size_t)nb * 4 + 16; }
+size_t bkt_state_bytes(u32 nb) { return (((size_t)nb + 2) * 4 + 15) / 16 * 16 + (size_t)nb * 32 + 16; }
 
 // ---- canonical ids (EULER_RUN_CANONICAL_IDS): bucket order -> ascending key order -------------------------------------
 // The bucketed build numbers vertices and edge records in bucket order.  Ids = rank in ascending key order

@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const 
     u32 *my_row = rows + (lane + 2) * BP_ROW;
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
-    const u32 k = l - 1, m = bk_m_of(k);
+    // W > 0 fixes k at compile time (m = 12, k = W + 11): the validity masks and shifts below unroll to constants
+    const u32 k = W > 0 ? (u32)(W + BK_M - 1) : l - 1, m = bk_m_of(k);
     u32 nl_tot = 0, nk_tot = 0;
     bool overflow = false;
     if (lane < 2) s_codes[wib][lane] = 0;

@@ -338,14 +338,15 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
     const u64 B = P->n_bases;
     cudaStream_t s = ctx->stream;
     if (B >= (1ull << 40)) return EULER_FALLBACK;
-    EULER_TRY(P->stats.reserve(ctx, 16));
+    EULER_TRY(P->stats.reserve(ctx, 64));
     EULER_TRY(P->start_bits.reserve(ctx, B / 32 + 2));
 
     // geometry: buckets sized for a shared-memory table at ~45 % load
-    const u32 cap = (env_u32("EULER_B200_BKT_CAP", 1792) + 255u) / 256u * 256u;   // 28 B per slot: 4 resident blocks per SM
+    const u32 cap = (env_u32("EULER_B200_BKT_CAP", 1536) + 255u) / 256u * 256u;   // 28 B per slot: 4 resident blocks per SM
     const bool learned = !distinct_hint && P->bk_learned_bases == B && P->bk_learned_l == l && P->bk_learned_nb;
     u64 est_c = distinct_hint ? distinct_hint : (learned ? (P->bk_learned_u + 1) / 2 : (B ? B : 1));
-    const double per_bucket = 0.45 * (double)cap;
+    const char *le = getenv("EULER_B200_BKT_LOAD");
+    const double per_bucket = (le && atof(le) > 0.05 && atof(le) < 0.9 ? atof(le) : 0.30) * (double)cap;   // mean table load (linear probing)
     u64 nb64 = learned ? P->bk_learned_nb : (u64)((double)est_c * 1.06 / per_bucket) + 1;
     if (const u32 f = env_u32("EULER_B200_BKT_NB", 0)) nb64 = f;
     if (nb64 > (1ull << 24)) return EULER_FALLBACK;
@@ -382,7 +383,7 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
         if (need_part) {
             uint4 *self = (uint4 *)P->bk_records.p;
             CUDA_TRY(ctx, cudaMemcpyAsync(P->bk_dst.ptr(), &self, sizeof(self), cudaMemcpyHostToDevice, s));
-            CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 16 * sizeof(u64), s));
+            CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 32 * sizeof(u64), s));
             CUDA_TRY(ctx, cudaMemsetAsync(P->bk_cursors.ptr(), 0, (size_t)nb * sizeof(u32), s));
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], s));
             EULER_TRY(bkt_partition(ctx, P->d_buf, B, P->start_bits.ptr(), l, 1, nb, 0, rcap, P->bk_dst.ptr(), P->bk_cursors.ptr(),
@@ -405,6 +406,12 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
         launches += 2;
         EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 8));   // the only host round trip of a steady-state step
+        if (getenv("EULER_B200_BKT_TIMING")) {   // library built with -DBKT_TIMING: clock cycles per build phase, summed over the blocks
+            u64 t[8];
+            EULER_TRY(read_u64s(ctx, P->stats.ptr() + 16, t, 8));
+            fprintf(stderr, "bkt_build phases (Mcycles over %u blocks): clear %.1f | A count %.1f | B vertices %.1f | C totals %.1f | D look-back %.1f | E1 vertex out %.1f | E2 edge out %.1f\n",
+                    nb, t[0] / 1e6, t[1] / 1e6, t[2] / 1e6, t[3] / 1e6, t[4] / 1e6, t[5] / 1e6, t[6] / 1e6);
+        }
         const u64 fl = h[2];
         if (fl & BKT_FLAG_INTERNAL) return euler_fail(ctx, EULER_ERR_STATE, "internal: bucketed build consistency check failed (flags %llx)", fl);
         if (!(fl & (BKT_FLAG_REGION | BKT_FLAG_TABLE | BKT_FLAG_OUTPUT | BKT_FLAG_BOUNDARY))) break;
@@ -423,8 +430,13 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
         }
     }
     const u64 N_l = h[0], N_k = h[1], U_l = h[3], V = h[4], E = h[5];
-    if (V >= 0x3fffffffull || N_l >= 0x7fffffffull)
+    // u32 ids: vertices and distinct l-mers.  The edge total may pass 2^32 (E is exact, 64-bit): the compressed graph stays
+    // exact and the `unsigned int` offsets of the reference layout (lmerOffsets, lstart / estart, EulerVertex.lp / .ep,
+    // pydebruijn.py:90-101) are then kept modulo 2^32 -- they only address the expanded edge arrays, which need E < 2^32.
+    if (V >= 0x3fffffffull || U_l >= 0xffffffffull)
         return euler_fail(ctx, EULER_ERR_RANGE, "graph exceeds u32 ids (U_l=%llu V=%llu E=%llu)", U_l, V, E);
+    if ((flags & EULER_RUN_EXPAND_EDGES) && E >= 0xffffffffull)
+        return euler_fail(ctx, EULER_ERR_RANGE, "expanded edges need E < 2^32 (E=%llu)", E);
     if (E != 2 * N_l) return euler_fail(ctx, EULER_ERR_STATE, "internal: edge total %llu != 2 N_l %llu", E, 2 * N_l);
     P->U_l = U_l; P->V = V; P->E = E;
 
@@ -1444,7 +1456,7 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
     u64 bcap = pow2_at_least((est_c ? est_c / 6 : (u64)nb * 64) + 1024);
     u64 h[8] = {0};
     u32 retries = 0, launches = 0;
-    u32 cap = (env_u32("EULER_B200_BKT_CAP", 1792) + 255u) / 256u * 256u;
+    u32 cap = (env_u32("EULER_B200_BKT_CAP", 1536) + 255u) / 256u * 256u;
     if (P->bk_scatter_ms < 0.f) {   // asynchronous scatter: its events have completed by now (the caller synchronised on the exchange)
         if (cudaEventElapsedTime(&P->bk_scatter_ms, ctx->ev[0], ctx->ev[1]) != cudaSuccess) { P->bk_scatter_ms = 0.f; cudaGetLastError(); }
     }

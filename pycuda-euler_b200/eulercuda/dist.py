@@ -281,7 +281,7 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
 # The minimizer-bucketed form (csrc/bucket.cuh): what crosses NVLink is the reads cut into 2-bit packed minimizer
 # runs (16-byte records of up to 17 l-mers), stored by the partition kernel straight into the owners' bucket
 # regions; the owner then builds every bucket in shared memory.  Used for l <= 32.
-BKT_CAP = 1792   # slots of a per-bucket shared-memory table (csrc/pipeline.cu default)
+BKT_CAP = 1536   # slots of a per-bucket shared-memory table (csrc/pipeline.cu default)
 
 
 def plan_buckets(n_bases, l, world, distinct_hint=0, cap=None):
@@ -292,7 +292,7 @@ def plan_buckets(n_bases, l, world, distinct_hint=0, cap=None):
     w = k - min(k, 12) + 1
     rec_per_base = 2.0 / (w + 1.0) + 1.0 / 16.0 + 0.01
     est = int(distinct_hint) or max(int(n_bases), 1)
-    nbpr = int(est * 1.06 / (0.45 * cap)) + 1
+    nbpr = int(est * 1.06 / (0.30 * cap)) + 1
     rcap = int(n_bases * rec_per_base / (world * nbpr) * 1.5) + 64
     return nbpr, rcap
 
@@ -407,7 +407,7 @@ def build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, wo
     t2 = time.perf_counter()
     # geometry for the next steps from what was counted (reported at the next exchange, adopted by all ranks together)
     cap = int(os.environ.get("EULER_B200_BKT_CAP", BKT_CAP))
-    ctx._bucket_want = int((st.distinct_lmers + 1) // 2 * 1.06 / (0.45 * cap)) + 1
+    ctx._bucket_want = int((st.distinct_lmers + 1) // 2 * 1.06 / (0.30 * cap)) + 1
     rec_bytes = 16
     info = {"n_lmer_windows": n_l, "n_kmer_windows": n_k, "sent_keys": 0, "recv_keys": 0,
             "exchange_bytes": int(rec_bytes * max_region * bx.nb_per_rank * (world - 1)),   # upper bound: largest region x regions

@@ -79,15 +79,16 @@ d_off = torch.arange(R + 1, dtype=torch.int64, device="cuda") * L
 ctx.sync()
 for mode in ("1", "0"):
     os.environ["EULER_B200_BUCKETED"] = mode
-    for logcap in ((1792, 2048, 1280, 1024, 2560) if mode == "1" else (0,)):
+    for logcap, load in (((1536, 0.3), (2048, 0.3)) if mode == "1" else ((0, 0),)):
         if logcap:
             os.environ["EULER_B200_BKT_CAP"] = str(logcap)
+            os.environ["EULER_B200_BKT_LOAD"] = str(load)
         for hint in (G,):
             ts = []
             for it in range(6):
                 t0 = time.perf_counter()
                 st = ctx.run_dev(d_reads.data_ptr(), d_off.data_ptr(), R, R * L, l, 0, hint)
                 ts.append(1e3 * (time.perf_counter() - t0))
-            print("bucketed=%s cap=%d hint=%d: path=%d nb=%d retries=%d maxrec=%d U=%d V=%d E=%d | ms total %.3f part %.3f build %.3f count %.3f graph %.3f | wall %s"
-                  % (mode, logcap, hint, st.path, st.n_buckets, st.retries, st.bucket_records, st.distinct_lmers, st.distinct_kmers, st.edge_count,
+            print("bucketed=%s cap=%d load=%.2f hint=%d: path=%d nb=%d retries=%d maxrec=%d U=%d V=%d E=%d | ms total %.3f part %.3f build %.3f count %.3f graph %.3f | wall %s"
+                  % (mode, logcap, load, hint, st.path, st.n_buckets, st.retries, st.bucket_records, st.distinct_lmers, st.distinct_kmers, st.edge_count,
                      st.ms_total, st.ms_count_kernel, st.ms_build_kernel, st.ms_count, st.ms_graph, " ".join("%.2f" % t for t in ts)))

@@ -203,7 +203,7 @@ def test_plan_buckets_pure():
     sys.path.insert(0, os.path.join(ROOT, "pycuda-euler_b200"))
     from eulercuda.dist import plan_buckets
     nb1, rc1 = plan_buckets(138_000_000, 32, 1, 4_600_000, cap=1792)
-    assert 5000 < nb1 < 7000 and rc1 * nb1 * 16 < 2 * 10 ** 9
+    assert 8000 < nb1 < 10000 and rc1 * nb1 * 16 < 2 * 10 ** 9
     nb8, rc8 = plan_buckets(138_000_000, 32, 8, 5_290_000, cap=1792)
     assert rc8 < rc1 and nb8 >= nb1
     assert plan_buckets(0, 10, 2) == (1, 64)
