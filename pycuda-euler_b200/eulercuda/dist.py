@@ -427,16 +427,21 @@ def emulate_partitioned_bucketed(ctx, shards, l, world, nb_per_rank=None, rcap=N
     n_max = max(int(off[-1]) for _, off in shards) if shards else 0
     a, b = plan_buckets(max(n_max, 1), l, world)
     nbpr, rcap = nb_per_rank or a, rcap or b
-    nbytes = nbpr * world * rcap * 16 + nbpr * world * 4 + 256
-    areas = [torch.zeros(nbytes // 8 + 1, dtype=torch.int64, device="cuda") for _ in range(world)]
-    ptrs = [t.data_ptr() for t in areas]
-    windows = []
-    for r, (buf, off) in enumerate(shards):
-        d_buf = torch.from_numpy(np.ascontiguousarray(buf)).cuda() if len(buf) else torch.zeros(16, dtype=torch.uint8, device="cuda")
-        d_off = torch.from_numpy(np.ascontiguousarray(off).astype(np.int64)).cuda()
-        out = ctx.bkt_scatter(d_buf.data_ptr(), d_off.data_ptr(), len(off) - 1, int(off[-1]), l, r, world, nbpr, rcap, ptrs)
-        assert not (int(out[2]) & 0x10), "region overflow in the emulation: raise rcap"
-        windows.append((int(out[0]), int(out[1])))
+    while True:
+        nbytes = nbpr * world * rcap * 16 + nbpr * world * 4 + 256
+        areas = [torch.zeros(nbytes // 8 + 1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        ptrs = [t.data_ptr() for t in areas]
+        windows, worst, overflow = [], 0, False
+        for r, (buf, off) in enumerate(shards):
+            d_buf = torch.from_numpy(np.ascontiguousarray(buf)).cuda() if len(buf) else torch.zeros(16, dtype=torch.uint8, device="cuda")
+            d_off = torch.from_numpy(np.ascontiguousarray(off).astype(np.int64)).cuda()
+            out = ctx.bkt_scatter(d_buf.data_ptr(), d_off.data_ptr(), len(off) - 1, int(off[-1]), l, r, world, nbpr, rcap, ptrs)
+            overflow |= bool(int(out[2]) & 0x10)
+            worst = max(worst, int(out[3]))
+            windows.append((int(out[0]), int(out[1])))
+        if not overflow:
+            break
+        rcap = int(worst * 1.25) + 16     # what the production path does collectively (build_partitioned_bucketed)
     ctx.sync()
     res = []
     for d in range(world):
