@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
     u32 *lt_cnt = (u32 *)(vt_keys + cap);
     u32 *vt_a = lt_cnt + cap;   // leaving total of the canonical strand, later the vertex id
     u32 *vt_b = vt_a + cap;     // entering total of the canonical strand
+    u32 *vt_m = vt_b + cap;     // one byte per vertex slot: which of its 8 degree slots are non-zero (bits 0-3 leaving, 4-7 entering)
     __shared__ ulonglong2 s_queue[BB_WARPS][64];
     __shared__ u64 s_wtot[BB_WARPS][4];
     __shared__ u64 s_base[2];
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
         const ulonglong2 e2 = make_ulonglong2(EULER_EMPTY_KEY, EULER_EMPTY_KEY);
         for (u32 i = tid; i < cap; i += BB_THREADS) reinterpret_cast<ulonglong2 *>(lt_keys)[i] = e2;   // lt_keys and vt_keys are adjacent
         const uint4 z = make_uint4(0, 0, 0, 0);
-        for (u32 i = tid; i < 3 * cap / 4; i += BB_THREADS) reinterpret_cast<uint4 *>(lt_cnt)[i] = z;
+        for (u32 i = tid; i < 13 * cap / 16; i += BB_THREADS) reinterpret_cast<uint4 *>(lt_cnt)[i] = z;   // counts, vertex words, masks
     }
     __syncthreads();
     const u32 b = s_bucket;
@@ -366,18 +367,30 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
             const bool pal = !(l & 1u) && c == bk_revcomp(c, l);
             const u32 m0 = pal ? 2u * n : n;
             bool first;
-            if (own_p) {   // strand c leaves prefix(c) with m0
+            // degree slots of the CANONICAL strand v0 of a vertex: lcount[v0][t] (mask bit t) and ecount[v0][t] (bit 4 + t);
+            // the other strand mirrors them: lcount[rc v0][t] = ecount[v0][3 - t], ecount[rc v0][t] = lcount[v0][3 - t]
+            if (own_p) {   // strand c leaves prefix(c) with m0, last base t
                 const u64 p = c >> 2, rp = bk_revcomp(p, k);
+                const u32 t = (u32)c & 3u;
                 const u32 vs = sm_insert(vt_keys, cap, p < rp ? p : rp, first);
                 if (vs == 0xffffffffu) fail = true;
-                else atomicAdd((p <= rp) ? vt_a + vs : vt_b + vs, m0);   // p is the canonical strand (or a palindrome): its leaving total
+                else {
+                    atomicAdd((p <= rp) ? vt_a + vs : vt_b + vs, m0);   // p is the canonical strand (or a palindrome): its leaving total
+                    const u32 bits = p < rp ? (1u << t) : (p > rp ? (16u << (3u - t)) : ((1u << t) | (16u << (3u - t))));
+                    atomicOr(vt_m + (vs >> 2), bits << (8u * (vs & 3u)));
+                }
             }
-            if (own_s && !pal) {   // strand c enters suffix(c) with n (a palindromic l-mer is covered by its prefix side)
+            if (own_s && !pal) {   // strand c enters suffix(c) with n, first base t (a palindromic l-mer is covered by its prefix side)
                 const u64 s = c & kmask, rs = bk_revcomp(s, k);
+                const u32 t = (u32)(c >> (2 * k)) & 3u;
                 const u32 vs = sm_insert(vt_keys, cap, s < rs ? s : rs, first);
                 if (vs == 0xffffffffu) fail = true;
-                else if (s == rs) atomicAdd(vt_a + vs, n);            // palindromic vertex: one strand, leaving total == entering total
-                else atomicAdd((s < rs) ? vt_b + vs : vt_a + vs, n);   // canonical strand: entering; else the mirror = leaving of the canonical strand
+                else {
+                    if (s == rs) atomicAdd(vt_a + vs, n);            // palindromic vertex: one strand, leaving total == entering total
+                    else atomicAdd((s < rs) ? vt_b + vs : vt_a + vs, n);   // canonical strand: entering; else the mirror = leaving of the canonical strand
+                    const u32 bits = s < rs ? (16u << t) : (s > rs ? (1u << (3u - t)) : ((16u << t) | (1u << (3u - t))));
+                    atomicOr(vt_m + (vs >> 2), bits << (8u * (vs & 3u)));
+                }
             }
         };
         for (u32 row = 0; row < rows; row++) {
@@ -525,9 +538,10 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
             const u32 L0 = vt_a[slot], E0 = vt_b[slot];
             u32 lc[4], ec[4];
 #pragma unroll
+            const u32 mask = (vt_m[slot >> 2] >> (8u * (slot & 3u))) & 0xffu;   // only the non-zero degree slots are looked up
             for (u32 t = 0; t < 4; t++) {   // rc(v t) = comp(t) rc(v), rc(t v) = rc(v) comp(t): no bit reversal per neighbour
-                lc[t] = bb_bs_count(lt_keys, lt_cnt, cap, (v << 2) | t, ((u64)(3u - t) << (2 * k)) | rv);
-                ec[t] = bb_bs_count(lt_keys, lt_cnt, cap, ((u64)t << (2 * k)) | v, (rv << 2) | (3u - t));
+                lc[t] = (mask >> t) & 1u ? bb_bs_count(lt_keys, lt_cnt, cap, (v << 2) | t, ((u64)(3u - t) << (2 * k)) | rv) : 0u;
+                ec[t] = (mask >> (4u + t)) & 1u ? bb_bs_count(lt_keys, lt_cnt, cap, ((u64)t << (2 * k)) | v, (rv << 2) | (3u - t)) : 0u;
             }
             const u32 ls = lc[0] + lc[1] + lc[2] + lc[3], es = ec[0] + ec[1] + ec[2] + ec[3];
             if (ls != L0 || es != (palv ? L0 : E0)) bad = true;
@@ -697,7 +711,7 @@ __global__ void __launch_bounds__(256) bkt_fixup_kernel(const u64 *__restrict__ 
     }
 }
 
-size_t bkt_build_smem(u32 cap) { return (size_t)28 * cap; }   // two key arrays (8 B) + count + two vertex words (4 B)
+size_t bkt_build_smem(u32 cap) { return (size_t)29 * cap; }   // two key arrays (8 B) + count + two vertex words (4 B) + mask byte
 
 int bkt_build(euler_ctx *ctx, const BktBuild &B)
 {

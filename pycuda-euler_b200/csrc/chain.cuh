@@ -194,6 +194,7 @@ static int chain_emit(euler_ctx *ctx, M m, u32 n, u32 k, char **d_out, u64 *out_
                                         (char *)ctx->text_buf.p);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    ctx->text_gen++;
     *d_out = (char *)ctx->text_buf.p;
     *out_bytes = bytes;
     *ncontigs = nc;

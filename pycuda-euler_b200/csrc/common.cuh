@@ -38,6 +38,7 @@ struct euler_ctx {
     DevBuf scan_state;  // tile descriptors of the single-pass scan
     DevBuf cg_buf;      // circuit edges of the last tour_circuit_edges call
     DevBuf text_buf;    // contig text of the last emission
+    u64 text_gen = 0;   // bumped by every emission: a cached text is valid only for the generation it was written in
     cudaEvent_t ev[8] = {};
     int num_sms = EULER_SMS;
     size_t l2_bytes = 0;

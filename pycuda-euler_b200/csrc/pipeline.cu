@@ -91,7 +91,7 @@ struct Pipeline {
     bool have_graph = false, expanded = false;
     // capacity memory: distinct canonical l-mers / k-mers seen on the last run of this input size
     u64 learned_bases = 0, learned_lc = 0, learned_vc = 0;
-    u64 text_bytes = 0, text_n = 0;
+    u64 text_bytes = 0, text_n = 0, text_gen = 0;
     bool text_valid = false;  // contig text of the current graph is resident
     bool ingested = false;    // in_buf / in_off hold reads parsed on device by euler_ingest
     DevArr<u64> blk_keys, blk_cur;  // partitioned path, tables >> L2: keys regrouped by table region, run cursors
@@ -330,7 +330,7 @@ static u64 pow2_at_least(u64 x)
     return p;
 }
 #define EULER_FALLBACK 1   // internal: take the global-table path instead
-#define BKT_MAX_CAP 7936u   // 28 B per slot: the largest per-bucket table that fits one block's shared memory
+#define BKT_MAX_CAP 7424u   // 29 B per slot: the largest per-bucket table that fits one block's shared memory
 
 static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 distinct_hint, euler_stats *stats)
 {
@@ -342,7 +342,7 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
     EULER_TRY(P->start_bits.reserve(ctx, B / 32 + 2));
 
     // geometry: buckets sized for a shared-memory table at ~45 % load
-    const u32 cap = (env_u32("EULER_B200_BKT_CAP", 1536) + 255u) / 256u * 256u;   // 28 B per slot: 4 resident blocks per SM
+    const u32 cap = (env_u32("EULER_B200_BKT_CAP", 1536) + 255u) / 256u * 256u;   // 29 B per slot: 4 resident blocks per SM
     const bool learned = !distinct_hint && P->bk_learned_bases == B && P->bk_learned_l == l && P->bk_learned_nb;
     u64 est_c = distinct_hint ? distinct_hint : (learned ? (P->bk_learned_u + 1) / 2 : (B ? B : 1));
     const char *le = getenv("EULER_B200_BKT_LOAD");
@@ -931,7 +931,7 @@ int euler_pipeline_contigs(euler_ctx *ctx, char *out, uint64_t *out_bytes, uint6
     const u32 E = (u32)P->E, V = (u32)P->V;
     *ncontigs = 0;
     if (!E) { *out_bytes = 0; return EULER_OK; }
-    if (!out || !P->text_valid) {  // sizing call (or first call): run the tour now, keep the text resident
+    if (!out || !P->text_valid || P->text_gen != ctx->text_gen) {  // sizing call, first call, or another emission overwrote the shared text buffer: run the tour now
         DevTmp<euler_succ_vertex> sv(ctx, E);
         DevTmp<u32> D(ctx, E), C(ctx, E), cmap(ctx, E), mark(ctx, E);
         DevTmp<u64> cnt(ctx, 1);
@@ -960,7 +960,7 @@ int euler_pipeline_contigs(euler_ctx *ctx, char *out, uint64_t *out_bytes, uint6
         u64 bytes = 0, nc = 0;
         EULER_TRY(tour_emit_contigs(ctx, P->ev.ptr(), V, P->ee.ptr(), E, P->l, &d_text, &bytes, &nc,
                                     P->wide ? P->vkeys_hi.ptr() : nullptr));
-        P->text_bytes = bytes; P->text_n = nc; P->text_valid = true;
+        P->text_bytes = bytes; P->text_n = nc; P->text_valid = true; P->text_gen = ctx->text_gen;
         if (!out) {
             *out_bytes = bytes; *ncontigs = nc;
             return EULER_OK;

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_exclusive_kernel(P p, u6
     }
     // warp total of the segment (the per-row prefixes are recomputed in the store pass instead of being
     // kept: 16 fewer live registers per thread, which buys a whole extra resident block)
-    T carry = 0;
+    u64 carry = 0;   // 64-bit even for the u32 policies: a 512-item segment of large weights must not wrap before it is widened
 #pragma unroll
     for (int r = 0; r < ROWS; r++) carry += v[r];
 #pragma unroll

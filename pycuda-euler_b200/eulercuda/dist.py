@@ -312,6 +312,7 @@ class BucketExchange:
         self.nb_per_rank = max(p[0] for p in props)
         self.rcap = max(p[1] for p in props)
         self.phase = 0
+        self.plan_key = (0, 0)   # (l, largest shard in bases) the geometry was planned for
         self.local, self.areas, self.opened = [None, None], [None, None], []
         handles, err = [None, None], None
         try:
@@ -364,7 +365,10 @@ def _bucket_exchange(ctx, rank, world, nbpr, rcap, group):
 def build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint=0, group=None, _retry=0):
     """One step of the bucketed multi-GPU path on this rank.  d_reads / d_off: CUDA tensors.  The caller's current
     torch stream must be the ctx stream (collectives and kernels are ordered on it).  Returns (stats, info), or None
-    when the ranks have no peer access to each other (the caller then takes the key exchange)."""
+    when the ranks have no peer access to each other (the caller then takes the key exchange).
+
+    Every decision that changes what the ranks do next (re-planning the geometry, redoing the scatter) is taken from
+    words that were MAX-reduced over all ranks, so all ranks take it together."""
     import time
     import torch
     import torch.distributed as dist
@@ -372,8 +376,14 @@ def build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, wo
     t0 = time.perf_counter()
     bx = getattr(ctx, "_bucket_exchange", None)
     if bx is None or bx.world != world:
-        nbpr, rcap = plan_buckets(n_bases, l, world, distinct_hint)
+        # first use: the plan needs the largest shard, which only a collective knows
+        nmax = torch.tensor([int(n_bases)], dtype=torch.int64, device=dev)
+        dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=group)
+        n_plan = int(nmax.item())
+        nbpr, rcap = plan_buckets(n_plan, l, world, distinct_hint)
         bx = _bucket_exchange(ctx, rank, world, nbpr, rcap, group)
+        bx.plan_key = (int(l), n_plan)
+        ctx._bucket_want = 0
     if not bx.ok:
         return None
     which = bx.phase & 1
@@ -381,25 +391,31 @@ def build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, wo
     words = _buffer("bkt_words", 8, dev)
     ctx.bkt_scatter(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, rank, world, bx.nb_per_rank, bx.rcap, bx.areas[which],
                     d_out=words.data_ptr())
-    # flags + largest region + wanted geometry: MAX over ranks.  The collective is also the barrier after which every
-    # rank's peer stores are complete (each rank's scatter precedes its contribution on its stream).
-    want = getattr(ctx, "_bucket_want", 0)
-    msg = torch.stack([words[2], words[3], torch.tensor(want, dtype=torch.int64, device=dev)])
+    # flags, largest region, wanted geometry, shard size, l: MAX over ranks.  The collective is also the barrier after
+    # which every rank's peer stores are complete (each rank's scatter precedes its contribution on its stream).
+    extra = torch.tensor([getattr(ctx, "_bucket_want", 0), int(n_bases), int(l)], dtype=torch.int64, device=dev)
+    msg = torch.cat([words[2:4], extra])
     dist.all_reduce(msg, op=dist.ReduceOp.MAX, group=group)
     host = torch.cat([words[:2], msg]).cpu().numpy()   # the one host round trip between scatter and build
     t1 = time.perf_counter()
-    n_l, n_k, flags, max_region, want_all = (int(x) for x in host)
-    if (flags & 0x10) or (want_all and (want_all > 2 * bx.nb_per_rank or 2 * want_all < bx.nb_per_rank)):
+    n_l, n_k, flags, max_region, want_all, n_max, l_max = (int(x) for x in host)
+    stale = bx.plan_key[0] != l_max or n_max > 2 * bx.plan_key[1] or 2 * n_max < bx.plan_key[1]   # planned for another workload
+    regeom = want_all and (want_all > 2 * bx.nb_per_rank or 2 * want_all < bx.nb_per_rank)
+    if (flags & 0x10) or stale or regeom:
         # collective knowledge (everyone sees the same reduced words): re-plan and redo this step
-        if _retry >= 3:
-            raise RuntimeError("bucketed exchange: the region capacity did not settle")
-        nbpr = want_all if want_all else bx.nb_per_rank
-        rcap = int(max_region * bx.nb_per_rank / nbpr * 1.25) + 64
+        if _retry >= 4:
+            raise RuntimeError("bucketed exchange: the geometry did not settle")
+        if stale:
+            nbpr, rcap = plan_buckets(n_max, l, world, distinct_hint)
+        else:
+            nbpr = want_all if regeom else bx.nb_per_rank
+            rcap = int(max(max_region, 16) * bx.nb_per_rank / nbpr * 1.25) + 64
         bx.close()
         bx.ok = False
         ctx._bucket_exchange = None
         ctx._bucket_want = 0
         bx = _bucket_exchange(ctx, rank, world, nbpr, rcap, group)
+        bx.plan_key = (int(l), n_max)
         if not bx.ok:
             return None
         return build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint, group, _retry + 1)
@@ -408,9 +424,8 @@ def build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, wo
     # geometry for the next steps from what was counted (reported at the next exchange, adopted by all ranks together)
     cap = int(os.environ.get("EULER_B200_BKT_CAP", BKT_CAP))
     ctx._bucket_want = int((st.distinct_lmers + 1) // 2 * 1.06 / (0.30 * cap)) + 1
-    rec_bytes = 16
     info = {"n_lmer_windows": n_l, "n_kmer_windows": n_k, "sent_keys": 0, "recv_keys": 0,
-            "exchange_bytes": int(rec_bytes * max_region * bx.nb_per_rank * (world - 1)),   # upper bound: largest region x regions
+            "exchange_bytes": int(16 * max_region * bx.nb_per_rank * (world - 1)),   # upper bound: largest region x regions sent to the peers
             "exact_fallback": False, "transport": "16-byte minimizer-run records stored into the owners' bucket regions over NVLink (CUDA IPC)",
             "geometry": {"nb_per_rank": bx.nb_per_rank, "rcap": bx.rcap, "max_region": max_region},
             "phase_ms": {"partition+exchange": 1e3 * (t1 - t0), "build": 1e3 * (t2 - t1), "scatter_kernel": float(st.ms_count),

@@ -155,6 +155,12 @@ def findEulerTour(d_ev, d_ee, d_levEdge, d_entEdge, edgeCountList, vertexCount, 
 def assemble2(lmerLength, buffer='', readLength=0, readCount=0, infile='', outfile='', mode='unitig', limit=1):
     """eulercuda.py:450 -- assemble reads into contigs.
 
+    DEVIATION from the reference, stated up front: the reference's ``assemble2`` is the (unfinished) GPU-Euler
+    path; here the DEFAULT ``mode='unitig'`` gives the contigs of the reference's own runnable CPU assembler
+    (BASELINE configs[0] checks exactly that), and ``mode='euler'`` selects the GPU-Euler path.  ``buffer`` is an
+    iterable of reads, or one flat string / bytes object cut every ``readLength`` bases; ``readCount`` > 0 keeps
+    the first reads only.
+
     ``lmerLength`` is the CLI's ``-k`` value (:554).  ``mode='unitig'`` (default) reproduces the
     reference's CPU assembler on the GPU: nodes are ``lmerLength``-mers with both-strand count >
     ``limit`` and the result equals ``referenceAssembler.all_contigs`` as an orientation-free set.
@@ -189,7 +195,19 @@ def assemble2(lmerLength, buffer='', readLength=0, readCount=0, infile='', outfi
                 for i, c in enumerate(contigs):
                     ofile.write('>%u\n%s\n' % (i, c))
         return contigs
+    if isinstance(buffer, (str, bytes, bytearray)):
+        # the reference's other calling convention: one flat string of concatenated reads plus readLength
+        # (eulercuda.py:485-486 joins the reads before encoding); iterating it would yield 1-base "reads"
+        if len(buffer) == 0:
+            buffer = []
+        elif readLength and int(readLength) > 0:
+            rl = int(readLength)
+            buffer = [buffer[i:i + rl] for i in range(0, len(buffer), rl)]
+        else:
+            raise ValueError("assemble2: a flat read buffer needs readLength > 0 (or pass an iterable of reads)")
     reads = [r.decode('ascii') if isinstance(r, (bytes, bytearray)) else str(r) for r in buffer]
+    if readCount and int(readCount) > 0:
+        reads = reads[:int(readCount)]
     logger.info("Got %s reads." % len(reads))
     data = b''.join(r.encode('ascii') for r in reads)
     buf = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(0, np.uint8)
