@@ -293,28 +293,31 @@ int euler_dist_build(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, uint32_
  * exchange above: what crosses NVLink is the 2-bit packed minimizer runs of the reads (16-byte records of up
  * to 17 l-mers), not one 8-byte key per l-mer.  The reference has no analogue (src/cli_spark_gpu.py:37 assembles
  * every read partition on its own).
- *   geometry (the same on every rank): nranks, nb_per_rank buckets owned by each rank, rcap records per
- *   (bucket, source rank) region.  Vertex v belongs to bucket(minimizer(v)); rank = bucket / nb_per_rank, the
+ *   geometry (the same on every rank): nranks, nb_per_rank buckets owned by each rank, scap records per
+ *   (destination, source) stream.  Vertex v belongs to bucket(minimizer(v)); rank = bucket / nb_per_rank, the
  *   round-1 owner rule.
- *   1. euler_bkt_area_alloc   a receive area (two per context, `which` = step parity) + its CUDA IPC handle
- *   2. euler_bkt_scatter      one pass over this rank's reads: records and region counts stored straight into the
- *                             owners' areas (dst_areas[r] = rank r's area, local or peer-mapped)
+ *   1. euler_bkt_area_alloc   a receive area (two per context, `which` = step parity) + its CUDA IPC handle:
+ *                             nranks streams of scap records, then the per-source record counts
+ *   2. euler_bkt_scatter      one pass over this rank's reads: per tile one contiguous run of records per destination,
+ *                             stored straight into the owners' streams (dst_areas[r] = rank r's area, local or
+ *                             peer-mapped); the local bucket id rides in the record header
  *   3. (barrier across ranks)
- *   4. euler_bkt_build        per-bucket shared-memory build over the local area; artefacts as after
- *                             euler_dist_build (local ids; v2 = 0xffffffff when the suffix vertex lives on another rank)
+ *   4. euler_bkt_build        regroup the incoming streams into bucket regions (local), then the per-bucket
+ *                             shared-memory build; artefacts as after euler_dist_build (local ids; v2 = 0xffffffff
+ *                             when the suffix vertex lives on another rank).  Every repair (region, table or
+ *                             output capacity) is local to the rank.
  * ======================================================================================= */
-int euler_bkt_area_bytes(uint32_t nb_per_rank, uint32_t nranks, uint32_t rcap, uint64_t *bytes);
-int euler_bkt_area_alloc(euler_ctx *ctx, int which, uint32_t nb_per_rank, uint32_t nranks, uint32_t rcap, void **dptr,
-                         unsigned char *handle64);
-/* out[0] forward l-mer windows, out[1] forward k-mer windows of this rank's reads, out[2] flags (0x10: a region
- * overflowed -- partition again with the capacity of out[3]), out[3] records in the largest region */
-/* d_out != NULL: asynchronous form, the four words are left in device memory (u64[4]) on the ctx stream and `out`
+int euler_bkt_area_bytes(uint32_t nranks, uint32_t scap, uint64_t *bytes);
+int euler_bkt_area_alloc(euler_ctx *ctx, int which, uint32_t nranks, uint32_t scap, void **dptr, unsigned char *handle64);
+/* out[0] forward l-mer windows, out[1] forward k-mer windows of this rank's reads, out[2] flags (0x10: a stream
+ * overflowed -- scatter again with the capacity of out[3]), out[3] records in the fullest stream.
+ * d_out != NULL: asynchronous form, the four words are left in device memory (u64[4]) on the ctx stream and `out`
  * may be NULL -- e.g. as the payload of the collective that doubles as the barrier of step 3 */
 int euler_bkt_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads, uint64_t n_bases,
-                      uint32_t l, uint32_t my_rank, uint32_t nranks, uint32_t nb_per_rank, uint32_t rcap,
+                      uint32_t l, uint32_t my_rank, uint32_t nranks, uint32_t nb_per_rank, uint32_t scap,
                       void *const *dst_areas, uint64_t *out, void *d_out);
 int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_rank, uint32_t nranks,
-                    uint32_t nb_per_rank, uint32_t rcap, uint64_t distinct_hint, euler_stats *stats);
+                    uint32_t nb_per_rank, uint32_t scap, uint64_t distinct_hint, euler_stats *stats);
 
 /* =========================================================================================
  * Step-level entry points of the reference's fine-grained wrappers (kept for callers; the

@@ -113,8 +113,8 @@ def load():
         "euler_dist_peer_close": [vp, vp],
         "euler_dist_scatter_peers": [vp, vp, vp, u64, u64, u32, u32, vp, u64, vp],
         "euler_dist_build_regions": [vp, vp, u64, vp, u32, u32, u32, u64, vp],
-        "euler_bkt_area_bytes": [u32, u32, u32, vp],
-        "euler_bkt_area_alloc": [vp, i32, u32, u32, u32, vp, vp],
+        "euler_bkt_area_bytes": [u32, u32, vp],
+        "euler_bkt_area_alloc": [vp, i32, u32, u32, vp, vp],
         "euler_bkt_scatter": [vp, vp, vp, u64, u64, u32, u32, u32, u32, u32, vp, vp, vp],
         "euler_bkt_build": [vp, vp, u32, u32, u32, u32, u32, u64, vp],
         "euler_compat_phase1": [vp, vp, u64, u32, vp, vp],
@@ -606,27 +606,27 @@ class Context:
         return st
 
     # ------------------------------------------------------------------ multi-GPU form of the bucketed path
-    def bkt_area_alloc(self, which, nb_per_rank, nranks, rcap):
-        """(device pointer, 64-byte CUDA IPC handle) of receive area `which` (0 / 1) of this rank"""
+    def bkt_area_alloc(self, which, nranks, scap):
+        """(device pointer, 64-byte CUDA IPC handle) of receive area `which` (0 / 1) of this rank: nranks streams of scap records"""
         p = C.c_void_p()
         handle = (C.c_ubyte * 64)()
-        self.check(self.lib.euler_bkt_area_alloc(self.h, int(which), int(nb_per_rank), int(nranks), int(rcap), C.byref(p), handle))
+        self.check(self.lib.euler_bkt_area_alloc(self.h, int(which), int(nranks), int(scap), C.byref(p), handle))
         return p.value, bytes(handle)
 
-    def bkt_scatter(self, d_buf, d_off, nreads, n_bases, l, rank, nranks, nb_per_rank, rcap, dst_areas, d_out=None):
+    def bkt_scatter(self, d_buf, d_off, nreads, n_bases, l, rank, nranks, nb_per_rank, scap, dst_areas, d_out=None):
         """-> uint64[4]: forward l-mer windows, forward k-mer windows, flags (0x10 = a region overflowed), largest region.
         d_out (device pointer to 4 x u64): asynchronous form, the words stay on the device and None is returned."""
         out = np.zeros(4, np.uint64)
         arr = (C.c_void_p * nranks)(*[C.c_void_p(int(x)) for x in dst_areas])
         self.check(self.lib.euler_bkt_scatter(self.h, C.c_void_p(int(d_buf)), C.c_void_p(int(d_off)), int(nreads), int(n_bases),
-                                              int(l), int(rank), int(nranks), int(nb_per_rank), int(rcap), arr,
+                                              int(l), int(rank), int(nranks), int(nb_per_rank), int(scap), arr,
                                               None if d_out else _p(out), C.c_void_p(int(d_out)) if d_out else None))
         return None if d_out else out
 
-    def bkt_build(self, d_area, l, rank, nranks, nb_per_rank, rcap, distinct_hint=0):
+    def bkt_build(self, d_area, l, rank, nranks, nb_per_rank, scap, distinct_hint=0):
         st = Stats()
         self.check(self.lib.euler_bkt_build(self.h, C.c_void_p(int(d_area)), int(l), int(rank), int(nranks), int(nb_per_rank),
-                                            int(rcap), int(distinct_hint), C.byref(st)))
+                                            int(scap), int(distinct_hint), C.byref(st)))
         return st
 
     def synth_reads_dev(self, d_out, G, L, err_ppm, first, nreads):

@@ -22,12 +22,20 @@
 #define BP_MINB 8
 #endif
 
-template <int W>
+// STREAM = false: records go straight into the bucket regions (one GPU: `dst[0]`, region of bucket b at b * rcap, one
+//   cursor per bucket).
+// STREAM = true (multi-GPU): records go into ONE stream per destination rank (`dst[r]` + my_rank * rcap, rcap = stream
+//   capacity, one cursor per destination), the local bucket id rides in bits 8..31 of the header, and the owner regroups
+//   its incoming streams into bucket regions itself (bkt_regroup_kernel).  Isolated 16-byte stores into thousands of
+//   regions of a PEER's memory ran at ~1 GB/s on 8 GPUs; here every tile first reserves one contiguous run per
+//   destination (one cursor atomic each), so what crosses NVLink are runs of records.
+template <int W, bool STREAM>
 __global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const uint4 *__restrict__ buf16, u64 n_bases,
                                                                            const u32 *__restrict__ start_bits, u32 l, BkGeom geom,
                                                                            u32 my_rank, u32 rcap, uint4 *const *__restrict__ dst,
                                                                            u32 *__restrict__ cursors, u64 ntiles, u64 *__restrict__ stats)
 {
+    __shared__ u32 s_rcnt[STREAM ? BP_WARPS : 1][16], s_rbase[STREAM ? BP_WARPS : 1][16], s_rfill[STREAM ? BP_WARPS : 1][16];
     __shared__ __align__(16) u32 s_rows[BP_WARPS][BP_ROWS * BP_ROW];   // per lane: 16 m-mer scores, then 16 window minima
     __shared__ u32 s_codes[BP_WARPS][34];                              // 2-bit codes of every lane's chunk (two pad entries in front)
     __shared__ u32 s_vl[BP_WARPS][32];                                 // valid l-mer windows of every lane
@@ -106,6 +114,24 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const 
             s_desc[wib][at++] = (unsigned short)((lane << 8) | (e << 4) | s);
         }
         __syncwarp();
+        if constexpr (STREAM) {
+            // ---- reserve one run per destination rank for this tile: pieces (+ a slot for the orphan a chunk-leading piece may add)
+            if (lane < 16) { s_rcnt[wib][lane] = 0; s_rfill[wib][lane] = 0; }
+            __syncwarp();
+            for (u32 t = lane; t < total; t += 32) {
+                const u32 d = s_desc[wib][t];
+                const u32 L = d >> 8, s = d & 15u;
+                const u32 *row = rows + (L + 2) * BP_ROW;
+                atomicAdd(&s_rcnt[wib][bk_rank_of(row[s], geom.nranks)], 1u);
+                if (s == 0 && (s_vl[wib][L] & 1u)) atomicAdd(&s_rcnt[wib][bk_rank_of(row[-BP_ROW + 15], geom.nranks)], 1u);
+            }
+            __syncwarp();
+            if ((u32)lane < geom.nranks) {
+                const u32 cnt = s_rcnt[wib][lane];
+                s_rbase[wib][lane] = cnt ? atomicAdd(cursors + lane, cnt) : 0u;   // ONE cursor atomic per destination per tile
+            }
+            __syncwarp();
+        }
         // ---- one piece per lane per round: record(s), cursor atomic, 16-byte store -------------------------------------------
         for (u32 t = lane; t < total; t += 32) {
             const u32 d = s_desc[wib][t];
@@ -116,14 +142,29 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const 
                              [&](u32 bucket, const BkRec &r) {
                                  const u32 rank = geom.nranks > 1 ? bucket / geom.nb_per_rank : 0u;
                                  const u32 lb = bucket - rank * geom.nb_per_rank;
-                                 const u32 pos = atomicAdd(cursors + bucket, 1u);
-                                 if (pos < rcap) {
-                                     uint4 *region = dst[rank] + ((u64)lb * geom.nranks + my_rank) * rcap;
-                                     region[pos] = make_uint4(r.hdr, r.d[0], r.d[1], r.d[2]);
+                                 if constexpr (STREAM) {
+                                     const u32 pos = s_rbase[wib][rank] + atomicAdd(&s_rfill[wib][rank], 1u);
+                                     if (pos < rcap) dst[rank][(u64)my_rank * rcap + pos] = make_uint4(r.hdr | (lb << 8), r.d[0], r.d[1], r.d[2]);
+                                     else overflow = true;
                                  } else {
-                                     overflow = true;
+                                     const u32 pos = atomicAdd(cursors + bucket, 1u);
+                                     if (pos < rcap) {
+                                         uint4 *region = dst[rank] + ((u64)lb * geom.nranks + my_rank) * rcap;
+                                         region[pos] = make_uint4(r.hdr, r.d[0], r.d[1], r.d[2]);
+                                     } else {
+                                         overflow = true;
+                                     }
                                  }
                              });
+        }
+        if constexpr (STREAM) {
+            __syncwarp();
+            // reserved slots that no record took (a chunk-leading piece without an orphan, a lone k-mer): empty records
+            for (u32 r = 0; r < geom.nranks; r++) {
+                const u32 cnt = s_rcnt[wib][r], fill = s_rfill[wib][r], base = s_rbase[wib][r];
+                for (u32 j = fill + lane; j < cnt; j += 32)
+                    if (base + j < rcap) dst[r][(u64)my_rank * rcap + base + j] = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
         __syncwarp();   // the rows are rewritten by the next tile
     }
@@ -139,8 +180,8 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const 
     if (overflow) atomicOr((unsigned long long *)(stats + 2), (unsigned long long)BKT_FLAG_REGION);
 }
 
-int bkt_partition(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u32 nranks, u32 nb_per_rank, u32 my_rank,
-                  u32 rcap, uint4 *const *d_dst, u32 *d_cursors, u64 *d_stats)
+static int bkt_partition_launch(euler_ctx *ctx, bool stream, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u32 nranks,
+                                u32 nb_per_rank, u32 my_rank, u32 rcap, uint4 *const *d_dst, u32 *d_cursors, u64 *d_stats)
 {
     if (!n_bases) return EULER_OK;
     const u64 nchunks = (n_bases + 15) / 16;
@@ -151,42 +192,85 @@ int bkt_partition(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_b
     const BkGeom geom = {nranks, nb_per_rank};
     const u32 k = l - 1, W = k - bk_m_of(k) + 1;
     const unsigned g = (unsigned)grid;
-#define LAUNCH_BP(WW)                                                                                                        \
-    bkt_partition_kernel<WW><<<g, BP_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, geom, my_rank, rcap, d_dst, \
-                                                              d_cursors, ntiles, d_stats)
-    if (W == 20) LAUNCH_BP(20);        // k = 31
-    else if (W == 10) LAUNCH_BP(10);   // k = 21
-    else LAUNCH_BP(0);
+#define LAUNCH_BP(WW, SS)                                                                                                        \
+    bkt_partition_kernel<WW, SS><<<g, BP_BLOCK, 0, ctx->stream>>>((const uint4 *)d_buf, n_bases, d_bits, l, geom, my_rank, rcap, d_dst, \
+                                                                  d_cursors, ntiles, d_stats)
+    if (stream) {
+        if (W == 20) LAUNCH_BP(20, true);        // k = 31
+        else if (W == 10) LAUNCH_BP(10, true);   // k = 21
+        else LAUNCH_BP(0, true);
+    } else {
+        if (W == 20) LAUNCH_BP(20, false);
+        else if (W == 10) LAUNCH_BP(10, false);
+        else LAUNCH_BP(0, false);
+    }
 #undef LAUNCH_BP
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
 
-// ---- multi-GPU: publish this rank's region counts in every owner's area -----------------------------------------
-// counts of owner d live behind its records: counts[lb * nranks + src]
-__global__ void __launch_bounds__(256) bkt_push_counts_kernel(const u32 *__restrict__ cursors, uint4 *const *__restrict__ dst, u64 rec_bytes,
-                                                              u32 nbpr, u32 nranks, u32 my_rank, u64 *__restrict__ max_out)
+int bkt_partition(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u32 nranks, u32 nb_per_rank, u32 my_rank,
+                  u32 rcap, uint4 *const *d_dst, u32 *d_cursors, u64 *d_stats)
 {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u32 c = 0;
-    if (i < (u64)nbpr * nranks) {
-        const u32 d = (u32)(i / nbpr), lb = (u32)(i - (u64)d * nbpr);
-        c = cursors[i];
-        u32 *counts = (u32 *)((char *)dst[d] + rec_bytes);
-        counts[(u64)lb * nranks + my_rank] = c;
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        const u32 t = __shfl_xor_sync(0xffffffffu, c, o);
-        c = t > c ? t : c;
-    }
-    if ((threadIdx.x & 31) == 0 && c) atomicMax((unsigned long long *)max_out, (unsigned long long)c);
+    return bkt_partition_launch(ctx, false, d_buf, n_bases, d_bits, l, nranks, nb_per_rank, my_rank, rcap, d_dst, d_cursors, d_stats);
+}
+// stream form: d_dst[r] = base of rank r's stream area (nranks streams of scap records), d_cursors[nranks] zeroed by the caller
+int bkt_partition_streams(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u32 nranks, u32 nb_per_rank,
+                          u32 my_rank, u32 scap, uint4 *const *d_dst, u32 *d_cursors, u64 *d_stats)
+{
+    if (nranks > 16) return euler_fail(ctx, EULER_ERR_ARG, "at most 16 ranks");
+    if (nb_per_rank >= (1u << 24)) return euler_fail(ctx, EULER_ERR_ARG, "at most 2^24 buckets per rank (the id rides in the record header)");
+    return bkt_partition_launch(ctx, true, d_buf, n_bases, d_bits, l, nranks, nb_per_rank, my_rank, scap, d_dst, d_cursors, d_stats);
 }
 
-int bkt_push_counts(euler_ctx *ctx, const u32 *d_cursors, uint4 *const *d_dst, u64 rec_bytes, u32 nbpr, u32 nranks, u32 my_rank, u64 *d_max)
+// ---- multi-GPU: publish how many records this rank wrote into each owner's stream ---------------------------------------
+// the counts of owner d live behind its streams: u64 counts[nranks], entry `my_rank` is ours
+__global__ void bkt_push_counts_kernel(const u32 *__restrict__ cursors, uint4 *const *__restrict__ dst, u64 stream_bytes, u32 nranks,
+                                       u32 my_rank, u32 scap, u64 *__restrict__ max_out)
 {
-    const u64 n = (u64)nbpr * nranks;
-    bkt_push_counts_kernel<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_cursors, d_dst, rec_bytes, nbpr, nranks, my_rank, d_max);
+    const u32 d = threadIdx.x;
+    if (d >= nranks) return;
+    const u32 c = cursors[d];
+    u64 *counts = (u64 *)((char *)dst[d] + stream_bytes);
+    counts[my_rank] = c < scap ? c : scap;
+    atomicMax((unsigned long long *)max_out, (unsigned long long)c);
+}
+
+int bkt_push_counts(euler_ctx *ctx, const u32 *d_cursors, uint4 *const *d_dst, u64 stream_bytes, u32 nranks, u32 my_rank, u32 scap, u64 *d_max)
+{
+    bkt_push_counts_kernel<<<1, 32, 0, ctx->stream>>>(d_cursors, d_dst, stream_bytes, nranks, my_rank, scap, d_max);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return EULER_OK;
+}
+
+// ---- owner side: incoming streams -> bucket regions (local memory, one cursor per bucket) ---------------------------------
+__global__ void __launch_bounds__(256) bkt_regroup_kernel(const uint4 *__restrict__ streams, const u64 *__restrict__ counts, u32 nranks,
+                                                          u32 scap, u32 nb, u32 rcap, uint4 *__restrict__ records, u32 *__restrict__ cursors,
+                                                          u64 *__restrict__ stats)
+{
+    bool overflow = false, bad = false;
+    for (u32 src = 0; src < nranks; src++) {
+        const u64 n = counts[src] < scap ? counts[src] : scap;
+        const uint4 *in = streams + (u64)src * scap;
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+            const uint4 r = ld_stream_v4(in + i);
+            if ((r.x & 63u) == 0u) continue;   // an unused reserved slot
+            const u32 lb = r.x >> 8;
+            if (lb >= nb) { bad = true; continue; }
+            const u32 pos = atomicAdd(cursors + lb, 1u);
+            if (pos < rcap) records[(u64)lb * rcap + pos] = make_uint4(r.x & 0xffu, r.y, r.z, r.w);
+            else overflow = true;
+        }
+    }
+    if (overflow) atomicOr((unsigned long long *)(stats + 2), (unsigned long long)BKT_FLAG_REGION);
+    if (bad) atomicOr((unsigned long long *)(stats + 2), (unsigned long long)BKT_FLAG_INTERNAL);
+}
+
+int bkt_regroup(euler_ctx *ctx, const void *d_streams, const u64 *d_counts, u32 nranks, u32 scap, u32 nb, u32 rcap, void *d_records,
+                u32 *d_cursors, u64 *d_stats)
+{
+    bkt_regroup_kernel<<<(unsigned)ctx->num_sms * 8, 256, 0, ctx->stream>>>((const uint4 *)d_streams, d_counts, nranks, scap, nb, rcap,
+                                                                          (uint4 *)d_records, d_cursors, d_stats);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }

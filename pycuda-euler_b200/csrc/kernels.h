@@ -188,4 +188,10 @@ int bkt_invert_perm(euler_ctx *ctx, const u32 *perm, u64 n, u32 *inv);
 int bkt_gather_rows(euler_ctx *ctx, const u32 *perm, u64 n, const u32 *a_in, const u32 *b_in, u32 *a_out, u32 *b_out);
 int bkt_gather_edges(euler_ctx *ctx, const u32 *perm, u64 n, const u32 *newid, const u32 *lvals, const u32 *ev1, const u32 *ev2,
                      u32 *lvals_out, u32 *ev1_out, u32 *ev2_out);
-int bkt_push_counts(euler_ctx *ctx, const u32 *d_cursors, uint4 *const *d_dst, u64 rec_bytes, u32 nbpr, u32 nranks, u32 my_rank, u64 *d_max);
+// multi-GPU stream form of pass 1 (one stream per destination rank, the local bucket id in bits 8..31 of the record header),
+// the count hand-over and the owner-side regrouping of the incoming streams into bucket regions
+int bkt_partition_streams(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u32 nranks, u32 nb_per_rank,
+                          u32 my_rank, u32 scap, uint4 *const *d_dst, u32 *d_cursors, u64 *d_stats);
+int bkt_push_counts(euler_ctx *ctx, const u32 *d_cursors, uint4 *const *d_dst, u64 stream_bytes, u32 nranks, u32 my_rank, u32 scap, u64 *d_max);
+int bkt_regroup(euler_ctx *ctx, const void *d_streams, const u64 *d_counts, u32 nranks, u32 scap, u32 nb, u32 rcap, void *d_records,
+                u32 *d_cursors, u64 *d_stats);

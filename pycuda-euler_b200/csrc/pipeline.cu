@@ -114,6 +114,8 @@ struct Pipeline {
     void *bk_area[2] = {nullptr, nullptr};   // peer-visible bucket areas of the multi-GPU form (plain cudaMalloc)
     u64 bk_area_bytes[2] = {0, 0};
     u64 bk_dist_key = 0;
+    u32 bk_dist_rcap = 0;
+    DevArr<u32> bk_scursors;   // per-destination stream cursors of the multi-GPU form
     float bk_scatter_ms = 0;
     euler_stats st = {};
 };
@@ -132,7 +134,7 @@ void pipeline_destroy(Pipeline *p)
     p->wlt_keys.free(); p->wvt_keys.free(); p->wlt_cnt.free(); p->lkeys_hi.free(); p->vkeys_hi.free(); p->tf.free();
     for (int i = 0; i < 2; i++) if (p->bk_area[i]) cudaFree(p->bk_area[i]);
     dev_free(p->bk_records); dev_free(p->bk_state); p->bk_cursors.free(); p->bk_bvals.free(); p->bk_perm.free(); p->bk_newid.free();
-    p->bk_tmp32a.free(); p->bk_tmp32b.free(); p->bk_tmp32c.free(); p->bk_rows_a.free(); p->bk_rows_b.free(); p->bk_bkeys.free(); p->bk_dst.free();
+    p->bk_tmp32a.free(); p->bk_tmp32b.free(); p->bk_tmp32c.free(); p->bk_rows_a.free(); p->bk_rows_b.free(); p->bk_bkeys.free(); p->bk_dst.free(); p->bk_scursors.free();
     delete p;
 }
 
@@ -1351,28 +1353,28 @@ static int dist_build_impl(euler_ctx *ctx, const void *d_keys, uint64_t nkeys, u
 }
 
 // ---- multi-GPU form of the bucketed path -----------------------------------------------------------------------
-// Every rank owns nb_per_rank buckets; the region of (local bucket, source rank) lives in the OWNER's "area"
-// (records followed by the per-region record counts), published through a CUDA IPC handle.  Pass 1 on every
-// rank stores its records straight into the owners' areas over NVLink and then its region counts; after a
-// barrier, pass 2 runs on the local area.  No key ever crosses the fabric: a 16-byte record carries ~7 l-mers.
-static size_t bkt_area_record_bytes(u32 nbpr, u32 nranks, u32 rcap) { return (size_t)nbpr * nranks * rcap * 16; }
+// Every rank owns nb_per_rank buckets.  Pass 1 on every rank cuts its reads into records and stores them, as
+// contiguous runs, into ONE stream per destination rank that lives in the destination's "area" (nranks streams of
+// scap records, followed by the per-source record counts), published through a CUDA IPC handle; the local bucket id
+// rides in the record header.  After a barrier the owner regroups its incoming streams into bucket regions (local
+// memory) and runs pass 2 on them.  No key ever crosses the fabric: a 16-byte record carries ~7 l-mers.
+static size_t bkt_stream_bytes(u32 nranks, u32 scap) { return (size_t)nranks * scap * 16; }
 
-int euler_bkt_area_bytes(uint32_t nb_per_rank, uint32_t nranks, uint32_t rcap, uint64_t *bytes)
+int euler_bkt_area_bytes(uint32_t nranks, uint32_t scap, uint64_t *bytes)
 {
     if (!bytes) return EULER_ERR_ARG;
-    *bytes = bkt_area_record_bytes(nb_per_rank, nranks, rcap) + (size_t)nb_per_rank * nranks * 4 + 256;
+    *bytes = bkt_stream_bytes(nranks, scap) + (size_t)nranks * 8 + 256;
     return EULER_OK;
 }
 
 // which in {0, 1}: two areas per context so that a rank may scatter step i+1 while a peer still builds step i
-int euler_bkt_area_alloc(euler_ctx *ctx, int which, uint32_t nb_per_rank, uint32_t nranks, uint32_t rcap, void **dptr,
-                         unsigned char *handle64)
+int euler_bkt_area_alloc(euler_ctx *ctx, int which, uint32_t nranks, uint32_t scap, void **dptr, unsigned char *handle64)
 {
     if (!ctx || !dptr || which < 0 || which > 1) return EULER_ERR_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     Pipeline *P = get_pipe(ctx);
     uint64_t need = 0;
-    euler_bkt_area_bytes(nb_per_rank, nranks, rcap, &need);
+    euler_bkt_area_bytes(nranks, scap, &need);
     if (P->bk_area[which] && P->bk_area_bytes[which] < need) {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(P->bk_area[which]);
@@ -1381,7 +1383,10 @@ int euler_bkt_area_alloc(euler_ctx *ctx, int which, uint32_t nb_per_rank, uint32
     if (!P->bk_area[which]) {
         // plain cudaMalloc: IPC handles cannot be taken from stream-ordered pool memory
         cudaError_t e = cudaMalloc(&P->bk_area[which], need);
-        if (e != cudaSuccess) return euler_fail(ctx, EULER_ERR_NOMEM, "cudaMalloc(bucket area %llu bytes): %s", (u64)need, cudaGetErrorString(e));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return euler_fail(ctx, EULER_ERR_NOMEM, "cudaMalloc(stream area %llu bytes): %s", (u64)need, cudaGetErrorString(e));
+        }
         P->bk_area_bytes[which] = need;
     }
     if (handle64) {
@@ -1393,9 +1398,9 @@ int euler_bkt_area_alloc(euler_ctx *ctx, int which, uint32_t nb_per_rank, uint32
     return EULER_OK;
 }
 
-// out[0] N_l, out[1] N_k of this rank's reads, out[2] flags (BKT_FLAG_REGION = a region overflowed), out[3] largest region
+// out[0] N_l, out[1] N_k of this rank's reads, out[2] flags (BKT_FLAG_REGION = a stream overflowed), out[3] records in the fullest stream
 int euler_bkt_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off, uint64_t nreads, uint64_t n_bases, uint32_t l,
-                      uint32_t my_rank, uint32_t nranks, uint32_t nb_per_rank, uint32_t rcap, void *const *dst_areas, uint64_t *out,
+                      uint32_t my_rank, uint32_t nranks, uint32_t nb_per_rank, uint32_t scap, void *const *dst_areas, uint64_t *out,
                       void *d_out)
 {
     if (!ctx || (!out && !d_out) || !dst_areas) return EULER_ERR_ARG;
@@ -1405,22 +1410,21 @@ int euler_bkt_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off,
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     Pipeline *P = get_pipe(ctx);
     cudaStream_t s = ctx->stream;
-    const u32 NB = nranks * nb_per_rank;
     EULER_TRY(P->stats.reserve(ctx, 64));
     EULER_TRY(P->start_bits.reserve(ctx, n_bases / 32 + 2));
-    EULER_TRY(P->bk_cursors.reserve(ctx, NB));
+    EULER_TRY(P->bk_scursors.reserve(ctx, 16));
     EULER_TRY(P->bk_dst.reserve(ctx, 16));
     uint4 *h_dst[16];
     for (u32 d = 0; d < nranks; d++) h_dst[d] = (uint4 *)dst_areas[d];
     CUDA_TRY(ctx, cudaMemcpyAsync(P->bk_dst.ptr(), h_dst, nranks * sizeof(uint4 *), cudaMemcpyHostToDevice, s));
     CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr() + 40, 0, 8 * sizeof(u64), s));
-    CUDA_TRY(ctx, cudaMemsetAsync(P->bk_cursors.ptr(), 0, (size_t)NB * sizeof(u32), s));
+    CUDA_TRY(ctx, cudaMemsetAsync(P->bk_scursors.ptr(), 0, 16 * sizeof(u32), s));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
     EULER_TRY(enc_mark_starts(ctx, (const u64 *)d_read_off, nreads, n_bases, P->start_bits.ptr()));
-    EULER_TRY(bkt_partition(ctx, d_buf, n_bases, P->start_bits.ptr(), l, nranks, nb_per_rank, my_rank, rcap, P->bk_dst.ptr(),
-                            P->bk_cursors.ptr(), P->stats.ptr() + 40));
-    EULER_TRY(bkt_push_counts(ctx, P->bk_cursors.ptr(), P->bk_dst.ptr(), bkt_area_record_bytes(nb_per_rank, nranks, rcap), nb_per_rank,
-                              nranks, my_rank, P->stats.ptr() + 46));
+    EULER_TRY(bkt_partition_streams(ctx, d_buf, n_bases, P->start_bits.ptr(), l, nranks, nb_per_rank, my_rank, scap, P->bk_dst.ptr(),
+                                    P->bk_scursors.ptr(), P->stats.ptr() + 40));
+    EULER_TRY(bkt_push_counts(ctx, P->bk_scursors.ptr(), P->bk_dst.ptr(), bkt_stream_bytes(nranks, scap), nranks, my_rank, scap,
+                              P->stats.ptr() + 46));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], s));
     if (d_out) {   // asynchronous form: the four words stay on the device (e.g. as the payload of the caller's collective)
         CUDA_TRY(ctx, cudaMemcpyAsync(d_out, P->stats.ptr() + 40, 3 * sizeof(u64), cudaMemcpyDeviceToDevice, s));
@@ -1435,8 +1439,9 @@ int euler_bkt_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off,
     return EULER_OK;
 }
 
+// n_bases_hint: bases of the largest shard (sizes the bucket regions before anything has been learned; 0 = from scap)
 int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_rank, uint32_t nranks, uint32_t nb_per_rank,
-                    uint32_t rcap, uint64_t distinct_hint, euler_stats *stats)
+                    uint32_t scap, uint64_t distinct_hint, euler_stats *stats)
 {
     if (!ctx || !d_area) return EULER_ERR_ARG;
     if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
@@ -1449,19 +1454,26 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
     EULER_TRY(P->stats.reserve(ctx, 64));
     const u32 nb = nb_per_rank;
     const u64 key = ((u64)nb << 32) ^ ((u64)nranks << 8) ^ l;   // what the learned capacities belong to
-    const bool learned = !distinct_hint && P->bk_dist_key == key && P->bk_learned_u;
+    const bool learned = P->bk_dist_key == key && P->bk_learned_u;
     const u64 est_c = distinct_hint ? distinct_hint : (learned ? (P->bk_learned_u + 1) / 2 : 0);
-    u64 ucap = est_c ? (distinct_hint ? 2 * est_c + est_c / 4 : P->bk_learned_u + P->bk_learned_u / 32) + 1024 : 0;
-    u64 vcap = est_c ? (distinct_hint ? 2 * est_c + est_c / 4 : P->bk_learned_v + P->bk_learned_v / 32) + 1024 : 0;
+    u64 ucap = learned ? P->bk_learned_u + P->bk_learned_u / 32 + 1024 : (distinct_hint ? 2 * est_c + est_c / 4 + 1024 : 0);
+    u64 vcap = learned ? P->bk_learned_v + P->bk_learned_v / 32 + 1024 : (distinct_hint ? 2 * est_c + est_c / 4 + 1024 : 0);
     u64 bcap = pow2_at_least((est_c ? est_c / 6 : (u64)nb * 64) + 1024);
+    // bucket regions: what arrives is about one shard's worth of records, spread over nb buckets
+    u32 rcap = learned && P->bk_dist_rcap ? P->bk_dist_rcap : (u32)((double)scap * nranks / 1.5 / nb * 1.5) + 64;
     u64 h[8] = {0};
     u32 retries = 0, launches = 0;
     u32 cap = (env_u32("EULER_B200_BKT_CAP", 1536) + 255u) / 256u * 256u;
     if (P->bk_scatter_ms < 0.f) {   // asynchronous scatter: its events have completed by now (the caller synchronised on the exchange)
         if (cudaEventElapsedTime(&P->bk_scatter_ms, ctx->ev[0], ctx->ev[1]) != cudaSuccess) { P->bk_scatter_ms = 0.f; cudaGetLastError(); }
     }
+    const u64 *d_counts = (const u64 *)((const char *)d_area + bkt_stream_bytes(nranks, scap));
+    bool need_regroup = true;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[7], s));
     while (true) {
+        if ((u64)nb * rcap * 16 > (64ull << 30)) return euler_fail(ctx, EULER_ERR_NOMEM, "bucket regions of %u x %u records do not fit", nb, rcap);
+        EULER_TRY(dev_reserve(ctx, P->bk_records, (size_t)nb * rcap * 16 + 16));
+        EULER_TRY(P->bk_cursors.reserve(ctx, nb));
         EULER_TRY(dev_reserve(ctx, P->bk_state, bkt_state_bytes(nb)));
         EULER_TRY(P->bk_bkeys.reserve(ctx, bcap)); EULER_TRY(P->bk_bvals.reserve(ctx, 2 * bcap));
         EULER_TRY(P->lkeys.reserve(ctx, ucap)); EULER_TRY(P->lvals.reserve(ctx, ucap)); EULER_TRY(P->loffs.reserve(ctx, ucap));
@@ -1471,9 +1483,14 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
         EULER_TRY(P->lstart.reserve(ctx, 4 * vcap + 4)); EULER_TRY(P->estart.reserve(ctx, 4 * vcap + 4));
         EULER_TRY(P->ev.reserve(ctx, vcap));
         CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr(), 0, 8 * sizeof(u64), s));
+        if (need_regroup) {
+            CUDA_TRY(ctx, cudaMemsetAsync(P->bk_cursors.ptr(), 0, (size_t)nb * sizeof(u32), s));
+            EULER_TRY(bkt_regroup(ctx, d_area, d_counts, nranks, scap, nb, rcap, P->bk_records.p, P->bk_cursors.ptr(), P->stats.ptr()));
+            launches++;
+            need_regroup = false;
+        }
         BktBuild bb;
-        bb.records = d_area; bb.counts = (const u32 *)((const char *)d_area + bkt_area_record_bytes(nb, nranks, rcap));
-        bb.nb = nb; bb.nranks = nranks; bb.rcap = rcap; bb.l = l; bb.cap = cap;
+        bb.records = P->bk_records.p; bb.counts = P->bk_cursors.ptr(); bb.nb = nb; bb.nranks = 1; bb.rcap = rcap; bb.l = l; bb.cap = cap;
         bb.lkeys = P->lkeys.ptr(); bb.lvals = P->lvals.ptr(); bb.loffs = P->loffs.ptr(); bb.ev1 = P->ev1.ptr(); bb.ev2 = P->ev2.ptr(); bb.ucap = ucap;
         bb.vkeys = P->vkeys.ptr(); bb.lcount = P->lcount.ptr(); bb.ecount = P->ecount.ptr(); bb.lstart = P->lstart.ptr();
         bb.estart = P->estart.ptr(); bb.ev = P->ev.ptr(); bb.vcap = vcap;
@@ -1481,15 +1498,17 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], s));
         EULER_TRY(bkt_build(ctx, bb));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
-        launches += 2;
+        launches += 3;
         EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 8));
         const u64 fl = h[2];
         if (fl & BKT_FLAG_INTERNAL) return euler_fail(ctx, EULER_ERR_STATE, "internal: bucketed build consistency check failed (flags %llx)", fl);
         if ((fl & BKT_FLAG_TABLE) && cap * 2 > BKT_MAX_CAP)
             return euler_fail(ctx, EULER_ERR_OVERFLOW, "a bucket does not fit its shared-memory table: partition again with more buckets per rank");
-        if (!(fl & (BKT_FLAG_TABLE | BKT_FLAG_OUTPUT | BKT_FLAG_BOUNDARY))) break;
-        if (++retries > 6) return euler_fail(ctx, EULER_ERR_OVERFLOW, "bucketed build: capacities did not settle");
-        if (fl & BKT_FLAG_TABLE) cap *= 2;   // a local decision (no re-partition across ranks): larger tables, fewer resident blocks
+        if (!(fl & (BKT_FLAG_REGION | BKT_FLAG_TABLE | BKT_FLAG_OUTPUT | BKT_FLAG_BOUNDARY))) break;
+        if (++retries > 8) return euler_fail(ctx, EULER_ERR_OVERFLOW, "bucketed build: capacities did not settle");
+        // every repair below is local to this rank (the streams stay where they are)
+        if (fl & BKT_FLAG_REGION) { rcap = (u32)(h[6] + h[6] / 8 + 16); need_regroup = true; }   // stats[6] = the fullest bucket
+        else if (fl & BKT_FLAG_TABLE) cap *= 2;   // larger tables, fewer resident blocks
         else if (fl & BKT_FLAG_OUTPUT) { ucap = h[3] + h[3] / 64 + 1024; vcap = h[4] + h[4] / 64 + 1024; }
         if (fl & BKT_FLAG_BOUNDARY) bcap *= 4;
     }
@@ -1498,7 +1517,7 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
     P->U_l = U_l; P->V = V; P->E = E;
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     P->have_graph = true;
-    P->bk_dist_key = key; P->bk_learned_u = U_l; P->bk_learned_v = V;
+    P->bk_dist_key = key; P->bk_learned_u = U_l; P->bk_learned_v = V; P->bk_dist_rcap = (u32)(h[6] + h[6] / 8 + 16);
     euler_stats &st = P->st;
     st.distinct_lmers = U_l; st.distinct_kmers = V; st.edge_count = E;
     st.lmer_table_capacity = (u64)nb * cap; st.kmer_table_capacity = (u64)nb * cap; st.retries = retries;

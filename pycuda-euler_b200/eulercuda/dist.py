@@ -285,7 +285,7 @@ BKT_CAP = 1536   # slots of a per-bucket shared-memory table (csrc/pipeline.cu d
 
 
 def plan_buckets(n_bases, l, world, distinct_hint=0, cap=None):
-    """(buckets per rank, records per (bucket, source) region) for shards of at most n_bases bases per rank.
+    """(buckets per rank, records per (destination, source) stream) for shards of at most n_bases bases per rank.
     distinct_hint = expected distinct canonical l-mers PER RANK (0 = unknown: every window distinct)."""
     cap = cap or int(os.environ.get("EULER_B200_BKT_CAP", BKT_CAP))
     k = l - 1
@@ -293,8 +293,8 @@ def plan_buckets(n_bases, l, world, distinct_hint=0, cap=None):
     rec_per_base = 2.0 / (w + 1.0) + 1.0 / 16.0 + 0.01
     est = int(distinct_hint) or max(int(n_bases), 1)
     nbpr = int(est * 1.06 / (0.30 * cap)) + 1
-    rcap = int(n_bases * rec_per_base / (world * nbpr) * 1.5) + 64
-    return nbpr, rcap
+    scap = int(n_bases * rec_per_base / world * 1.5) + 4096
+    return nbpr, scap
 
 
 class BucketExchange:
@@ -303,21 +303,21 @@ class BucketExchange:
     peers' areas opened through CUDA IPC.  Created collectively; `ok` is the COLLECTIVE outcome, so either every rank
     uses the object or none does."""
 
-    def __init__(self, ctx, rank, world, nb_per_rank, rcap, group=None):
+    def __init__(self, ctx, rank, world, nb_per_rank, scap, group=None):
         import torch
         import torch.distributed as dist
         self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
         props = [None] * world
-        dist.all_gather_object(props, (int(nb_per_rank), int(rcap)), group=group)
+        dist.all_gather_object(props, (int(nb_per_rank), int(scap)), group=group)
         self.nb_per_rank = max(p[0] for p in props)
-        self.rcap = max(p[1] for p in props)
+        self.scap = max(p[1] for p in props)
         self.phase = 0
         self.plan_key = (0, 0)   # (l, largest shard in bases) the geometry was planned for
         self.local, self.areas, self.opened = [None, None], [None, None], []
         handles, err = [None, None], None
         try:
             for which in (0, 1):
-                self.local[which], handles[which] = ctx.bkt_area_alloc(which, self.nb_per_rank, world, self.rcap)
+                self.local[which], handles[which] = ctx.bkt_area_alloc(which, world, self.scap)
         except Exception as e:   # reported to everyone below
             err = e
         table = [None] * world
@@ -352,12 +352,12 @@ class BucketExchange:
         self.opened = []
 
 
-def _bucket_exchange(ctx, rank, world, nbpr, rcap, group):
+def _bucket_exchange(ctx, rank, world, nbpr, scap, group):
     """the exchange object kept ON the context (closed with it), re-created collectively when the geometry grows"""
     bx = getattr(ctx, "_bucket_exchange", None)
     if bx is not None and bx.world == world and bx.ok:
         return bx
-    bx = BucketExchange(ctx, rank, world, nbpr, rcap, group)
+    bx = BucketExchange(ctx, rank, world, nbpr, scap, group)
     ctx._bucket_exchange = bx
     return bx
 
@@ -380,8 +380,8 @@ def build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, wo
         nmax = torch.tensor([int(n_bases)], dtype=torch.int64, device=dev)
         dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=group)
         n_plan = int(nmax.item())
-        nbpr, rcap = plan_buckets(n_plan, l, world, distinct_hint)
-        bx = _bucket_exchange(ctx, rank, world, nbpr, rcap, group)
+        nbpr, scap = plan_buckets(n_plan, l, world, distinct_hint)
+        bx = _bucket_exchange(ctx, rank, world, nbpr, scap, group)
         bx.plan_key = (int(l), n_plan)
         ctx._bucket_want = 0
     if not bx.ok:
@@ -389,9 +389,9 @@ def build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, wo
     which = bx.phase & 1
     bx.phase += 1
     words = _buffer("bkt_words", 8, dev)
-    ctx.bkt_scatter(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, rank, world, bx.nb_per_rank, bx.rcap, bx.areas[which],
+    ctx.bkt_scatter(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, rank, world, bx.nb_per_rank, bx.scap, bx.areas[which],
                     d_out=words.data_ptr())
-    # flags, largest region, wanted geometry, shard size, l: MAX over ranks.  The collective is also the barrier after
+    # flags, fullest stream, wanted geometry, shard size, l: MAX over ranks.  The collective is also the barrier after
     # which every rank's peer stores are complete (each rank's scatter precedes its contribution on its stream).
     extra = torch.tensor([getattr(ctx, "_bucket_want", 0), int(n_bases), int(l)], dtype=torch.int64, device=dev)
     msg = torch.cat([words[2:4], extra])
@@ -406,34 +406,35 @@ def build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, wo
         if _retry >= 4:
             raise RuntimeError("bucketed exchange: the geometry did not settle")
         if stale:
-            nbpr, rcap = plan_buckets(n_max, l, world, distinct_hint)
+            nbpr, scap = plan_buckets(n_max, l, world, distinct_hint)
         else:
             nbpr = want_all if regeom else bx.nb_per_rank
-            rcap = int(max(max_region, 16) * bx.nb_per_rank / nbpr * 1.25) + 64
+            scap = int(max_region * 1.25) + 4096 if (flags & 0x10) else bx.scap
         bx.close()
         bx.ok = False
         ctx._bucket_exchange = None
         ctx._bucket_want = 0
-        bx = _bucket_exchange(ctx, rank, world, nbpr, rcap, group)
+        bx = _bucket_exchange(ctx, rank, world, nbpr, scap, group)
         bx.plan_key = (int(l), n_max)
         if not bx.ok:
             return None
         return build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint, group, _retry + 1)
-    st = ctx.bkt_build(bx.local[which], l, rank, world, bx.nb_per_rank, bx.rcap, distinct_hint)
+    st = ctx.bkt_build(bx.local[which], l, rank, world, bx.nb_per_rank, bx.scap, distinct_hint)
     t2 = time.perf_counter()
     # geometry for the next steps from what was counted (reported at the next exchange, adopted by all ranks together)
     cap = int(os.environ.get("EULER_B200_BKT_CAP", BKT_CAP))
     ctx._bucket_want = int((st.distinct_lmers + 1) // 2 * 1.06 / (0.30 * cap)) + 1
     info = {"n_lmer_windows": n_l, "n_kmer_windows": n_k, "sent_keys": 0, "recv_keys": 0,
-            "exchange_bytes": int(16 * max_region * bx.nb_per_rank * (world - 1)),   # upper bound: largest region x regions sent to the peers
-            "exact_fallback": False, "transport": "16-byte minimizer-run records stored into the owners' bucket regions over NVLink (CUDA IPC)",
-            "geometry": {"nb_per_rank": bx.nb_per_rank, "rcap": bx.rcap, "max_region": max_region},
+            "exchange_bytes": int(16 * max_region * (world - 1)),   # upper bound: the fullest stream x the peers
+            "exact_fallback": False,
+            "transport": "16-byte minimizer-run records stored as runs into one stream per destination rank over NVLink (CUDA IPC), regrouped by the owner",
+            "geometry": {"nb_per_rank": bx.nb_per_rank, "scap": bx.scap, "fullest_stream": max_region, "fullest_bucket": int(st.bucket_records)},
             "phase_ms": {"partition+exchange": 1e3 * (t1 - t0), "build": 1e3 * (t2 - t1), "scatter_kernel": float(st.ms_count),
                          "build_kernel": float(st.ms_build_kernel)}}
     return st, info
 
 
-def emulate_partitioned_bucketed(ctx, shards, l, world, nb_per_rank=None, rcap=None):
+def emulate_partitioned_bucketed(ctx, shards, l, world, nb_per_rank=None, scap=None):
     """Single-process emulation of `world` ranks on one GPU (tests) through the entry points the production path
     uses (euler_bkt_scatter with one area per destination, euler_bkt_build per area).  Same return value as
     emulate_partitioned."""
@@ -441,26 +442,26 @@ def emulate_partitioned_bucketed(ctx, shards, l, world, nb_per_rank=None, rcap=N
     import _native as N
     n_max = max(int(off[-1]) for _, off in shards) if shards else 0
     a, b = plan_buckets(max(n_max, 1), l, world)
-    nbpr, rcap = nb_per_rank or a, rcap or b
+    nbpr, scap = nb_per_rank or a, scap or b
     while True:
-        nbytes = nbpr * world * rcap * 16 + nbpr * world * 4 + 256
+        nbytes = world * scap * 16 + world * 8 + 256
         areas = [torch.zeros(nbytes // 8 + 1, dtype=torch.int64, device="cuda") for _ in range(world)]
         ptrs = [t.data_ptr() for t in areas]
         windows, worst, overflow = [], 0, False
         for r, (buf, off) in enumerate(shards):
             d_buf = torch.from_numpy(np.ascontiguousarray(buf)).cuda() if len(buf) else torch.zeros(16, dtype=torch.uint8, device="cuda")
             d_off = torch.from_numpy(np.ascontiguousarray(off).astype(np.int64)).cuda()
-            out = ctx.bkt_scatter(d_buf.data_ptr(), d_off.data_ptr(), len(off) - 1, int(off[-1]), l, r, world, nbpr, rcap, ptrs)
+            out = ctx.bkt_scatter(d_buf.data_ptr(), d_off.data_ptr(), len(off) - 1, int(off[-1]), l, r, world, nbpr, scap, ptrs)
             overflow |= bool(int(out[2]) & 0x10)
             worst = max(worst, int(out[3]))
             windows.append((int(out[0]), int(out[1])))
         if not overflow:
             break
-        rcap = int(worst * 1.25) + 16     # what the production path does collectively (build_partitioned_bucketed)
+        scap = int(worst * 1.25) + 16     # what the production path does collectively (build_partitioned_bucketed)
     ctx.sync()
     res = []
     for d in range(world):
-        st = ctx.bkt_build(ptrs[d], l, d, world, nbpr, rcap, 0)
+        st = ctx.bkt_build(ptrs[d], l, d, world, nbpr, scap, 0)
         names = ("LMER_KEYS", "LMER_VALUES", "LMER_OFFSETS", "KMER_KEYS", "LCOUNT", "ECOUNT", "LSTART", "ESTART", "EV", "EDGE_V1", "EDGE_V2")
         art = {name: ctx.download(getattr(N, "ART_" + name)) for name in names}
         art["stats"] = st.as_dict()

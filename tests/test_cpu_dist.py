@@ -133,7 +133,7 @@ class _FakeCtx:
     def __init__(self, rank, fail_alloc=False, fail_open=False):
         self.rank, self.fail_alloc, self.fail_open, self.closed = rank, fail_alloc, fail_open, []
 
-    def bkt_area_alloc(self, which, nbpr, world, rcap):
+    def bkt_area_alloc(self, which, world, scap):
         if self.fail_alloc:
             raise RuntimeError("out of memory (injected)")
         return 0x1000 * (self.rank + 1) + which, bytes([self.rank, which]) * 32
@@ -165,7 +165,7 @@ def _handshake_worker(rank, world, port, q, mode):
         ctx = _FakeCtx(rank, fail_alloc=(mode == "alloc" and rank == 1), fail_open=(mode == "open" and rank == 0))
         bx = BucketExchange(ctx, rank, world, 10 + rank, 100 - rank)
         out["bucket_ok"] = bx.ok
-        out["geometry"] = (bx.nb_per_rank, bx.rcap)
+        out["geometry"] = (bx.nb_per_rank, bx.scap)
         px = _peer_exchange(ctx, rank, world, 64 + 2 * rank, None)
         out["peer"] = px is not None
         out["peer_again"] = _peer_exchange(ctx, rank, world, 64, None) is not None   # remembered, no second handshake
@@ -202,8 +202,8 @@ def test_transport_is_agreed_collectively(mode, port):
 def test_plan_buckets_pure():
     sys.path.insert(0, os.path.join(ROOT, "pycuda-euler_b200"))
     from eulercuda.dist import plan_buckets
-    nb1, rc1 = plan_buckets(138_000_000, 32, 1, 4_600_000, cap=1792)
-    assert 8000 < nb1 < 10000 and rc1 * nb1 * 16 < 2 * 10 ** 9
-    nb8, rc8 = plan_buckets(138_000_000, 32, 8, 5_290_000, cap=1792)
-    assert rc8 < rc1 and nb8 >= nb1
-    assert plan_buckets(0, 10, 2) == (1, 64)
+    nb1, sc1 = plan_buckets(138_000_000, 32, 1, 4_600_000, cap=1792)
+    assert 8000 < nb1 < 10000 and 15_000_000 < sc1 < 40_000_000      # ~0.16 records per base, x 1.5
+    nb8, sc8 = plan_buckets(138_000_000, 32, 8, 5_290_000, cap=1792)
+    assert sc8 * 8 < sc1 * 1.01 + 8 * 4096 and nb8 >= nb1
+    assert plan_buckets(0, 10, 2) == (1, 4096)
