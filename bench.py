@@ -390,6 +390,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra BASELINE configs (configs[2..4]) reported under `extra`")
+    ap.add_argument("--extra-scale", type=float, default=1.0,
+                    help="development aid: scale the genome of the extra configs (0.25 on 2 GPUs = the per-rank size of the 8-GPU run)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -414,7 +416,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that dies must not leave the others waiting for the default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=90))
 
     ctx = N.Context(local_rank)
     stream = torch.cuda.Stream()
@@ -520,22 +524,46 @@ def main():
     if not args.no_extra and args.workload == DEFAULT_WORKLOAD and args.scaling == "weak" and not args.k:
         plan = []
         if world == 1:
-            # configs[3] per-GPU share: 1/8 of the 1 Gbp genome at 30x on ONE GPU, the N = 1 point of the ">= 6x at 8 GPUs" target
-            plan.append(("1Gbp_150bp_30x_k31", dict(WORKLOADS["1Gbp_150bp_30x_k31"], G=125_000_000), False, "1/8 of configs[3] (125 Mbp, 150 bp, 30x) on one GPU"))
+            # configs[3] cut to what one GPU's u32 ids hold (E = 2 N_l < 2^32): 1/16 of the 1 Gbp genome at 30x, the single-GPU
+            # reference point for the 8-GPU run of configs[3] (16x this data set)
+            plan.append(("1Gbp_150bp_30x_k31", dict(WORKLOADS["1Gbp_150bp_30x_k31"], G=62_500_000), False, "1/16 of configs[3] (62.5 Mbp, 150 bp, 30x) on one GPU"))
+        sc = args.extra_scale
         if world >= 2:
-            plan.append(("100Mbp_150bp_40x_1pct_k31", dict(WORKLOADS["100Mbp_150bp_40x_1pct_k31"]), True, "configs[2], strong scaling"))
-        if world == 8:
-            plan.append(("1Gbp_150bp_30x_k31", dict(WORKLOADS["1Gbp_150bp_30x_k31"]), True, "configs[3], strong scaling"))
+            w3 = dict(WORKLOADS["100Mbp_150bp_40x_1pct_k31"])
+            w3["G"] = int(w3["G"] * sc)
+            plan.append(("100Mbp_150bp_40x_1pct_k31", w3, True, "configs[2], strong scaling" + ("" if sc == 1.0 else ", genome x %g" % sc)))
+        if world == 8 or sc != 1.0:
+            w4 = dict(WORKLOADS["1Gbp_150bp_30x_k31"])
+            w4["G"] = int(w4["G"] * sc)
+            plan.append(("1Gbp_150bp_30x_k31", w4, True, "configs[3], strong scaling" + ("" if sc == 1.0 else ", genome x %g" % sc)))
+        t_extra = time.perf_counter()
         for name, xwl, xstrong, note in plan:
             rec = {"workload": name, "note": note, "n_gpus": world, "scaling": "strong" if xstrong else "single"}
+            # every rank must take the same decisions here: elapsed time and failures are reduced over the ranks first
+            late = torch.tensor([1 if time.perf_counter() - t_extra > 150 else 0], dtype=torch.int64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(late, op=dist.ReduceOp.MAX)
+            if int(late.item()):
+                rec["skipped"] = "time budget of the extra configurations used up"
+                extra.append(rec)
+                continue
             try:
                 runner.free()
                 torch.cuda.empty_cache()
-                runner.load(xwl, xstrong)
+                err = None
+                try:
+                    runner.load(xwl, xstrong)
+                except Exception as e:   # e.g. out of memory on one rank: agreed below before any collective step
+                    err = e
+                bad = torch.tensor([0 if err is None else 1], dtype=torch.int64, device="cuda")
+                if dist is not None:
+                    dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+                if int(bad.item()):
+                    raise err if err is not None else RuntimeError("loading the workload failed on another rank")
                 xs = ClockSampler(local_rank)
                 xs.start()
-                xm = runner.measure(3, 2)
-                rec.update({"value": xm["nk_total"] / (xm["ms"] * 1e-3), "unit": UNIT, "ms_per_step": xm["ms"], "steps": 3, "warmup": 2,
+                xm = runner.measure(2, 1)
+                rec.update({"value": xm["nk_total"] / (xm["ms"] * 1e-3), "unit": UNIT, "ms_per_step": xm["ms"], "steps": 2, "warmup": 1,
                             "genome_bp": xwl["G"], "read_len": xwl["L"], "coverage": xwl["cov"], "err_ppm": xwl["err_ppm"], "k": xwl["k"],
                             "counts": {"n_kmer_windows": int(xm["nk_total"]), "distinct_lmers_rank0": int(xm["st"].distinct_lmers),
                                        "distinct_kmers_rank0": int(xm["st"].distinct_kmers), "edges_rank0": int(xm["st"].edge_count)},

@@ -205,6 +205,9 @@ struct WarpQueue {
     }
 };
 
+// L > 0 fixes the l-mer length at compile time (the benchmark lengths 32 and 22): masks and shift counts of the
+// rolling step become constants.  L == 0 reads it from the arguments.
+template <int L>
 __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const BkBuildArgs a)
 {
     extern __shared__ __align__(16) unsigned char bb_smem[];
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const u32 l = a.l, k = l - 1;
+    const u32 l = L > 0 ? (u32)L : a.l, k = l - 1;
     const u64 lmask = l >= 32 ? ~0ull : ((1ull << (2 * l)) - 1ull), kmask = lmask >> 2;
     const u32 top = 2 * (l - 1);
     WarpQueue wq;
@@ -721,7 +724,9 @@ int bkt_build(euler_ctx *ctx, const BktBuild &B)
     const size_t smem = bkt_build_smem(B.cap);
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(bkt_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(bkt_build_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(bkt_build_kernel<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(bkt_build_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
     // state: flag u32[nb] | work ticket, output ticket u32[2] | (16-byte aligned) agg_uv, agg_e, inc_uv, inc_e u64[nb]
@@ -739,7 +744,9 @@ int bkt_build(euler_ctx *ctx, const BktBuild &B)
     a.vkeys = B.vkeys; a.lcount = B.lcount; a.ecount = B.ecount; a.lstart = B.lstart; a.estart = B.estart; a.ev = B.ev; a.vcap = B.vcap;
     a.flag = flag; a.ticket = ticket; a.agg_uv = w64; a.agg_e = w64 + B.nb; a.inc_uv = w64 + 2ull * B.nb; a.inc_e = w64 + 3ull * B.nb;
     a.bkeys = B.bkeys; a.bvals = B.bvals; a.bcap = B.bcap; a.stats = B.stats;
-    bkt_build_kernel<<<B.nb, BB_THREADS, smem, ctx->stream>>>(a);
+    if (B.l == 32) bkt_build_kernel<32><<<B.nb, BB_THREADS, smem, ctx->stream>>>(a);
+    else if (B.l == 22) bkt_build_kernel<22><<<B.nb, BB_THREADS, smem, ctx->stream>>>(a);
+    else bkt_build_kernel<0><<<B.nb, BB_THREADS, smem, ctx->stream>>>(a);
     CUDA_TRY(ctx, cudaGetLastError());
     const unsigned g = (unsigned)ctx->num_sms * 8;
     bkt_boundary_publish_kernel<<<g, 256, 0, ctx->stream>>>(B.lkeys, B.ev1, B.ev2, B.stats + 3, B.ucap, B.l, B.bkeys, B.bvals, B.bcap, B.stats);

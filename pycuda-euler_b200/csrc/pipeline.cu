@@ -332,6 +332,7 @@ static u64 pow2_at_least(u64 x)
     return p;
 }
 #define EULER_FALLBACK 1   // internal: take the global-table path instead
+#define BKT_MAX_DISTINCT 50000000ull   // distinct canonical l-mers up to which the bucketed path is taken by default
 #define BKT_MAX_CAP 7424u   // 29 B per slot: the largest per-bucket table that fits one block's shared memory
 
 static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 distinct_hint, euler_stats *stats)
@@ -346,11 +347,21 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
     // geometry: buckets sized for a shared-memory table at ~45 % load
     const u32 cap = (env_u32("EULER_B200_BKT_CAP", 1536) + 255u) / 256u * 256u;   // 29 B per slot: 4 resident blocks per SM
     const bool learned = !distinct_hint && P->bk_learned_bases == B && P->bk_learned_l == l && P->bk_learned_nb;
-    u64 est_c = distinct_hint ? distinct_hint : (learned ? (P->bk_learned_u + 1) / 2 : (B ? B : 1));
+    // a previous run of the same reads through the global-table path has left its distinct count as well
+    const bool learned_gt = !distinct_hint && !learned && P->learned_bases == B && P->learned_lc;
+    u64 est_c = distinct_hint ? distinct_hint : (learned ? (P->bk_learned_u + 1) / 2 : (learned_gt ? P->learned_lc : (B ? B : 1)));
     const char *le = getenv("EULER_B200_BKT_LOAD");
     const double per_bucket = (le && atof(le) > 0.05 && atof(le) < 0.9 ? atof(le) : 0.30) * (double)cap;   // mean table load (linear probing)
     u64 nb64 = learned ? P->bk_learned_nb : (u64)((double)est_c * 1.06 / per_bucket) + 1;
     if (const u32 f = env_u32("EULER_B200_BKT_NB", 0)) nb64 = f;
+    // Where the bucketed path pays: tables whose buckets stay few enough for the 12-mer minimizers to balance them and
+    // for the scattered 16-byte record stores to stay inside the TLB reach (measured: 1.25e8 distinct l-mers -> 3.3e5
+    // buckets with a 5x spread of the bucket sizes and a 59 GB record area).  Larger tables take the round-1 path
+    // (global tables, L2-blocked); EULER_B200_BUCKETED=2 forces the bucketed path at any size.
+    {
+        const char *e = getenv("EULER_B200_BUCKETED");
+        if (!(e && atoi(e) == 2) && est_c > BKT_MAX_DISTINCT) return EULER_FALLBACK;
+    }
     if (nb64 > (1ull << 24)) return EULER_FALLBACK;
     u32 nb = (u32)nb64;
     // records: one per minimizer run cut at 16-base chunk boundaries, plus the orphans
@@ -359,9 +370,9 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
     u32 rcap = learned && P->bk_learned_rcap ? P->bk_learned_rcap
                                             : (u32)((double)B * rec_per_base / nb * 1.5) + 64;
     // artefact capacities: known from a hint or the last run of this input, else a first build only counts
-    u64 ucap = distinct_hint ? 2 * est_c + est_c / 4 + 1024 : (learned ? P->bk_learned_u + P->bk_learned_u / 64 + 1024 : 0);
-    u64 vcap = distinct_hint ? 2 * est_c + est_c / 4 + 1024 : (learned ? P->bk_learned_v + P->bk_learned_v / 64 + 1024 : 0);
-    u64 bcap = pow2_at_least((distinct_hint || learned ? est_c / 6 : est_c / 16) + 1024);
+    u64 ucap = (distinct_hint || learned_gt) ? 2 * est_c + est_c / 4 + 1024 : (learned ? P->bk_learned_u + P->bk_learned_u / 64 + 1024 : 0);
+    u64 vcap = (distinct_hint || learned_gt) ? 2 * est_c + est_c / 4 + 1024 : (learned ? P->bk_learned_v + P->bk_learned_v / 64 + 1024 : 0);
+    u64 bcap = pow2_at_least((distinct_hint || learned || learned_gt ? est_c / 6 : est_c / 16) + 1024);
 
     u64 h[8] = {0};
     u32 retries = 0, launches = 0;

@@ -186,7 +186,13 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
     import torch
     import torch.distributed as dist
     dev = d_reads.device
-    if world > 1 and l <= 32 and use_peer and os.environ.get("EULER_B200_DIST_KEYS", "0") != "1":
+    # The record exchange + per-bucket build is the fast path while a rank's table stays in the small-bucket regime
+    # (a known distinct count of at most BKT_MAX_DISTINCT canonical l-mers per rank; the caller's hint is the same on
+    # every rank, so the choice is collective).  Larger or unknown tables take the key exchange below with its L2-blocked
+    # global tables.  EULER_B200_DIST_KEYS=1 / 0 forces the one or the other.
+    forced = os.environ.get("EULER_B200_DIST_KEYS")
+    bucketed = (0 < int(distinct_hint) <= BKT_MAX_DISTINCT) if forced is None else forced == "0"
+    if world > 1 and l <= 32 and use_peer and bucketed:
         res = build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint, group)
         if res is not None:
             return res
@@ -282,6 +288,7 @@ def build_partitioned(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, dist
 # runs (16-byte records of up to 17 l-mers), stored by the partition kernel straight into the owners' bucket
 # regions; the owner then builds every bucket in shared memory.  Used for l <= 32.
 BKT_CAP = 1536   # slots of a per-bucket shared-memory table (csrc/pipeline.cu default)
+BKT_MAX_DISTINCT = 50_000_000   # per-rank distinct canonical l-mers up to which the bucketed path is taken by default
 
 
 def plan_buckets(n_bases, l, world, distinct_hint=0, cap=None):
@@ -389,16 +396,24 @@ def build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, wo
     which = bx.phase & 1
     bx.phase += 1
     words = _buffer("bkt_words", 8, dev)
-    ctx.bkt_scatter(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, rank, world, bx.nb_per_rank, bx.scap, bx.areas[which],
-                    d_out=words.data_ptr())
+    serr = None
+    try:
+        ctx.bkt_scatter(d_reads.data_ptr(), d_off.data_ptr(), nreads, n_bases, l, rank, world, bx.nb_per_rank, bx.scap, bx.areas[which],
+                        d_out=words.data_ptr())
+    except Exception as e:   # reported through the collective below: every rank raises, nobody waits
+        serr = e
+        words.zero_()
     # flags, fullest stream, wanted geometry, shard size, l: MAX over ranks.  The collective is also the barrier after
     # which every rank's peer stores are complete (each rank's scatter precedes its contribution on its stream).
-    extra = torch.tensor([getattr(ctx, "_bucket_want", 0), int(n_bases), int(l)], dtype=torch.int64, device=dev)
+    extra = torch.tensor([getattr(ctx, "_bucket_want", 0), int(n_bases), int(l), 0 if serr is None else 1], dtype=torch.int64, device=dev)
     msg = torch.cat([words[2:4], extra])
     dist.all_reduce(msg, op=dist.ReduceOp.MAX, group=group)
     host = torch.cat([words[:2], msg]).cpu().numpy()   # the one host round trip between scatter and build
     t1 = time.perf_counter()
-    n_l, n_k, flags, max_region, want_all, n_max, l_max = (int(x) for x in host)
+    n_l, n_k, flags, max_region, want_all, n_max, l_max, failed = (int(x) for x in host)
+    if failed:
+        raise RuntimeError("bucketed scatter failed on rank %d: %s" % (rank, serr) if serr is not None
+                           else "bucketed scatter failed on another rank")
     stale = bx.plan_key[0] != l_max or n_max > 2 * bx.plan_key[1] or 2 * n_max < bx.plan_key[1]   # planned for another workload
     regeom = want_all and (want_all > 2 * bx.nb_per_rank or 2 * want_all < bx.nb_per_rank)
     if (flags & 0x10) or stale or regeom:
@@ -419,7 +434,18 @@ def build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, wo
         if not bx.ok:
             return None
         return build_partitioned_bucketed(ctx, d_reads, d_off, nreads, n_bases, l, rank, world, distinct_hint, group, _retry + 1)
-    st = ctx.bkt_build(bx.local[which], l, rank, world, bx.nb_per_rank, bx.scap, distinct_hint)
+    # the build can fail on ONE rank (memory, a bucket that does not fit shared memory): the outcome is made
+    # collective before anyone moves on, or the other ranks would wait for it in the next collective for ever
+    st, err = None, None
+    try:
+        st = ctx.bkt_build(bx.local[which], l, rank, world, bx.nb_per_rank, bx.scap, distinct_hint)
+    except Exception as e:
+        err = e
+    okw = torch.tensor([0 if err is None else 1], dtype=torch.int64, device=dev)
+    dist.all_reduce(okw, op=dist.ReduceOp.MAX, group=group)
+    if int(okw.item()):
+        raise RuntimeError("bucketed build failed on rank %d: %s" % (rank, err) if err is not None
+                           else "bucketed build failed on another rank")
     t2 = time.perf_counter()
     # geometry for the next steps from what was counted (reported at the next exchange, adopted by all ranks together)
     cap = int(os.environ.get("EULER_B200_BKT_CAP", BKT_CAP))
