@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """TEST / BENCH INFRASTRUCTURE ONLY.  Byte-compile the UNMODIFIED reference CPU assembler
-(/root/reference/src/referenceassembler/referenceAssembler.py) into oracle/_ref/referenceAssembler.pyc.
+(/root/reference/src/referenceassembler/referenceAssembler.py) into oracle/_ref/referenceAssembler.bytecode.
 
 The reference path is pure Python: there is nothing for gcc to build.  Its compiled form is CPython bytecode,
 so that is what goes into oracle/_ref/ (git-ignored, but shipped to the GPU box like the built .so files): the
@@ -14,7 +14,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = "/root/reference/src/referenceassembler/referenceAssembler.py"
-OUT = os.path.join(HERE, "_ref", "referenceAssembler.pyc")
+OUT = os.path.join(HERE, "_ref", "referenceAssembler.bytecode")
 
 
 def build(force=False):

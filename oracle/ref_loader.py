@@ -10,7 +10,7 @@ import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = "/root/reference/src/referenceassembler/referenceAssembler.py"
-PYC = os.path.join(HERE, "_ref", "referenceAssembler.pyc")
+PYC = os.path.join(HERE, "_ref", "referenceAssembler.bytecode")
 _mod = None
 
 
