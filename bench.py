@@ -305,18 +305,62 @@ class Runner:
         ms = e0.elapsed_time(e1) / steps
         if self.world > 1:
             st.n_kmer_windows, st.n_lmer_windows, st.n_bases = info["n_kmer_windows"], info["n_lmer_windows"], self.R * self.wl["L"]
-        vals = torch.tensor([ms, part_ms / steps, build_ms / steps, wall], dtype=torch.float64, device="cuda")
+        vals = torch.tensor([ms, part_ms / steps, build_ms / steps, wall, float(st.retries), float(st.redo_buckets)],
+                            dtype=torch.float64, device="cuda")
         tot = torch.tensor([float(st.n_kmer_windows), float(launches)], dtype=torch.float64, device="cuda")
+        per_rank = None
+        if self.dist is not None:   # what every rank saw, before the MAX: ms, partition, build, wall, retries, second-pass buckets
+            mine = torch.cat([vals, torch.tensor([graph_ms / steps, float(st.bucket_records), float(st.distinct_lmers)],
+                                                 dtype=torch.float64, device="cuda")])
+            allr = [torch.empty_like(mine) for _ in range(self.world)]
+            self.dist.all_gather(allr, mine)
+            per_rank = [[round(float(x), 3) for x in t.tolist()] for t in allr]
         if self.dist is not None:
             self.dist.all_reduce(vals, op=self.dist.ReduceOp.MAX)
             self.dist.all_reduce(tot, op=self.dist.ReduceOp.SUM)
-        ms_max, part_max, build_max, wall_max = (float(x) for x in vals.tolist())
+        ms_max, part_max, build_max, wall_max, retries_max, redo_max = (float(x) for x in vals.tolist())
         nk_total, launches_total = (float(x) for x in tot.tolist())
         return {"st": st, "info": info, "ms": ms_max, "part_ms": part_max, "build_ms": build_max, "graph_ms": graph_ms / steps,
-                "wall_ms": wall_max, "per_step": per_step, "nk_total": nk_total, "launches": int(launches_total)}
+                "wall_ms": wall_max, "per_step": per_step, "nk_total": nk_total, "launches": int(launches_total),
+                "retries": int(retries_max), "redo_buckets": int(redo_max), "per_rank": per_rank}
 
     def free(self):
         self.d_reads = self.d_off = None
+
+
+class LineGuard:
+    """Prints the JSON line exactly once.  If the main thread has not called finish() within `seconds`, the guard
+    prints the line as it stands (marked incomplete) and ends the process with status 0; with line None it only
+    ends the process.  Every rank runs one, so a stalled rank cannot keep the others (or the launcher) waiting."""
+
+    def __init__(self, seconds, line):
+        self.seconds, self.line = seconds, line
+        self.lock, self.done, self.ev = threading.Lock(), False, threading.Event()
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def _run(self):
+        if self.ev.wait(self.seconds):
+            return
+        with self.lock:
+            if self.done:
+                return
+            self.done = True
+            if self.line is not None:
+                self.line["incomplete"] = "a phase after the timed steps did not finish within %d s; printed by the watchdog" % self.seconds
+                try:
+                    print(json.dumps(self.line), flush=True)
+                except Exception:   # the main thread was adding a key: the headline part is what matters
+                    print(json.dumps({k: v for k, v in list(self.line.items()) if k not in ("e2e", "extra", "cpu_baseline")}), flush=True)
+        os._exit(0)
+
+    def finish(self, line):
+        with self.lock:
+            if self.done:
+                return
+            self.done = True
+            if line is not None:
+                print(json.dumps(line), flush=True)
+        self.ev.set()
 
 
 def parity_check_partitioned(runner):
@@ -447,9 +491,52 @@ def main():
         m0 = runner.measure(max(3, args.steps // 4), 2, hint=0)
         nohint = {"ms_per_step": m0["ms"], "value": m0["nk_total"] / (m0["ms"] * 1e-3)}
 
+    # The headline numbers are in hand: from here on (end-to-end steps, the extra configurations) a stall must not
+    # cost the line.  A watchdog on every rank prints what there is (rank 0) and leaves, before the NCCL timeout would
+    # abort the processes.
+    line = None
+    if rank == 0:
+        roof = roofline_record(st, m["part_ms"], m["build_ms"], ms_max, l, args.workload, world)
+        per_step = m["per_step"]
+        line = {
+            "metric": METRIC, "value": m["nk_total"] / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "u64" if l <= 32 else "u128", "data": "synthetic",
+            "config": {
+                "workload": args.workload, "genome_bp": wl["G"], "read_len": L, "coverage": wl["cov"], "err_ppm": wl["err_ppm"],
+                "k": k, "reads_per_gpu": R, "bases_per_gpu": R * L,
+                "parallelism": "1 GPU" if world == 1 else
+                "%d GPUs: reads sharded, k-mer space partitioned by the minimizer of each vertex, one exchange (see dist.transport)" % world,
+                "genome_bp_total": G,
+                "l2": "inputs (%d MB ASCII) and the record regions written / re-read every step exceed the 126 MB L2" % (R * L // 10 ** 6),
+                "distinct_hint": hint, "ids": "bucket order (canonical-id sort not in the timed region)",
+                "path": "minimizer-bucketed (partition pass + per-bucket shared-memory build)" if st.path == 1 else "global table (round 1)",
+                "buckets": int(st.n_buckets),
+                "timing": "CUDA events on the library's stream around the K steps, max over ranks",
+            },
+            "counts": {"n_kmer_windows": int(st.n_kmer_windows), "n_lmer_windows": int(st.n_lmer_windows),
+                       "distinct_lmers": int(st.distinct_lmers), "distinct_kmers": int(st.distinct_kmers),
+                       "edges": int(st.edge_count), "retries": m["retries"], "second_pass_buckets": m["redo_buckets"]},
+            "stage_ms": {"partition_kernel": m["part_ms"], "build_kernel": m["build_ms"], "step_wall": m["wall_ms"],
+                         "step_median": sorted(per_step)[len(per_step) // 2], "step_best": min(per_step)},
+            "roofline": roof,
+            "clocks": clocks,
+            "gpu_launches": m["launches"],
+        }
+        if nohint:
+            line["no_hint"] = nohint
+        if parity is not None:
+            line["parity_check"] = parity
+        if m.get("per_rank"):
+            line["per_rank"] = {"columns": ["ms_per_step", "partition_kernel_ms", "build_kernel_ms", "step_wall_ms", "retries",
+                                            "second_pass_buckets", "graph_ms", "fullest_bucket", "distinct_lmers"], "rows": m["per_rank"]}
+        if world > 1 and info:
+            line["dist"] = {kk: info[kk] for kk in ("exchange_bytes", "exact_fallback", "transport", "phase_ms", "geometry") if kk in info}
+    guard = LineGuard(80.0 if world > 1 else 240.0, line)
+
     # ---- e2e: host buffers through the reference-facing C-ABI call, copies inside the timed region
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         d_reads, d_off = runner.d_reads, runner.d_off
         h_reads = torch.empty(R * L, dtype=torch.uint8, pin_memory=True)
         h_reads.copy_(d_reads)
@@ -459,11 +546,18 @@ def main():
         arts = [N.ART_LMER_KEYS, N.ART_LMER_VALUES, N.ART_LMER_OFFSETS, N.ART_EDGE_V1, N.ART_EDGE_V2, N.ART_EV]
         width = {N.ART_LMER_KEYS: 8, N.ART_LMER_VALUES: 4, N.ART_LMER_OFFSETS: 4, N.ART_EDGE_V1: 4, N.ART_EDGE_V2: 4,
                  N.ART_EV: 24}
-        cap_items = int(max(st.distinct_lmers, st.distinct_kmers) * 1.05) + 1024
+        cap_items = int(max(st.distinct_lmers, st.distinct_kmers) * (1.05 if world == 1 else 1.15)) + 1024
         h_out = {a: torch.empty(cap_items * width[a], dtype=torch.uint8, pin_memory=True) for a in arts}
 
         def e2e_step(c=ctx, out=h_out):
-            s = c.run_host_ptr(h_reads.data_ptr(), h_off.data_ptr(), R, l, 0, hint)
+            if world > 1:   # this rank's shard in from pinned host memory, the partitioned build, this rank's part of the graph out
+                from eulercuda.dist import build_partitioned
+                with torch.cuda.stream(stream):
+                    d_reads.copy_(h_reads, non_blocking=True)
+                    d_off.copy_(h_off, non_blocking=True)
+                    s, _ = build_partitioned(c, d_reads, d_off, R, R * L, l, rank, world, hint)
+            else:
+                s = c.run_host_ptr(h_reads.data_ptr(), h_off.data_ptr(), R, l, 0, hint)
             nb = 0
             for a in arts:
                 nb += c.download_into(a, out[a].data_ptr(), out[a].numel())
@@ -482,42 +576,47 @@ def main():
         runner.barrier()
         e2e_wall = 1e3 * (time.perf_counter() - t0) / args.steps
         serial_ms = max(e0.elapsed_time(e1) / args.steps, e2e_wall)  # the call returns synchronously: wall is the truth
-        # Two contexts (two streams, two host threads) alternate steps, so the PCIe copies of one step
-        # overlap the kernels and the opposite-direction copy of the other; every step still moves its own
-        # inputs in and its own result out inside the timed region.
-        ctx_b = N.Context(local_rank)
-        h_out_b = {a: torch.empty(cap_items * width[a], dtype=torch.uint8, pin_memory=True) for a in arts}
-        for _ in range(2):
-            e2e_step(ctx_b, h_out_b)
-        nsteps2 = max(2, args.steps + (args.steps & 1))
-        errs = []
+        piped_ms = serial_ms
+        if world == 1:
+            # Two contexts (two streams, two host threads) alternate steps, so the PCIe copies of one step
+            # overlap the kernels and the opposite-direction copy of the other; every step still moves its own
+            # inputs in and its own result out inside the timed region.
+            ctx_b = N.Context(local_rank)
+            h_out_b = {a: torch.empty(cap_items * width[a], dtype=torch.uint8, pin_memory=True) for a in arts}
+            for _ in range(2):
+                e2e_step(ctx_b, h_out_b)
+            nsteps2 = max(2, args.steps + (args.steps & 1))
+            errs = []
 
-        def worker(c, out):
-            try:
-                for _ in range(nsteps2 // 2):
-                    e2e_step(c, out)
-            except Exception as exc:   # surfaced below: a failed step must not look like a fast one
-                errs.append(exc)
+            def worker(c, out):
+                try:
+                    for _ in range(nsteps2 // 2):
+                        e2e_step(c, out)
+                except Exception as exc:   # surfaced below: a failed step must not look like a fast one
+                    errs.append(exc)
 
-        runner.barrier()
-        th = [threading.Thread(target=worker, args=(ctx, h_out)), threading.Thread(target=worker, args=(ctx_b, h_out_b))]
-        t0 = time.perf_counter()
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        torch.cuda.synchronize()
-        piped_ms = 1e3 * (time.perf_counter() - t0) / nsteps2
-        if errs:
-            raise errs[0]
-        ctx_b.close()
+            runner.barrier()
+            th = [threading.Thread(target=worker, args=(ctx, h_out)), threading.Thread(target=worker, args=(ctx_b, h_out_b))]
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            torch.cuda.synchronize()
+            piped_ms = 1e3 * (time.perf_counter() - t0) / nsteps2
+            if errs:
+                raise errs[0]
+            ctx_b.close()
         e2e = {"ms": min(serial_ms, piped_ms), "serial_ms": serial_ms, "piped_ms": piped_ms, "h2d": int(R * L + (R + 1) * 8),
                "d2h": int(d2h)}
-        del h_reads, h_off, h_out, h_out_b
+        del h_reads, h_off, h_out
     e2e_t = torch.tensor([e2e["ms"] if e2e else 0.0], dtype=torch.float64, device="cuda")
+    e2e_b = torch.tensor([e2e["h2d"], e2e["d2h"]] if e2e else [0, 0], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_b, op=dist.ReduceOp.SUM)   # bytes of the whole job: every rank copies its own shard in and its own part out
     e2e_ms_max = float(e2e_t.item())
+    e2e_h2d, e2e_d2h = (int(x) for x in e2e_b.tolist())
 
     # ---- the other BASELINE configs, reported under `extra` (every rank takes part; rank 0 prints)
     extra = []
@@ -576,46 +675,20 @@ def main():
             extra.append(rec)
 
     if rank == 0:
-        roof = roofline_record(st, m["part_ms"], m["build_ms"], ms_max, l, args.workload, world)
-        per_step = m["per_step"]
-        line = {
-            "metric": METRIC, "value": m["nk_total"] / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
-            "vs_baseline": None, "dtype": "u64" if l <= 32 else "u128", "data": "synthetic",
-            "config": {
-                "workload": args.workload, "genome_bp": wl["G"], "read_len": L, "coverage": wl["cov"], "err_ppm": wl["err_ppm"],
-                "k": k, "reads_per_gpu": R, "bases_per_gpu": R * L,
-                "parallelism": "1 GPU" if world == 1 else
-                "%d GPUs: reads sharded, k-mer space partitioned by the minimizer of each vertex, one exchange (see dist.transport)" % world,
-                "genome_bp_total": G,
-                "l2": "inputs (%d MB ASCII) and the record regions written / re-read every step exceed the 126 MB L2" % (R * L // 10 ** 6),
-                "distinct_hint": hint, "ids": "bucket order (canonical-id sort not in the timed region)",
-                "path": "minimizer-bucketed (partition pass + per-bucket shared-memory build)" if st.path == 1 else "global table (round 1)",
-                "buckets": int(st.n_buckets),
-                "timing": "CUDA events on the library's stream around the K steps, max over ranks",
-            },
-            "counts": {"n_kmer_windows": int(st.n_kmer_windows), "n_lmer_windows": int(st.n_lmer_windows),
-                       "distinct_lmers": int(st.distinct_lmers), "distinct_kmers": int(st.distinct_kmers),
-                       "edges": int(st.edge_count), "retries": int(st.retries)},
-            "stage_ms": {"partition_kernel": m["part_ms"], "build_kernel": m["build_ms"], "step_wall": m["wall_ms"],
-                         "step_median": sorted(per_step)[len(per_step) // 2], "step_best": min(per_step)},
-            "roofline": roof,
-            "clocks": clocks,
-            "gpu_launches": m["launches"],
-        }
-        if nohint:
-            line["no_hint"] = nohint
-        if parity is not None:
-            line["parity_check"] = parity
-        if world > 1 and info:
-            line["dist"] = {kk: info[kk] for kk in ("exchange_bytes", "exact_fallback", "transport", "phase_ms", "geometry") if kk in info}
         if e2e:
             line["e2e"] = {"value": m["nk_total"] / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
-                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "api": "euler_pipeline_run_host + euler_pipeline_download (compressed graph)",
-                           "serial_ms_per_step": e2e["serial_ms"], "pipelined_ms_per_step": e2e["piped_ms"],
-                           "pipelining": "2 contexts on 2 host threads alternate steps (copies of one overlap the kernels of the other); "
-                                         "serial_ms_per_step is one context, one step at a time"}
+                           "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h}
+            if world == 1:
+                line["e2e"].update({
+                    "api": "euler_pipeline_run_host + euler_pipeline_download (compressed graph)",
+                    "serial_ms_per_step": e2e["serial_ms"], "pipelined_ms_per_step": e2e["piped_ms"],
+                    "pipelining": "2 contexts on 2 host threads alternate steps (copies of one overlap the kernels of the other); "
+                                  "serial_ms_per_step is one context, one step at a time"})
+            else:
+                line["e2e"].update({
+                    "api": "per rank: pinned host shard -> device, eulercuda.dist.build_partitioned, euler_pipeline_download of the rank's "
+                           "part of the compressed graph; wall clock between barriers, max over ranks; bytes summed over ranks",
+                    "pipelining": "none (one step at a time)"})
         if extra:
             line["extra"] = extra
         if world == 1 and not args.no_cpu:
@@ -624,13 +697,14 @@ def main():
                 import subprocess
                 out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
                                       "--workload", args.workload] + (["--k", str(args.k)] if args.k else []),
-                                     capture_output=True, text=True, timeout=600)
+                                     capture_output=True, text=True, timeout=180)
                 ref = json.loads(out.stdout.strip().splitlines()[-1])
                 line["cpu_baseline"] = dict(ref["cpu_baseline"], code=ref["config"]["code"])
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "unavailable",
                                         "sample": "reference arm failed: %s" % e}
-        print(json.dumps(line))
+    guard.finish(line)
+    LineGuard(30.0, None)   # the shutdown (barrier, NCCL teardown) must not keep a finished run alive
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -183,7 +183,7 @@ typedef struct {
     float ms_build_kernel;
     uint32_t path;                        /* 0 = global-table path (round 1), 1 = minimizer-bucketed path */
     uint32_t n_buckets;                   /* buckets of the last run */
-    uint32_t pad_;
+    uint32_t redo_buckets;     /* bucketed path: buckets rebuilt by the second pass (they overflowed the first pass's tables) */
     uint64_t bucket_records;              /* largest number of 16-byte records in one bucket region */
 } euler_stats;
 

@@ -45,7 +45,7 @@ class Stats(C.Structure):
                 ("kmer_table_capacity", C.c_uint64), ("retries", C.c_uint32),
                 ("ms_count", C.c_float), ("ms_graph", C.c_float), ("ms_total", C.c_float),
                 ("ms_count_kernel", C.c_float), ("kernel_launches", C.c_uint32),
-                ("ms_build_kernel", C.c_float), ("path", C.c_uint32), ("n_buckets", C.c_uint32), ("pad_", C.c_uint32),
+                ("ms_build_kernel", C.c_float), ("path", C.c_uint32), ("n_buckets", C.c_uint32), ("redo_buckets", C.c_uint32),
                 ("bucket_records", C.c_uint64)]
 
     def as_dict(self):

@@ -23,6 +23,9 @@
 #include "kernels.h"
 
 #define BB_THREADS 256
+#ifndef BB_PROBE_LIMIT
+#define BB_PROBE_LIMIT 128u   // probes after which the first pass hands a bucket to the second
+#endif
 #define BB_WARPS (BB_THREADS / 32)
 #ifndef BB_STEPS
 #define BB_STEPS 2   // l-mers a lane rolls between two refills
@@ -52,6 +55,8 @@ struct BkBuildArgs {
     u64 *lkeys; u32 *lvals, *loffs, *ev1, *ev2; u64 ucap;
     u64 *vkeys; u32 *lcount, *ecount, *lstart, *estart; euler_vertex *ev; u64 vcap;
     u32 *flag; u64 *agg_uv, *agg_e, *inc_uv, *inc_e; u32 *ticket;
+    u32 *redo;           // [0] number of buckets that did not fit the first pass's tables, [1 + i] their ids
+    u32 second;          // the second pass: block i rebuilds bucket redo[1 + i] with the largest tables
     u64 *bkeys; u32 *bvals; u64 bcap;
     u64 *stats;
 };
@@ -83,12 +88,14 @@ __device__ __forceinline__ void st_vol_u64(u64 *p, u64 v) { asm volatile("st.vol
 
 // Slots are never freed, so the first EMPTY slot ends a search.  One exit per function: with early returns the compiler
 // duplicated the caller's tail per return point and the warp ran it once per group of lanes.
-// insert: returns the slot, 0xffffffff when the table is full; first = this call claimed the slot.
-__device__ __forceinline__ u32 sm_insert(u64 *keys, u32 cap, u64 key, bool &first)
+// insert: returns the slot, 0xffffffff when `limit` probes did not find the key or a free slot (a table that is full,
+// or so full that linear probing has degenerated: the bucket then goes to the second pass); first = this call claimed
+// the slot.
+__device__ __forceinline__ u32 sm_insert(u64 *keys, u32 cap, u64 key, bool &first, u32 limit)
 {
     u32 h = bb_home(key, cap), slot = 0xffffffffu;
     first = false;
-    for (u32 probe = 0; probe < cap; probe++) {
+    for (u32 probe = 0; probe < limit; probe++) {
         u64 cur = keys[h];
         if (cur == EULER_EMPTY_KEY) {
             cur = atomicCAS(keys + h, EULER_EMPTY_KEY, key);
@@ -231,11 +238,27 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
     WarpQueue wq;
     wq.q = s_queue[warp];
     wq.n = 0;
+    // A bucket several times the mean size fills its table to the point where every insert walks hundreds of slots and
+    // one block holds up the whole grid (measured: 4.9 ms instead of 1.9 ms on the rank that owned such a bucket).
+    // The first pass therefore gives up on a bucket after BB_PROBE_LIMIT probes; the second pass probes to the end.
+    const u32 plimit = a.second ? cap : (cap < BB_PROBE_LIMIT ? cap : BB_PROBE_LIMIT);
 
 #ifdef BKT_TIMING
     long long tick_ = clock64();
 #endif
-    if (tid == 0) { s_bucket = atomicAdd(a.ticket, 1u); s_fail = 0; }   // which bucket this block builds
+    if (tid == 0) {   // which bucket this block builds
+        if (a.second) {
+            const u32 nredo = a.redo[0] < BKT_REDO_CAP ? a.redo[0] : BKT_REDO_CAP;
+            if (blockIdx.x == 0) a.stats[7] = a.redo[0];   // how many buckets the first pass handed over
+            s_bucket = blockIdx.x < nredo ? a.redo[1 + blockIdx.x] : 0xffffffffu;
+        } else {
+            s_bucket = atomicAdd(a.ticket, 1u);
+        }
+        s_fail = 0;
+    }
+    __syncthreads();
+    const u32 b = s_bucket;
+    if (b >= a.nb) return;   // second pass: nothing (more) to redo
     {
         const ulonglong2 e2 = make_ulonglong2(EULER_EMPTY_KEY, EULER_EMPTY_KEY);
         for (u32 i = tid; i < cap; i += BB_THREADS) reinterpret_cast<ulonglong2 *>(lt_keys)[i] = e2;   // lt_keys and vt_keys are adjacent
@@ -243,8 +266,6 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
         for (u32 i = tid; i < 13 * cap / 16; i += BB_THREADS) reinterpret_cast<uint4 *>(lt_cnt)[i] = z;   // counts, vertex words, masks
     }
     __syncthreads();
-    const u32 b = s_bucket;
-    if (b >= a.nb) return;   // never: the grid is nb blocks
 
     BB_TICK(0);
     // ---- A: count the l-mers of the bucket's records ---------------------------------------------------------
@@ -254,8 +275,8 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
     auto count_slow = [&](ulonglong2 e, bool valid) {
         if (valid) {
             bool first;
-            const u32 slot = sm_insert(lt_keys, cap, e.x, first);
-            if (slot == 0xffffffffu) fail = true;
+            const u32 slot = sm_insert(lt_keys, cap, e.x, first, plimit);
+            if (slot == 0xffffffffu) fail = true;   // noted per lane and published after the loop: nothing warp-uniform may depend on it
             else atomicAdd(lt_cnt + slot, first ? (1u | ((u32)e.y << 30)) : 1u);
         }
     };
@@ -375,7 +396,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
             if (own_p) {   // strand c leaves prefix(c) with m0, last base t
                 const u64 p = c >> 2, rp = bk_revcomp(p, k);
                 const u32 t = (u32)c & 3u;
-                const u32 vs = sm_insert(vt_keys, cap, p < rp ? p : rp, first);
+                const u32 vs = sm_insert(vt_keys, cap, p < rp ? p : rp, first, plimit);
                 if (vs == 0xffffffffu) fail = true;
                 else {
                     atomicAdd((p <= rp) ? vt_a + vs : vt_b + vs, m0);   // p is the canonical strand (or a palindrome): its leaving total
@@ -386,7 +407,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
             if (own_s && !pal) {   // strand c enters suffix(c) with n, first base t (a palindromic l-mer is covered by its prefix side)
                 const u64 s = c & kmask, rs = bk_revcomp(s, k);
                 const u32 t = (u32)(c >> (2 * k)) & 3u;
-                const u32 vs = sm_insert(vt_keys, cap, s < rs ? s : rs, first);
+                const u32 vs = sm_insert(vt_keys, cap, s < rs ? s : rs, first, plimit);
                 if (vs == 0xffffffffu) fail = true;
                 else {
                     if (s == rs) atomicAdd(vt_a + vs, n);            // palindromic vertex: one strand, leaving total == entering total
@@ -445,7 +466,19 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
     // The output ticket is taken now, not at the start: every lower ticket belongs to a block that has already
     // reached this point, so its totals are published (or are a few instructions away) and nobody ever waits for
     // another block's counting.  The artefacts therefore come out in completion order of the buckets.
-    if (warp == 0) {
+    if (warp == 0 && failed) {
+        // A bucket that does not fit the tables takes no output ticket (the chain never sees it): it is listed and
+        // rebuilt by the second pass with the largest tables, its artefacts appended after everybody else's.
+        if (lane == 0) {
+            bool lost = true;
+            if (!a.second) {
+                const u32 i = atomicAdd(a.redo, 1u);
+                if (i < BKT_REDO_CAP) { a.redo[1 + i] = b; lost = false; }
+            }
+            if (lost) atomicOr((unsigned long long *)(a.stats + 2), (unsigned long long)BKT_FLAG_TABLE);
+            atomicMax((unsigned long long *)(a.stats + 6), (unsigned long long)max_region);
+        }
+    } else if (warp == 0) {
         u32 ticket = 0;
         if (lane == 0) ticket = atomicAdd(a.ticket + 1, 1u);
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
@@ -509,13 +542,11 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
         if (lane == 0) {
             s_base[0] = pre_uv;
             s_base[1] = pre_e;
-            if (ticket == a.nb - 1) {   // grand totals
-                a.stats[3] = (pre_uv + tot_uv) & 0xffffffffull;
-                a.stats[4] = (pre_uv + tot_uv) >> 32;
-                a.stats[5] = pre_e + tot_e;
-            }
+            // grand totals: the inclusive totals grow with the ticket, the last one to arrive leaves the maximum
+            atomicMax((unsigned long long *)(a.stats + 3), (unsigned long long)((pre_uv + tot_uv) & 0xffffffffull));
+            atomicMax((unsigned long long *)(a.stats + 4), (unsigned long long)((pre_uv + tot_uv) >> 32));
+            atomicMax((unsigned long long *)(a.stats + 5), (unsigned long long)(pre_e + tot_e));
             atomicMax((unsigned long long *)(a.stats + 6), (unsigned long long)max_region);
-            if (failed) atomicOr((unsigned long long *)(a.stats + 2), (unsigned long long)BKT_FLAG_TABLE);
             if (tot_w != tot_e) atomicOr((unsigned long long *)(a.stats + 2), (unsigned long long)BKT_FLAG_INTERNAL);
         }
     }
@@ -721,18 +752,20 @@ int bkt_build(euler_ctx *ctx, const BktBuild &B)
     if (!B.nb) return EULER_OK;
     if (B.cap < BB_THREADS || B.cap % 256) return euler_fail(ctx, EULER_ERR_ARG, "bucket table capacity must be a multiple of 256");
     if (B.bcap & (B.bcap - 1)) return euler_fail(ctx, EULER_ERR_ARG, "boundary table capacity must be a power of two");
-    const size_t smem = bkt_build_smem(B.cap);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(bkt_build_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(bkt_build_kernel<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(bkt_build_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    if (B.cap > BKT_MAX_CAP) return euler_fail(ctx, EULER_ERR_ARG, "bucket table capacity above %u", BKT_MAX_CAP);
+    const size_t smem = bkt_build_smem(B.cap), smem_max = bkt_build_smem(BKT_MAX_CAP);
+    static bool smem_set[64] = {false};   // the attribute belongs to the device
+    if (ctx->device < 0 || ctx->device >= 64 || !smem_set[ctx->device]) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(bkt_build_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(bkt_build_kernel<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(bkt_build_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        if (ctx->device >= 0 && ctx->device < 64) smem_set[ctx->device] = true;
     }
-    // state: flag u32[nb] | work ticket, output ticket u32[2] | (16-byte aligned) agg_uv, agg_e, inc_uv, inc_e u64[nb]
+    // state: flag u32[nb] | work ticket, output ticket u32[2] | redo count, redo list u32[1 + BKT_REDO_CAP] |
+    //        (16-byte aligned) agg_uv, agg_e, inc_uv, inc_e u64[nb]
     u32 *flag = (u32 *)B.state;
     u32 *ticket = flag + B.nb;
-    const size_t zero_bytes = ((size_t)B.nb + 2) * 4;
+    const size_t zero_bytes = ((size_t)B.nb + 2 + 1 + BKT_REDO_CAP) * 4;
     u64 *w64 = (u64 *)((char *)B.state + (zero_bytes + 15) / 16 * 16);
     CUDA_TRY(ctx, cudaMemsetAsync(B.state, 0, zero_bytes, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(B.bkeys, 0xFF, B.bcap * 8, ctx->stream));
@@ -744,10 +777,20 @@ int bkt_build(euler_ctx *ctx, const BktBuild &B)
     a.vkeys = B.vkeys; a.lcount = B.lcount; a.ecount = B.ecount; a.lstart = B.lstart; a.estart = B.estart; a.ev = B.ev; a.vcap = B.vcap;
     a.flag = flag; a.ticket = ticket; a.agg_uv = w64; a.agg_e = w64 + B.nb; a.inc_uv = w64 + 2ull * B.nb; a.inc_e = w64 + 3ull * B.nb;
     a.bkeys = B.bkeys; a.bvals = B.bvals; a.bcap = B.bcap; a.stats = B.stats;
+    a.redo = ticket + 2; a.second = 0;
     if (B.l == 32) bkt_build_kernel<32><<<B.nb, BB_THREADS, smem, ctx->stream>>>(a);
     else if (B.l == 22) bkt_build_kernel<22><<<B.nb, BB_THREADS, smem, ctx->stream>>>(a);
     else bkt_build_kernel<0><<<B.nb, BB_THREADS, smem, ctx->stream>>>(a);
     CUDA_TRY(ctx, cudaGetLastError());
+    if (B.cap < BKT_MAX_CAP) {
+        // second pass: the few buckets that overflowed the tables above (skewed minimizers) are rebuilt with the largest
+        // tables one block can hold, one block per SM; with nothing listed every block leaves at once
+        a.second = 1; a.cap = BKT_MAX_CAP;
+        if (B.l == 32) bkt_build_kernel<32><<<BKT_REDO_CAP, BB_THREADS, smem_max, ctx->stream>>>(a);
+        else if (B.l == 22) bkt_build_kernel<22><<<BKT_REDO_CAP, BB_THREADS, smem_max, ctx->stream>>>(a);
+        else bkt_build_kernel<0><<<BKT_REDO_CAP, BB_THREADS, smem_max, ctx->stream>>>(a);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
     const unsigned g = (unsigned)ctx->num_sms * 8;
     bkt_boundary_publish_kernel<<<g, 256, 0, ctx->stream>>>(B.lkeys, B.ev1, B.ev2, B.stats + 3, B.ucap, B.l, B.bkeys, B.bvals, B.bcap, B.stats);
     bkt_fixup_kernel<<<g, 256, 0, ctx->stream>>>(B.lkeys, B.ev2, B.stats + 3, B.ucap, B.l, B.bkeys, B.bvals, B.bcap);
@@ -755,7 +798,7 @@ int bkt_build(euler_ctx *ctx, const BktBuild &B)
     return EULER_OK;
 }
 
-size_t bkt_state_bytes(u32 nb) { return (((size_t)nb + 2) * 4 + 15) / 16 * 16 + (size_t)nb * 32 + 16; }
+size_t bkt_state_bytes(u32 nb) { return (((size_t)nb + 2 + 1 + BKT_REDO_CAP) * 4 + 15) / 16 * 16 + (size_t)nb * 32 + 16; }
 
 // ---- canonical ids (EULER_RUN_CANONICAL_IDS): bucket order -> ascending key order -------------------------------------
 // The bucketed build numbers vertices and edge records in bucket order.  Ids = rank in ascending key order

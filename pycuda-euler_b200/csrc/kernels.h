@@ -169,6 +169,8 @@ int pipeline_resident_reads(euler_ctx *ctx, const void **d_buf, const u64 **d_of
 int bkt_partition(euler_ctx *ctx, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u32 nranks, u32 nb_per_rank, u32 my_rank,
                   u32 rcap, uint4 *const *d_dst, u32 *d_cursors, u64 *d_stats);
 // pass 2 over the nb local buckets
+#define BKT_MAX_CAP 7424u   // 29 B per slot: the largest per-bucket table that fits one block's shared memory
+#define BKT_REDO_CAP 128u   // buckets the second pass of the build can take over from the first
 struct BktBuild {
     const void *records;   // region (b, src) at ((b * nranks + src) * rcap) records of 16 bytes
     const u32 *counts;     // [nb * nranks]
@@ -177,7 +179,7 @@ struct BktBuild {
     u64 *vkeys; u32 *lcount, *ecount, *lstart, *estart; euler_vertex *ev; u64 vcap;
     void *state;           // bkt_state_bytes(nb)
     u64 *bkeys; u32 *bvals; u64 bcap;   // cross-bucket edge table: bcap keys (power of two), 2 * bcap values
-    u64 *stats;            // [2] |= flags, [3] U_l, [4] V, [5] E, [6] max records in a region
+    u64 *stats;            // [2] |= flags, [3] U_l, [4] V, [5] E, [6] max records in a region, [7] buckets redone by the second pass
 };
 int bkt_build(euler_ctx *ctx, const BktBuild &B);
 size_t bkt_state_bytes(u32 nb);

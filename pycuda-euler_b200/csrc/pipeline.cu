@@ -115,6 +115,7 @@ struct Pipeline {
     u64 bk_area_bytes[2] = {0, 0};
     u64 bk_dist_key = 0;
     u32 bk_dist_rcap = 0;
+    u32 bk_dist_cap = 0;     // table capacity the last build of this geometry settled on
     DevArr<u32> bk_scursors;   // per-destination stream cursors of the multi-GPU form
     float bk_scatter_ms = 0;
     euler_stats st = {};
@@ -333,7 +334,6 @@ static u64 pow2_at_least(u64 x)
 }
 #define EULER_FALLBACK 1   // internal: take the global-table path instead
 #define BKT_MAX_DISTINCT 50000000ull   // distinct canonical l-mers up to which the bucketed path is taken by default
-#define BKT_MAX_CAP 7424u   // 29 B per slot: the largest per-bucket table that fits one block's shared memory
 
 static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 distinct_hint, euler_stats *stats)
 {
@@ -405,7 +405,7 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
             launches++;
             need_part = false;
         } else {
-            CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr() + 2, 0, 5 * sizeof(u64), s));   // flags, totals, max region
+            CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr() + 2, 0, 6 * sizeof(u64), s));   // flags, totals, max region
         }
         BktBuild bb;
         bb.records = P->bk_records.p; bb.counts = P->bk_cursors.ptr(); bb.nb = nb; bb.nranks = 1; bb.rcap = rcap; bb.l = l;
@@ -417,7 +417,7 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], s));
         EULER_TRY(bkt_build(ctx, bb));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
-        launches += 2;
+        launches += 4;   // build, second pass, boundary publish, fix-up
         EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 8));   // the only host round trip of a steady-state step
         if (getenv("EULER_B200_BKT_TIMING")) {   // library built with -DBKT_TIMING: clock cycles per build phase, summed over the blocks
             u64 t[8];
@@ -510,7 +510,7 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
     cudaEventElapsedTime(&st.ms_count_kernel, ctx->ev[4], ctx->ev[1]);
     cudaEventElapsedTime(&st.ms_build_kernel, ctx->ev[5], ctx->ev[2]);
     st.kernel_launches = launches;
-    st.path = 1; st.n_buckets = nb; st.bucket_records = h[6];
+    st.path = 1; st.n_buckets = nb; st.bucket_records = h[6]; st.redo_buckets = (u32)h[7];
     if (stats) *stats = st;
     return EULER_OK;
 }
@@ -1475,6 +1475,7 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
     u64 h[8] = {0};
     u32 retries = 0, launches = 0;
     u32 cap = (env_u32("EULER_B200_BKT_CAP", 1536) + 255u) / 256u * 256u;
+    if (learned && P->bk_dist_cap > cap) cap = P->bk_dist_cap;
     if (P->bk_scatter_ms < 0.f) {   // asynchronous scatter: its events have completed by now (the caller synchronised on the exchange)
         if (cudaEventElapsedTime(&P->bk_scatter_ms, ctx->ev[0], ctx->ev[1]) != cudaSuccess) { P->bk_scatter_ms = 0.f; cudaGetLastError(); }
     }
@@ -1509,7 +1510,7 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], s));
         EULER_TRY(bkt_build(ctx, bb));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], s));
-        launches += 3;
+        launches += 4;   // build, second pass, boundary publish, fix-up
         EULER_TRY(read_u64s(ctx, P->stats.ptr(), h, 8));
         const u64 fl = h[2];
         if (fl & BKT_FLAG_INTERNAL) return euler_fail(ctx, EULER_ERR_STATE, "internal: bucketed build consistency check failed (flags %llx)", fl);
@@ -1529,6 +1530,7 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     P->have_graph = true;
     P->bk_dist_key = key; P->bk_learned_u = U_l; P->bk_learned_v = V; P->bk_dist_rcap = (u32)(h[6] + h[6] / 8 + 16);
+    P->bk_dist_cap = cap;
     euler_stats &st = P->st;
     st.distinct_lmers = U_l; st.distinct_kmers = V; st.edge_count = E;
     st.lmer_table_capacity = (u64)nb * cap; st.kmer_table_capacity = (u64)nb * cap; st.retries = retries;
@@ -1536,7 +1538,7 @@ int euler_bkt_build(euler_ctx *ctx, const void *d_area, uint32_t l, uint32_t my_
     cudaEventElapsedTime(&st.ms_graph, ctx->ev[7], ctx->ev[2]);
     st.ms_total = st.ms_graph;
     cudaEventElapsedTime(&st.ms_build_kernel, ctx->ev[5], ctx->ev[2]);
-    st.kernel_launches = launches; st.path = 1; st.n_buckets = nb; st.bucket_records = h[6];
+    st.kernel_launches = launches; st.path = 1; st.n_buckets = nb; st.bucket_records = h[6]; st.redo_buckets = (u32)h[7];
     if (stats) *stats = st;
     return EULER_OK;
 }

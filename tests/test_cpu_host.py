@@ -152,3 +152,25 @@ def test_reference_bytecode_is_the_reference():
     case = next(c for c in fx["cases"] if c["k"] == 9 and c["limit"] == 1)
     d = mod.build(fx["reads"], 9, 1)
     assert sorted([km, c] for km, c in d.items()) == case["kmers"]
+
+
+def test_bench_line_guard_prints_once():
+    """bench.py's watchdog: a stalled phase after the timed steps costs the extra keys, not the line."""
+    code = r'''
+import sys, time, importlib.util
+spec = importlib.util.spec_from_file_location("bench", %r)
+b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+g = b.LineGuard(0.3, {"metric": "x", "value": 1})
+%s
+print("main thread went on")
+'''
+    bench = os.path.join(ROOT, "bench.py")
+    stalled = subprocess.run([sys.executable, "-c", code % (bench, "time.sleep(5)")], capture_output=True, text=True, timeout=60)
+    assert stalled.returncode == 0 and "main thread went on" not in stalled.stdout
+    import json
+    line = json.loads(stalled.stdout.strip().splitlines()[-1])
+    assert line["value"] == 1 and "incomplete" in line
+    fine = subprocess.run([sys.executable, "-c", code % (bench, "g.finish({'metric': 'x', 'value': 2}); time.sleep(0.6)")],
+                          capture_output=True, text=True, timeout=60)
+    lines = fine.stdout.strip().splitlines()
+    assert fine.returncode == 0 and json.loads(lines[0])["value"] == 2 and lines[1] == "main thread went on" and len(lines) == 2

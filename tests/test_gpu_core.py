@@ -271,3 +271,36 @@ print("ok")
     env = dict(os.environ, **{knob: "1", "EULER_B200_BUCKETED": "0"})
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_second_pass_rebuilds_the_buckets_that_overflow():
+    """Small tables at a high load make some buckets overflow the first pass of the per-bucket build; the second pass
+    rebuilds them with the largest tables and appends their artefacts: same graph, no repartition."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oracle, _native as N
+from util import random_reads
+ctx = N.Context(0)
+reads = random_reads(4, 3000, genome_len=40000) + ["A" * 90, "ACGT" * 30]
+buf, off = oracle.pack_reads(reads)
+redone = 0
+for l in (32, 22, 27, 13):
+    g = oracle.graph_build(buf, off, l, expand=True)
+    st = ctx.run_host(buf, off, l, N.RUN_EXPAND_EDGES | N.RUN_CANONICAL_IDS)
+    assert st.path == 1
+    assert (st.distinct_lmers, st.distinct_kmers, st.edge_count) == (g.nl, g.nv, g.ne), l
+    assert np.array_equal(ctx.download(N.ART_LMER_KEYS), g.lk_lo) and np.array_equal(ctx.download(N.ART_LMER_VALUES), g.lvals)
+    assert np.array_equal(ctx.download(N.ART_EV), g.ev) and np.array_equal(ctx.download(N.ART_EE), g.ee)
+    redone += st.redo_buckets
+    print(l, st.n_buckets, st.redo_buckets, st.retries)
+assert redone > 0
+print("ok")
+''' % (root, os.path.join(root, "pycuda-euler_b200"), os.path.join(root, "tests"))
+    env = dict(os.environ, EULER_B200_BUCKETED="2", EULER_B200_BKT_CAP="256", EULER_B200_BKT_LOAD="0.6")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout[-500:] + out.stderr[-2000:]
