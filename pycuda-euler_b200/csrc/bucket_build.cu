@@ -240,8 +240,10 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
     wq.n = 0;
     // A bucket several times the mean size fills its table to the point where every insert walks hundreds of slots and
     // one block holds up the whole grid (measured: 4.9 ms instead of 1.9 ms on the rank that owned such a bucket).
-    // The first pass therefore gives up on a bucket after BB_PROBE_LIMIT probes; the second pass probes to the end.
-    const u32 plimit = a.second ? cap : (cap < BB_PROBE_LIMIT ? cap : BB_PROBE_LIMIT);
+    // The first pass therefore gives up on a bucket after BB_PROBE_LIMIT probes, the second pass after 8x as many
+    // (its table is 4.8x larger than the default: a bucket that still fails there is repartitioned by the host).
+    const u32 plimit1 = a.second ? 8u * BB_PROBE_LIMIT : BB_PROBE_LIMIT;   // the second pass tolerates a fuller table, not an endless walk per failing insert
+    const u32 plimit = cap < plimit1 ? cap : plimit1;
 
 #ifdef BKT_TIMING
     long long tick_ = clock64();

@@ -353,6 +353,9 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
     const char *le = getenv("EULER_B200_BKT_LOAD");
     const double per_bucket = (le && atof(le) > 0.05 && atof(le) < 0.9 ? atof(le) : 0.30) * (double)cap;   // mean table load (linear probing)
     u64 nb64 = learned ? P->bk_learned_nb : (u64)((double)est_c * 1.06 / per_bucket) + 1;
+    // a hint that is far too small must not pile the whole input into a handful of buckets (every occurrence of every
+    // l-mer would walk a full table before the repartition): at least one bucket per 128 Ki bases
+    if (!learned && nb64 < (B >> 17)) nb64 = B >> 17;
     if (const u32 f = env_u32("EULER_B200_BKT_NB", 0)) nb64 = f;
     // Where the bucketed path pays: tables whose buckets stay few enough for the 12-mer minimizers to balance them and
     // for the scattered 16-byte record stores to stay inside the TLB reach (measured: 1.25e8 distinct l-mers -> 3.3e5
