@@ -18,7 +18,7 @@ OUT = os.path.join(HERE, "_ref", "referenceAssembler.bytecode")
 
 
 def build(force=False):
-    """returns the path of the .pyc, or None when neither the reference nor a previous build is present"""
+    """returns the path of the bytecode file, or None when neither the reference nor a previous build is present"""
     if os.path.exists(SRC):
         if force or not os.path.exists(OUT) or os.path.getmtime(OUT) < os.path.getmtime(SRC):
             os.makedirs(os.path.dirname(OUT), exist_ok=True)
