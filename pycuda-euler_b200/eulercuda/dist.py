@@ -299,7 +299,9 @@ def plan_buckets(n_bases, l, world, distinct_hint=0, cap=None):
     w = k - min(k, 12) + 1
     rec_per_base = 2.0 / (w + 1.0) + 1.0 / 16.0 + 0.01
     est = int(distinct_hint) or max(int(n_bases), 1)
-    nbpr = int(est * 1.06 / (0.30 * cap)) + 1
+    # a hint that is far too small must not pile a whole shard's worth of l-mers into a handful of shared-memory
+    # tables (same floor as pipeline_run_bucketed): at least one bucket per 128 Ki bases
+    nbpr = max(int(est * 1.06 / (0.30 * cap)) + 1, int(n_bases) >> 17)
     scap = int(n_bases * rec_per_base / world * 1.5) + 4096
     return nbpr, scap
 
