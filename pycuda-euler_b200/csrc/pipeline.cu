@@ -115,6 +115,7 @@ struct Pipeline {
     u64 bk_area_bytes[2] = {0, 0};
     u64 bk_dist_key = 0;
     u32 bk_dist_rcap = 0;
+    u64 dist_bits_bases = ~0ull; u32 dist_bits_l = 0;   // what the read-start bitmap of the last euler_dist_count was built for
     u32 bk_dist_cap = 0;     // table capacity the last build of this geometry settled on
     DevArr<u32> bk_scursors;   // per-destination stream cursors of the multi-GPU form
     float bk_scatter_ms = 0;
@@ -227,6 +228,7 @@ static int pipeline_run_wide(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], s));
     if (wide_tiled) {
         EULER_TRY(P->start_bits.reserve(ctx, B / 32 + 2));
+        P->dist_bits_bases = ~0ull;   // the bitmap no longer belongs to an euler_dist_count call
         EULER_TRY(enc_mark_starts(ctx, P->d_off, P->nreads, B, P->start_bits.ptr()));
         launches++;
     }
@@ -343,6 +345,7 @@ static int pipeline_run_bucketed(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, 
     if (B >= (1ull << 40)) return EULER_FALLBACK;
     EULER_TRY(P->stats.reserve(ctx, 64));
     EULER_TRY(P->start_bits.reserve(ctx, B / 32 + 2));
+    P->dist_bits_bases = ~0ull;   // the bitmap no longer belongs to an euler_dist_count call
 
     // geometry: buckets sized for a shared-memory table at ~45 % load
     const u32 cap = (env_u32("EULER_B200_BKT_CAP", 1536) + 255u) / 256u * 256u;   // 29 B per slot: 4 resident blocks per SM
@@ -539,6 +542,7 @@ static int pipeline_run(euler_ctx *ctx, Pipeline *P, u32 l, u32 flags, u64 disti
 
     EULER_TRY(P->stats.reserve(ctx, 16));
     EULER_TRY(P->start_bits.reserve(ctx, B / 32 + 2));
+    P->dist_bits_bases = ~0ull;   // the bitmap no longer belongs to an euler_dist_count call
 
     // expected distinct canonical l-mers / k-mers
     u64 est_l, est_v;
@@ -1080,6 +1084,7 @@ int euler_dist_count(euler_ctx *ctx, const void *d_buf, const void *d_read_off, 
     for (u32 d = 0; d < nranks; d++) counts[d] = h[d];
     counts[nranks] = h[16];       // forward l-mer windows of this rank's reads
     counts[nranks + 1] = h[17];   // forward k-mer windows
+    P->dist_bits_bases = n_bases; P->dist_bits_l = l;
     return EULER_OK;
 }
 
@@ -1091,7 +1096,11 @@ int euler_dist_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off
     if (nranks < 1 || nranks > 16) return euler_fail(ctx, EULER_ERR_ARG, "nranks %u out of range [1,16]", nranks);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     Pipeline *P = get_pipe(ctx);
-    if (!P->start_bits.ptr()) return euler_fail(ctx, EULER_ERR_STATE, "euler_dist_scatter must follow euler_dist_count");
+    if (l < 2 || l > 32) return euler_fail(ctx, EULER_ERR_ARG, "l-mer length %u out of range [2,32]", l);
+    if (((uintptr_t)d_buf & 15) != 0) return euler_fail(ctx, EULER_ERR_ARG, "d_buf must be 16-byte aligned");
+    // the pass reuses the read-start bitmap of the count pass: it must be the one of these reads
+    if (!P->start_bits.ptr() || P->dist_bits_bases != n_bases || P->dist_bits_l != l)
+        return euler_fail(ctx, EULER_ERR_STATE, "euler_dist_scatter must follow euler_dist_count on the same reads and l");
     // cursors count from 0 inside each destination's segment, which starts at send_off[d]
     CUDA_TRY(ctx, cudaMemsetAsync(P->stats.ptr() + 8, 0, 16 * sizeof(u64), ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(P->stats.ptr() + 24, send_off, nranks * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
@@ -1120,6 +1129,7 @@ static int scatter_to_segments(euler_ctx *ctx, const void *d_buf, const void *d_
                                     d_send, P->stats.ptr() + 24, seg_cap));
     } else {
         EULER_TRY(P->start_bits.reserve(ctx, n_bases / 32 + 2));
+        P->dist_bits_bases = ~0ull;   // the bitmap no longer belongs to an euler_dist_count call
         EULER_TRY(enc_mark_starts(ctx, (const u64 *)d_read_off, nreads, n_bases, P->start_bits.ptr()));
         EULER_TRY(dist_partition(ctx, true, d_buf, n_bases, P->start_bits.ptr(), l, nranks, P->stats.ptr() + 32, P->stats.ptr() + 8,
                                  (u64 *)d_send, P->stats.ptr() + 24, seg_cap));
@@ -1426,6 +1436,7 @@ int euler_bkt_scatter(euler_ctx *ctx, const void *d_buf, const void *d_read_off,
     cudaStream_t s = ctx->stream;
     EULER_TRY(P->stats.reserve(ctx, 64));
     EULER_TRY(P->start_bits.reserve(ctx, n_bases / 32 + 2));
+    P->dist_bits_bases = ~0ull;   // the bitmap no longer belongs to an euler_dist_count call
     EULER_TRY(P->bk_scursors.reserve(ctx, 16));
     EULER_TRY(P->bk_dst.reserve(ctx, 16));
     uint4 *h_dst[16];
