@@ -20,7 +20,11 @@
 //      over the records through a small global table keyed by the canonical l-mer (bkt_boundary_publish_kernel,
 //      bkt_fixup_kernel).
 #include "bucket.cuh"
+#ifdef EULER_SIMT_EMU   // tests/host/simt_build_check.cpp compiles the kernels of this file for the CPU (tests/host/simt_emu.h)
+#include "simt_emu.h"
+#else
 #include "kernels.h"
+#endif
 
 #define BB_THREADS 256
 #ifndef BB_PROBE_LIMIT
@@ -71,6 +75,7 @@ __device__ __forceinline__ u32 bb_home(u64 key, u32 cap)
     h ^= h >> 13;
     return __umulhi(h, cap);
 }
+#ifndef EULER_SIMT_EMU   // (the emulator header brings its own)
 __device__ __forceinline__ u32 ld_vol_u32(const u32 *p)
 {
     u32 v;
@@ -85,6 +90,7 @@ __device__ __forceinline__ u64 ld_vol_u64(const u64 *p)
 }
 __device__ __forceinline__ void st_vol_u32(u32 *p, u32 v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_vol_u64(u64 *p, u64 v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+#endif
 
 // Slots are never freed, so the first EMPTY slot ends a search.  One exit per function: with early returns the compiler
 // duplicated the caller's tail per return point and the warp ran it once per group of lanes.
@@ -217,7 +223,11 @@ struct WarpQueue {
 template <int L>
 __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const BkBuildArgs a)
 {
+#ifdef EULER_SIMT_EMU
+    unsigned char *bb_smem = simt::dyn_smem();
+#else
     extern __shared__ __align__(16) unsigned char bb_smem[];
+#endif
     const u32 cap = a.cap;
     u64 *lt_keys = (u64 *)bb_smem;
     u64 *vt_keys = lt_keys + cap;
@@ -747,6 +757,7 @@ __global__ void __launch_bounds__(256) bkt_fixup_kernel(const u64 *__restrict__ 
     }
 }
 
+#ifndef EULER_SIMT_EMU   // host side (launches, canonical-id helpers): not part of the CPU emulation
 size_t bkt_build_smem(u32 cap) { return (size_t)29 * cap; }   // two key arrays (8 B) + count + two vertex words (4 B) + mask byte
 
 int bkt_build(euler_ctx *ctx, const BktBuild &B)
@@ -869,3 +880,4 @@ int bkt_gather_edges(euler_ctx *ctx, const u32 *perm, u64 n, const u32 *newid, c
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
+#endif   // EULER_SIMT_EMU
