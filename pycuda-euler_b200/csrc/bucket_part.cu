@@ -12,7 +12,9 @@
 // 16-byte record: a cursor atomic and one 16-byte store.
 #include "bucket.cuh"
 #include "encode.cuh"
+#ifndef EULER_SIMT_EMU   // (tests/host/simt_part_check.cpp compiles the kernels of this file for the CPU)
 #include "kernels.h"
+#endif
 
 #define BP_BLOCK 128
 #define BP_WARPS (BP_BLOCK / 32)
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const 
     if (overflow) atomicOr((unsigned long long *)(stats + 2), (unsigned long long)BKT_FLAG_REGION);
 }
 
+#ifndef EULER_SIMT_EMU   // host side
 static int bkt_partition_launch(euler_ctx *ctx, bool stream, const void *d_buf, u64 n_bases, const u32 *d_bits, u32 l, u32 nranks,
                                 u32 nb_per_rank, u32 my_rank, u32 rcap, uint4 *const *d_dst, u32 *d_cursors, u64 *d_stats)
 {
@@ -223,6 +226,8 @@ int bkt_partition_streams(euler_ctx *ctx, const void *d_buf, u64 n_bases, const 
     return bkt_partition_launch(ctx, true, d_buf, n_bases, d_bits, l, nranks, nb_per_rank, my_rank, scap, d_dst, d_cursors, d_stats);
 }
 
+#endif
+
 // ---- multi-GPU: publish how many records this rank wrote into each owner's stream ---------------------------------------
 // the counts of owner d live behind its streams: u64 counts[nranks], entry `my_rank` is ours
 __global__ void bkt_push_counts_kernel(const u32 *__restrict__ cursors, uint4 *const *__restrict__ dst, u64 stream_bytes, u32 nranks,
@@ -236,12 +241,15 @@ __global__ void bkt_push_counts_kernel(const u32 *__restrict__ cursors, uint4 *c
     atomicMax((unsigned long long *)max_out, (unsigned long long)c);
 }
 
+#ifndef EULER_SIMT_EMU
 int bkt_push_counts(euler_ctx *ctx, const u32 *d_cursors, uint4 *const *d_dst, u64 stream_bytes, u32 nranks, u32 my_rank, u32 scap, u64 *d_max)
 {
     bkt_push_counts_kernel<<<1, 32, 0, ctx->stream>>>(d_cursors, d_dst, stream_bytes, nranks, my_rank, scap, d_max);
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
+
+#endif
 
 // ---- owner side: incoming streams -> bucket regions (local memory, one cursor per bucket) ---------------------------------
 __global__ void __launch_bounds__(256) bkt_regroup_kernel(const uint4 *__restrict__ streams, const u64 *__restrict__ counts, u32 nranks,
@@ -266,6 +274,7 @@ __global__ void __launch_bounds__(256) bkt_regroup_kernel(const uint4 *__restric
     if (bad) atomicOr((unsigned long long *)(stats + 2), (unsigned long long)BKT_FLAG_INTERNAL);
 }
 
+#ifndef EULER_SIMT_EMU
 int bkt_regroup(euler_ctx *ctx, const void *d_streams, const u64 *d_counts, u32 nranks, u32 scap, u32 nb, u32 rcap, void *d_records,
                 u32 *d_cursors, u64 *d_stats)
 {
@@ -274,3 +283,4 @@ int bkt_regroup(euler_ctx *ctx, const void *d_streams, const u64 *d_counts, u32 
     CUDA_TRY(ctx, cudaGetLastError());
     return EULER_OK;
 }
+#endif

@@ -7,7 +7,11 @@
 // in their chunk.  HALO = 2 for l <= 32.  Consecutive tiles advance by 32-HALO chunks, so every
 // load is a 16-byte aligned vector load and no state is carried between tiles.
 #pragma once
+#ifdef EULER_SIMT_EMU   // CPU tests of the kernels (tests/host/simt_emu.h)
+#include "simt_emu.h"
+#else
 #include "common.cuh"
+#endif
 
 #define ENC_HALO 2
 #define ENC_ADV (32 - ENC_HALO)

@@ -5,7 +5,8 @@
 // thread, warp collectives are rendezvous that abort when lanes disagree about which collective they are at, and a
 // deadlock shows as a hang (the caller runs this binary under a timeout).
 //
-// Input records come from the partition pass's lane logic (bucket.cuh, the functions bucket_lane_check.cpp verifies).
+// Input records come from the partition pass's lane logic (lane_driver.h: the bucket.cuh functions that
+// bucket_lane_check.cpp verifies).
 // Checked, for l = 32 / 22 (templated kernels) and generic lengths: edge records (both strands, multiplicities,
 // offsets), vertices, the eight degree slots of every vertex, the scans, EulerVertex, prefix / suffix vertex ids of
 // every edge (cross-bucket ones through the post-pass), the totals -- and the overflow protocol: buckets that do not
@@ -16,52 +17,7 @@
 #define EULER_SIMT_EMU
 #include "../../pycuda-euler_b200/csrc/bucket_build.cu"
 
-#include <algorithm>
-#include <map>
-#include <set>
-#include <string>
-
-static u64 rng_state = 0x9E3779B97F4A7C15ull;
-static u64 rnd()
-{
-    u64 z = (rng_state += 0x9E3779B97F4A7C15ull);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-static int code_of(char ch)
-{
-    switch (ch & 0xDF) {
-    case 'A': return 0;
-    case 'C': return 1;
-    case 'G': return 2;
-    case 'T': return 3;
-    }
-    return -1;
-}
-struct ChunkH { u32 codes, vmask, smask; };
-static ChunkH load_chunk_h(const std::string &buf, const std::vector<char> &is_start, long long chunk)
-{
-    ChunkH c = {0, 0, 0};
-    if (chunk < 0) return c;
-    for (int i = 0; i < 16; i++) {
-        const u64 pos = (u64)chunk * 16 + i;
-        if (pos >= buf.size()) break;
-        const int cd = code_of(buf[pos]);
-        if (cd >= 0) { c.codes |= (u32)cd << (30 - 2 * i); c.vmask |= 1u << (15 - i); }
-        if (is_start[pos]) c.smask |= 1u << (15 - i);
-    }
-    return c;
-}
-
-template <typename T>
-static T *aligned_array(size_t n, int fill)
-{
-    void *p = nullptr;
-    if (posix_memalign(&p, 64, (n + 8) * sizeof(T))) abort();
-    memset(p, fill, (n + 8) * sizeof(T));
-    return (T *)p;
-}
+#include "lane_driver.h"
 
 struct Case {
     u32 l, nb, cap;
@@ -73,89 +29,16 @@ struct Case {
 
 static int run_case(const Case &cs, int rep)
 {
-    const u32 l = cs.l, k = l - 1, m = bk_m_of(k), W = k - m + 1;
+    const u32 l = cs.l, k = l - 1;
     const BkGeom g = {1, cs.nb};
-    std::string genome;
-    for (int i = 0; i < cs.genome; i++) genome.push_back("ACGT"[rnd() & 3]);
-    std::string buf;
-    std::vector<u64> off;
-    for (int r = 0; r < cs.nreads; r++) {
-        off.push_back(buf.size());
-        int len = (int)(rnd() % (u64)(cs.maxlen + 1));
-        if (cs.genome > 0) {
-            if (len > cs.genome) len = cs.genome;
-            const int s = (int)(rnd() % (u64)(cs.genome - len + 1));
-            std::string rd = genome.substr(s, len);
-            if (rnd() & 1) {   // the other strand
-                std::reverse(rd.begin(), rd.end());
-                for (auto &ch : rd) ch = ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : 'A';
-            }
-            if ((rnd() % 16) == 0 && len > 0) rd[rnd() % (u64)len] = 'N';
-            buf += rd;
-        } else {
-            for (int i = 0; i < len; i++) {
-                char ch = "ACGT"[rnd() & 3];
-                if ((rnd() % 512) == 0) ch = 'N';
-                if ((rnd() & 31) == 0) ch = (char)(ch | 0x20);
-                if (i >= 3 && (rnd() & 7) == 0) ch = buf[buf.size() - 3];   // low-complexity stretches: palindromes, repeats
-                buf.push_back(ch);
-            }
-        }
-    }
-    off.push_back(buf.size());
-    const u64 B = buf.size();
-    std::vector<char> is_start(B + 1, 0);
-    for (size_t r = 0; r + 1 < off.size(); r++)
-        if (off[r] < B) is_start[off[r]] = 1;
-
-    // ---- brute force: forward l-mer occurrences
-    std::map<u64, u64> occ;
-    u64 N_l = 0;
-    for (size_t r = 0; r + 1 < off.size(); r++)
-        for (u64 p = off[r]; p + l <= off[r + 1]; p++) {
-            u64 x = 0;
-            bool ok = true;
-            for (u32 j = 0; j < l && ok; j++) { const int cd = code_of(buf[p + j]); if (cd < 0) ok = false; else x = (x << 2) | (u64)cd; }
-            if (ok) { occ[x]++; N_l++; }
-        }
-    std::map<u64, u64> M;   // strand l-mer -> both-strand multiplicity
-    for (auto &kv : occ) {
-        const u64 x = kv.first, r = bk_revcomp(x, l);
-        M[x] += kv.second;
-        M[r] += kv.second;
-    }
+    const Reads R = make_reads(cs.nreads, cs.maxlen, cs.genome);
+    const Census C = census(R, l);
+    const std::map<u64, u64> &M = C.M;     // strand l-mer -> both-strand multiplicity
+    const std::set<u64> &VS = C.VS;
+    const u64 N_l = C.N_l;
     const u64 kmask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
-    std::set<u64> VS;
-    for (auto &kv : M) { VS.insert(kv.first >> 2); VS.insert(kv.first & kmask); }
-
     // ---- records per bucket from the partition pass's lane logic
-    std::vector<std::vector<BkRec>> recs(cs.nb);
-    {
-        const int HALO = 2, ADV = 30;
-        const u64 nchunks = (B + 15) / 16, ntiles = (nchunks + ADV - 1) / ADV;
-        for (u64 tile = 0; tile < ntiles; tile++) {
-            ChunkH ch[32];
-            u32 sc[32][16], win[32][16];
-            for (int lane = 0; lane < 32; lane++) ch[lane] = load_chunk_h(buf, is_start, (long long)(tile * ADV) - HALO + lane);
-            for (int lane = 0; lane < 32; lane++) bk_chunk_scores(lane >= 1 ? ch[lane - 1].codes : 0u, ch[lane].codes, m, sc[lane]);
-            for (int lane = 0; lane < 32; lane++) {
-                u32 sa[36];
-                for (int t = 0; t < 4; t++) sa[t] = lane >= 2 ? sc[lane - 2][12 + t] : 0xdeadbeefu + t;
-                for (int t = 0; t < 16; t++) sa[4 + t] = lane >= 1 ? sc[lane - 1][t] : 0xfeedf00du + t;
-                for (int t = 0; t < 16; t++) sa[20 + t] = sc[lane][t];
-                bk_window_min_any(sa, W, win[lane]);
-            }
-            for (int lane = HALO; lane < 32; lane++) {
-                const u64 vmw = ((u64)ch[lane - 2].vmask << 48) | ((u64)ch[lane - 1].vmask << 32) | ((u64)ch[lane].vmask << 16);
-                const u64 smw = ((u64)ch[lane - 2].smask << 48) | ((u64)ch[lane - 1].smask << 32) | ((u64)ch[lane].smask << 16);
-                const u64 VK = bk_valid_kmers(vmw, smw, k);
-                const u32 vk16 = bk_own16(VK), vl16 = bk_own16(bk_valid_lmers(VK, smw, k));
-                const u32 win_prev = win[lane - 1][15];
-                bk_lane_pieces(ch[lane - 2].codes, ch[lane - 1].codes, ch[lane].codes, win[lane], win_prev, bk_eq16(win[lane], win_prev),
-                               vk16, vl16, k, g, [&](u32 bucket, const BkRec &r) { recs[bucket].push_back(r); });
-            }
-        }
-    }
+    std::vector<std::vector<BkRec>> recs = host_records(R, l, g);
     u32 rcap = 1;
     for (auto &v : recs) rcap = std::max<u32>(rcap, (u32)v.size());
     uint4 *records = aligned_array<uint4>((size_t)cs.nb * rcap, 0);
@@ -242,7 +125,7 @@ static int run_case(const Case &cs, int rep)
                 u64 ls = 0, es = 0;
                 for (u32 t = 0; t < 4; t++) {
                     const u64 out = (v << 2) | t, in = ((u64)t << (2 * k)) | v;
-                    const u64 mo = M.count(out) ? M[out] : 0, mi = M.count(in) ? M[in] : 0;
+                    const u64 mo = M.count(out) ? M.at(out) : 0, mi = M.count(in) ? M.at(in) : 0;
                     if (lcount[4 * i + t] != mo) fail("lcount", lcount[4 * i + t], mo);
                     if (ecount[4 * i + t] != mi) fail("ecount", ecount[4 * i + t], mi);
                     if (lstart[4 * i + t] != (u32)(run_l + ls)) fail("lstart", lstart[4 * i + t], run_l + ls);

@@ -46,7 +46,7 @@ typedef unsigned int u32;
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
 
 struct alignas(16) uint4 { u32 x, y, z, w; };
@@ -250,4 +250,14 @@ static inline unsigned __brev(unsigned x)
     x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
     return __builtin_bswap32(x);
 }
+static inline u32 __ldg(const u32 *p) { return *p; }
+// per-byte compare: 0xff where the bytes are equal
+static inline u32 __vcmpeq4(u32 a, u32 b)
+{
+    u32 r = 0;
+    for (int i = 0; i < 4; i++)
+        if (((a >> (8 * i)) & 0xffu) == ((b >> (8 * i)) & 0xffu)) r |= 0xffu << (8 * i);
+    return r;
+}
+static inline u64 key_mask_d(u32 len) { return len >= 32 ? ~0ull : ((1ull << (2 * len)) - 1ull); }
 static inline unsigned long long __brevll(unsigned long long x) { return ((unsigned long long)__brev((unsigned)x) << 32) | __brev((unsigned)(x >> 32)); }
