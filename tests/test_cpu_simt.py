@@ -4,7 +4,7 @@ collectives as rendezvous that abort when the lanes of a warp disagree about whi
 small inputs against brute force:
 * tests/host/simt_build_check.cpp -- the per-bucket build: first and second pass, the look-back, the cross-bucket
   post-pass, the TABLE / OUTPUT overflow protocol;
-* tests/host/simt_part_check.cpp -- the partition pass in its direct and its multi-GPU stream form (1, 2, 3 and 8
+* tests/host/simt_part_check.cpp -- the partition pass in its direct and its multi-GPU stream form (1, 2, 3, 8 and 16
   emulated ranks scattering into each other's stream areas), count push, owner-side regroup, then the build per owner:
   the union of the owners' graphs must be the graph of all reads.
 A deadlock shows as the timeout below.
@@ -56,4 +56,4 @@ def test_partition_kernels_under_the_simt_emulator():
                                os.path.join(HOST, "simt_part_check.cpp"), "-o", exe])
         out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "7 cases, 0 failed" in out.stdout
+    assert "8 cases, 0 failed" in out.stdout
