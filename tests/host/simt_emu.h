@@ -102,6 +102,18 @@ inline Dim &block_dim() { static Dim d; return d; }
 inline Dim &grid_dim() { static Dim d; return d; }
 inline unsigned char *dyn_smem() { return cur_block()->dyn; }
 
+// SIMT_EMU_JITTER=n: every lane yields at random before one in n collectives / atomics, to vary the interleavings
+inline unsigned jitter_period() { static const unsigned n = getenv("SIMT_EMU_JITTER") ? (unsigned)atoi(getenv("SIMT_EMU_JITTER")) : 0u; return n; }
+inline void jitter()
+{
+    const unsigned n = jitter_period();
+    if (!n) return;
+    static thread_local unsigned long long s = 0x9E3779B97F4A7C15ull ^ (unsigned long long)(uintptr_t)&s;
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    if (s % n == 0)
+        for (unsigned i = 0; i < 1 + (s >> 20) % 4; i++) std::this_thread::yield();
+}
+
 [[noreturn]] inline void die(const char *what, u32 a, u32 b)
 {
     fprintf(stderr, "SIMT EMU: %s (op %08x vs %08x) in block %u, warp %d, lane %d\n", what, a, b, tls().bid.x, tls().warp, tls().lane);
@@ -115,6 +127,7 @@ inline auto collective(u64 v, u32 op, R read) -> decltype(read((const Warp *)nul
 {
     Warp &w = cur_block()->warps[tls().warp];
     const int lane = tls().lane;
+    jitter();
     w.slot[lane] = v;
     w.op[lane] = op;
     w.bar.wait();
@@ -215,9 +228,9 @@ static inline unsigned simt_ballot(bool p, u32 op)
 #define __any_sync(mask, p) (simt_ballot((p), SIMT_OP(6)) != 0u)
 
 // ---- atomics, memory ------------------------------------------------------------------------------------------------------
-static inline u32 atomicAdd(u32 *p, u32 v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-static inline u32 atomicOr(u32 *p, u32 v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline u32 atomicAdd(u32 *p, u32 v) { simt::jitter(); return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { simt::jitter(); return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline u32 atomicOr(u32 *p, u32 v) { simt::jitter(); return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v)
 {
@@ -227,6 +240,7 @@ static inline unsigned long long atomicMax(unsigned long long *p, unsigned long 
 }
 static inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long v)
 {
+    simt::jitter();
     __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
     return cmp;   // the old value either way
 }
