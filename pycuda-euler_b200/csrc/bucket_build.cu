@@ -795,9 +795,10 @@ int bkt_build(euler_ctx *ctx, const BktBuild &B)
     else if (B.l == 22) bkt_build_kernel<22><<<B.nb, BB_THREADS, smem, ctx->stream>>>(a);
     else bkt_build_kernel<0><<<B.nb, BB_THREADS, smem, ctx->stream>>>(a);
     CUDA_TRY(ctx, cudaGetLastError());
-    if (B.cap < BKT_MAX_CAP) {
+    {
         // second pass: the few buckets that overflowed the tables above (skewed minimizers) are rebuilt with the largest
-        // tables one block can hold, one block per SM; with nothing listed every block leaves at once
+        // tables one block can hold, one block per SM; with nothing listed every block leaves at once.  (Always launched:
+        // a first pass that already runs with the largest tables lists its failures all the same.)
         a.second = 1; a.cap = BKT_MAX_CAP;
         if (B.l == 32) bkt_build_kernel<32><<<BKT_REDO_CAP, BB_THREADS, smem_max, ctx->stream>>>(a);
         else if (B.l == 22) bkt_build_kernel<22><<<BKT_REDO_CAP, BB_THREADS, smem_max, ctx->stream>>>(a);
