@@ -174,3 +174,41 @@ print("main thread went on")
                           capture_output=True, text=True, timeout=60)
     lines = fine.stdout.strip().splitlines()
     assert fine.returncode == 0 and json.loads(lines[0])["value"] == 2 and lines[1] == "main thread went on" and len(lines) == 2
+
+
+def _bench_mock(args, world=1, stall=False, timeout=240):
+    """bench.main() with the device replaced by stand-ins (tests/bench_flow_mock.py); returns rank 0's stdout"""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        if stall:
+            env["BENCH_MOCK_STALL"] = "1"
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "bench_flow_mock.py")] + args, env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=timeout) for p in procs]
+    for p, (out, err) in zip(procs, outs):
+        assert p.returncode == 0, err[-2000:]
+    assert all(not out.strip() for out, _ in outs[1:])      # only rank 0 prints
+    return outs[0][0]
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_bench_main_flow_with_stand_ins(world):
+    """The control flow of bench.py's GPU arm, without a GPU: one JSON line with the contract's keys, the end-to-end
+    and extra phases, the per-rank rows and collectives of the N > 1 path (over gloo) -- and the watchdog: when a phase
+    after the timed steps never returns, every rank still exits 0 and rank 0 has printed the line, marked incomplete."""
+    import json
+    args = ["--gpus", str(world), "--steps", "3", "--warmup", "3", "--no-cpu"]
+    line = json.loads(_bench_mock(args, world).strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "roofline", "clocks", "gpu_launches", "e2e", "extra"):
+        assert key in line, key
+    assert line["n_gpus"] == world and line["steps"] == 3 and "incomplete" not in line
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["value"] > 0
+    assert ("per_rank" in line and len(line["per_rank"]["rows"]) == world and line["parity_check"]["ok"]) if world > 1 else "no_hint" in line
+    stalled = json.loads(_bench_mock(args + ["--no-extra"], world, stall=True).strip().splitlines()[-1])
+    assert "incomplete" in stalled and "e2e" not in stalled and stalled["value"] > 0 and stalled["n_gpus"] == world
