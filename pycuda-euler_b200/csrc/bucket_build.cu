@@ -7,18 +7,27 @@
 //   A  count the canonical l-mers spelled by the bucket's records.  Every warp streams its own slice of the
 //      records (two batches of 32 in registers, handed to the lanes by shuffle), every lane rolls the forward and
 //      reverse-complement l-mer of its record one base per step, and a lane that finishes takes the warp's next
-//      record.  Shared-memory table of 4-slot buckets (two 128-bit loads per probe, atomicCAS claim); the count
-//      word also carries the "prefix / suffix vertex is ours" bits.
+//      record.  Shared-memory tables with ONE key per slot and linear probing: a key that sits in its home slot costs
+//      one 8-byte load and one shared atomicAdd; first occurrences and displaced keys go through a per-warp work queue
+//      to the atomicCAS path, 32 at a time.  The count word also carries the "prefix / suffix vertex is ours" bits.
 //   B  insert the owned end vertices of every distinct l-mer into a second shared-memory table and add the
-//      multiplicity to the vertex's leaving / entering total;
+//      multiplicity to the vertex's leaving / entering total; note which of its eight degree slots are non-zero;
 //   C  totals of (edge records, vertices, edge multiplicities) over the slots;
 //   D  decoupled look-back over the buckets in the order in which they finish counting (the output ticket is taken
 //      when a bucket's totals are ready, so no bucket ever waits for another one's work): global bases;
-//   E  vertex artefacts (the eight degree slots of a vertex are eight lookups in the bucket's own l-mer table)
+//   E  vertex artefacts (the non-zero degree slots of a vertex are look-ups in the bucket's own l-mer table)
 //      and edge artefacts, written in slot order with warp-row scans: consecutive lanes write consecutive ids.
 //      The suffix vertex of an edge whose suffix lives in another bucket is resolved afterwards by two light passes
 //      over the records through a small global table keyed by the canonical l-mer (bkt_boundary_publish_kernel,
 //      bkt_fixup_kernel).
+// Every sparse phase (B, E1, E2: ~30 % of the slots are occupied) compacts its work through the warp queue as well.
+// A bucket several times the mean size would fill its table: the first pass gives it up after BB_PROBE_LIMIT probes
+// and lists it, and a second launch of the same kernel rebuilds the listed buckets with the largest tables a block
+// can hold (BKT_MAX_CAP slots), appending their artefacts -- ids are in completion order anyway.
+//
+// Warp-uniformity is a correctness matter here (shuffles and votes inside data-dependent loops): nothing that steers
+// those loops may be read from memory another warp writes.  tests/host/simt_build_check.cpp runs this file under a
+// SIMT emulator that aborts when the lanes of a warp meet at different collectives.
 #include "bucket.cuh"
 #ifdef EULER_SIMT_EMU   // tests/host/simt_build_check.cpp compiles the kernels of this file for the CPU (tests/host/simt_emu.h)
 #include "simt_emu.h"
