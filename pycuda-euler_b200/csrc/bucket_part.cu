@@ -37,7 +37,12 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const 
                                                                            u32 my_rank, u32 rcap, uint4 *const *__restrict__ dst,
                                                                            u32 *__restrict__ cursors, u64 ntiles, u64 *__restrict__ stats)
 {
-    __shared__ u32 s_rcnt[STREAM ? BP_WARPS : 1][16], s_rbase[STREAM ? BP_WARPS : 1][16], s_rfill[STREAM ? BP_WARPS : 1][16];
+    // stream form, per warp and destination rank: pieces of the tile (s_rmain), slots reserved for orphans (s_rorph), orphans
+    // written (s_rfill), first piece of the rank in the tile's rank-sorted piece list (s_roff, s_rpos = next free), and the
+    // start of the run reserved in the destination's stream (s_rbase)
+    __shared__ u32 s_rmain[STREAM ? BP_WARPS : 1][16], s_rorph[STREAM ? BP_WARPS : 1][16], s_rfill[STREAM ? BP_WARPS : 1][16];
+    __shared__ u32 s_roff[STREAM ? BP_WARPS : 1][16], s_rpos[STREAM ? BP_WARPS : 1][16], s_rbase[STREAM ? BP_WARPS : 1][16];
+    __shared__ unsigned short s_sorted[STREAM ? BP_WARPS : 1][STREAM ? ENC_ADV * 16 : 1];   // the tile's pieces ordered by destination rank
     __shared__ __align__(16) u32 s_rows[BP_WARPS][BP_ROWS * BP_ROW];   // per lane: 16 m-mer scores, then 16 window minima
     __shared__ u32 s_codes[BP_WARPS][34];                              // 2-bit codes of every lane's chunk (two pad entries in front)
     __shared__ u32 s_vl[BP_WARPS][32];                                 // valid l-mer windows of every lane
@@ -117,38 +122,81 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const 
         }
         __syncwarp();
         if constexpr (STREAM) {
-            // ---- reserve one run per destination rank for this tile: pieces (+ a slot for the orphan a chunk-leading piece may add)
-            if (lane < 16) { s_rcnt[wib][lane] = 0; s_rfill[wib][lane] = 0; }
+            // ---- one run per destination rank for this tile: its pieces first, in the order of the rank-sorted piece list (so
+            // that the lanes of one store instruction write CONSECUTIVE records of a stream: on 8 GPUs the partition pass is
+            // bound by the number of remote write transactions, not by their bytes), then a slot for every orphan a
+            // chunk-leading piece MAY add
+            if (lane < 16) { s_rmain[wib][lane] = 0; s_rorph[wib][lane] = 0; s_rfill[wib][lane] = 0; s_rpos[wib][lane] = 0; }
             __syncwarp();
             for (u32 t = lane; t < total; t += 32) {
                 const u32 d = s_desc[wib][t];
                 const u32 L = d >> 8, s = d & 15u;
                 const u32 *row = rows + (L + 2) * BP_ROW;
-                atomicAdd(&s_rcnt[wib][bk_rank_of(row[s], geom.nranks)], 1u);
-                if (s == 0 && (s_vl[wib][L] & 1u)) atomicAdd(&s_rcnt[wib][bk_rank_of(row[-BP_ROW + 15], geom.nranks)], 1u);
+                atomicAdd(&s_rmain[wib][bk_rank_of(row[s], geom.nranks)], 1u);
+                if (s == 0 && (s_vl[wib][L] & 1u)) atomicAdd(&s_rorph[wib][bk_rank_of(row[-BP_ROW + 15], geom.nranks)], 1u);
             }
             __syncwarp();
-            if ((u32)lane < geom.nranks) {
-                const u32 cnt = s_rcnt[wib][lane];
-                s_rbase[wib][lane] = cnt ? atomicAdd(cursors + lane, cnt) : 0u;   // ONE cursor atomic per destination per tile
+            {
+                const u32 mine = lane < 16 ? s_rmain[wib][lane] : 0u;
+                u32 incl = mine;
+#pragma unroll
+                for (int d = 1; d < 16; d <<= 1) {
+                    const u32 t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (lane < 16) s_roff[wib][lane] = incl - mine;
+                if ((u32)lane < geom.nranks) {
+                    const u32 cnt = mine + s_rorph[wib][lane];
+                    s_rbase[wib][lane] = cnt ? atomicAdd(cursors + lane, cnt) : 0u;   // ONE cursor atomic per destination per tile
+                }
             }
             __syncwarp();
-        }
-        // ---- one piece per lane per round: record(s), cursor atomic, 16-byte store -------------------------------------------
-        for (u32 t = lane; t < total; t += 32) {
-            const u32 d = s_desc[wib][t];
-            const u32 L = d >> 8, e = (d >> 4) & 15u, s = d & 15u;
-            const u32 *row = rows + (L + 2) * BP_ROW;
-            const u32 w_s = row[s], w_before = s ? row[s - 1] : row[-BP_ROW + 15], w_after = e < 15u ? row[e + 1] : 0u;
-            bk_piece_records(s_codes[wib][L], s_codes[wib][L + 1], s_codes[wib][L + 2], s, e, w_s, w_before, w_after, s_vl[wib][L], k, geom,
-                             [&](u32 bucket, const BkRec &r) {
-                                 const u32 rank = geom.nranks > 1 ? bucket / geom.nb_per_rank : 0u;
-                                 const u32 lb = bucket - rank * geom.nb_per_rank;
-                                 if constexpr (STREAM) {
-                                     const u32 pos = s_rbase[wib][rank] + atomicAdd(&s_rfill[wib][rank], 1u);
+            for (u32 t = lane; t < total; t += 32) {
+                const u32 d = s_desc[wib][t];
+                const u32 rank = bk_rank_of(rows[((d >> 8) + 2) * BP_ROW + (d & 15u)], geom.nranks);
+                s_sorted[wib][s_roff[wib][rank] + atomicAdd(&s_rpos[wib][rank], 1u)] = (unsigned short)d;
+            }
+            __syncwarp();
+            // ---- one piece per lane per round, in rank order: the piece's record at its place in the run, an orphan behind the pieces
+            for (u32 t = lane; t < total; t += 32) {
+                const u32 d = s_sorted[wib][t];
+                const u32 L = d >> 8, e = (d >> 4) & 15u, s = d & 15u;
+                const u32 *row = rows + (L + 2) * BP_ROW;
+                const u32 w_s = row[s], w_before = s ? row[s - 1] : row[-BP_ROW + 15], w_after = e < 15u ? row[e + 1] : 0u;
+                const u32 home = bk_bucket_of(w_s, geom), hrank = geom.nranks > 1 ? home / geom.nb_per_rank : 0u;
+                const u32 hpos = s_rbase[wib][hrank] + (t - s_roff[wib][hrank]);
+                bool placed = false;
+                bk_piece_records(s_codes[wib][L], s_codes[wib][L + 1], s_codes[wib][L + 2], s, e, w_s, w_before, w_after, s_vl[wib][L], k, geom,
+                                 [&](u32 bucket, const BkRec &r) {
+                                     const u32 rank = geom.nranks > 1 ? bucket / geom.nb_per_rank : 0u;
+                                     const u32 lb = bucket - rank * geom.nb_per_rank;
+                                     u32 pos;
+                                     if (bucket == home) { pos = hpos; placed = true; }   // (an orphan goes to ANOTHER bucket by construction)
+                                     else pos = s_rbase[wib][rank] + s_rmain[wib][rank] + atomicAdd(&s_rfill[wib][rank], 1u);
                                      if (pos < rcap) dst[rank][(u64)my_rank * rcap + pos] = make_uint4(r.hdr | (lb << 8), r.d[0], r.d[1], r.d[2]);
                                      else overflow = true;
-                                 } else {
+                                 });
+                // a lone k-mer is no record: its place in the run gets an empty one (the owner skips it)
+                if (!placed && hpos < rcap) dst[hrank][(u64)my_rank * rcap + hpos] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            __syncwarp();
+            // orphan slots that no orphan took (the chunk-leading piece's neighbour was in the same bucket after all): empty records
+            for (u32 r = 0; r < geom.nranks; r++) {
+                const u32 first = s_rbase[wib][r] + s_rmain[wib][r], fill = s_rfill[wib][r], cnt = s_rorph[wib][r];
+                for (u32 j = fill + lane; j < cnt; j += 32)
+                    if (first + j < rcap) dst[r][(u64)my_rank * rcap + first + j] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        } else {
+            // ---- one piece per lane per round: record(s), cursor atomic, 16-byte store ---------------------------------------
+            for (u32 t = lane; t < total; t += 32) {
+                const u32 d = s_desc[wib][t];
+                const u32 L = d >> 8, e = (d >> 4) & 15u, s = d & 15u;
+                const u32 *row = rows + (L + 2) * BP_ROW;
+                const u32 w_s = row[s], w_before = s ? row[s - 1] : row[-BP_ROW + 15], w_after = e < 15u ? row[e + 1] : 0u;
+                bk_piece_records(s_codes[wib][L], s_codes[wib][L + 1], s_codes[wib][L + 2], s, e, w_s, w_before, w_after, s_vl[wib][L], k, geom,
+                                 [&](u32 bucket, const BkRec &r) {
+                                     const u32 rank = geom.nranks > 1 ? bucket / geom.nb_per_rank : 0u;
+                                     const u32 lb = bucket - rank * geom.nb_per_rank;
                                      const u32 pos = atomicAdd(cursors + bucket, 1u);
                                      if (pos < rcap) {
                                          uint4 *region = dst[rank] + ((u64)lb * geom.nranks + my_rank) * rcap;
@@ -156,16 +204,7 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_MINB) bkt_partition_kernel(const 
                                      } else {
                                          overflow = true;
                                      }
-                                 }
-                             });
-        }
-        if constexpr (STREAM) {
-            __syncwarp();
-            // reserved slots that no record took (a chunk-leading piece without an orphan, a lone k-mer): empty records
-            for (u32 r = 0; r < geom.nranks; r++) {
-                const u32 cnt = s_rcnt[wib][r], fill = s_rfill[wib][r], base = s_rbase[wib][r];
-                for (u32 j = fill + lane; j < cnt; j += 32)
-                    if (base + j < rcap) dst[r][(u64)my_rank * rcap + base + j] = make_uint4(0u, 0u, 0u, 0u);
+                                 });
             }
         }
         __syncwarp();   // the rows are rewritten by the next tile
