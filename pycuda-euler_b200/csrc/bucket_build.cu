@@ -592,8 +592,8 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MINB) bkt_build_kernel(const Bk
             const bool palv = v == rv;
             const u32 L0 = vt_a[slot], E0 = vt_b[slot];
             u32 lc[4], ec[4];
-#pragma unroll
             const u32 mask = (vt_m[slot >> 2] >> (8u * (slot & 3u))) & 0xffu;   // only the non-zero degree slots are looked up
+#pragma unroll
             for (u32 t = 0; t < 4; t++) {   // rc(v t) = comp(t) rc(v), rc(t v) = rc(v) comp(t): no bit reversal per neighbour
                 lc[t] = (mask >> t) & 1u ? bb_bs_count(lt_keys, lt_cnt, cap, (v << 2) | t, ((u64)(3u - t) << (2 * k)) | rv) : 0u;
                 ec[t] = (mask >> (4u + t)) & 1u ? bb_bs_count(lt_keys, lt_cnt, cap, ((u64)t << (2 * k)) | v, (rv << 2) | (3u - t)) : 0u;
