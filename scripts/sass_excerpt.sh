@@ -10,5 +10,5 @@ for spec in "bucket_part.o:bkt_partition_kernelILi20ELb0" "bucket_part.o:bkt_par
   echo "-- mnemonic histogram (top 30)"
   grep -E '^\s+/\*[0-9a-f]{4}\*/' /tmp/_sass.txt | awk '{print $2}' | sed 's/;//' | sort | uniq -c | sort -rn | head -30 | awk '{printf "%s:%s  ", $2, $1} END{print ""}'
   echo "-- memory / atomic / warp-collective instructions (distinct forms)"
-  grep -E '^\s+/\*[0-9a-f]{4}\*/' /tmp/_sass.txt | awk '{print $2}' | sed 's/;//' | grep -E '^(LDG|STG|LDS|STS|ATOM|RED|SHFL|VOTE|MATCH|BAR|WARPSYNC|NANOSLEEP|MEMBAR|CCTL|LDGSTS|UBLKCP|UTMA)' | sort | uniq -c | sort -rn | awk '{printf "%s:%s  ", $2, $1} END{print ""}'
+  grep -E '^\s+/\*[0-9a-f]{4}\*/' /tmp/_sass.txt | awk '{print $2}' | sed 's/;//' | grep -E '^(LDG|STG|LDS|STS|LDL|STL|ATOM|RED|SHFL|VOTE|MATCH|BAR|WARPSYNC|NANOSLEEP|MEMBAR|CCTL|LDGSTS|UBLKCP|UTMA)' | sort | uniq -c | sort -rn | awk '{printf "%s:%s  ", $2, $1} END{print ""}'
 done
