@@ -42,7 +42,8 @@ struct Reads {
 };
 
 // genome > 0: reads are windows of one random genome, either strand, an N now and then (coverage: repeated l-mers);
-// genome == 0: independent random reads with N's, lowercase and low-complexity stretches (palindromes, repeats)
+// genome == 0: independent random reads with N's, lowercase and low-complexity stretches (palindromes, repeats);
+// genome < 0: homopolymers and short tandem repeats only
 static inline Reads make_reads(int nreads, int maxlen, int genome_len)
 {
     Reads R;
@@ -51,7 +52,12 @@ static inline Reads make_reads(int nreads, int maxlen, int genome_len)
     for (int r = 0; r < nreads; r++) {
         R.off.push_back(R.buf.size());
         int len = (int)(rnd() % (u64)(maxlen + 1));
-        if (genome_len > 0) {
+        if (genome_len < 0) {   // low complexity: homopolymers, short tandem repeats (palindromic l-mers, large multiplicities)
+            static const char *units[] = {"A", "C", "AT", "ACGT", "AAC", "GGGTTT"};
+            const std::string u = units[rnd() % 6];
+            len = maxlen / 2 + (int)(rnd() % (u64)(maxlen / 2 + 1));
+            for (int i = 0; i < len; i++) R.buf.push_back(u[i % u.size()]);
+        } else if (genome_len > 0) {
             if (len > genome_len) len = genome_len;
             const int s = (int)(rnd() % (u64)(genome_len - len + 1));
             std::string rd = genome.substr(s, len);

@@ -168,6 +168,10 @@ int main(int argc, char **argv)
         {13, 4, 768, 120, 90, 0, 1.0, 0, false},                 // generic kernel; k = m: one k-mer per minimizer window
         {6, 3, 768, 60, 60, 0, 1.0, 0, false},                   // short l-mers: palindromes, dense graph, many repeats
         {2, 2, 256, 30, 40, 0, 1.0, 0, false},                   // k = 1
+        {31, 5, 1536, 120, 130, 1200, 1.0, 0, false},            // odd lengths take the generic kernel
+        {16, 4, 1536, 100, 100, 800, 1.0, 0, false},
+        {32, 3, 1536, 300, 120, -1, 1.0, 0, false},              // homopolymers and tandem repeats: multiplicities in the thousands
+        {8, 2, 256, 200, 100, -1, 1.0, 0, false},                // the same with palindromic l-mers (even l)
         {32, 1, 256, 40, 100, 0, 1.0, 0, true},                  // one bucket that cannot fit 256 slots: rebuilt by the second pass
         {22, 7, 256, 260, 100, 2500, 1.0, 0, true},              // several buckets overflow, the others do not
         {32, 1, 256, 420, 150, 0, 1.0, BKT_FLAG_TABLE, true},    // too large even for the second pass: the host must repartition

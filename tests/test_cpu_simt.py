@@ -45,7 +45,7 @@ def test_build_kernels_under_the_simt_emulator():
                                os.path.join(HOST, "simt_build_check.cpp"), "-o", exe])
         out = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "9 cases, 0 failed" in out.stdout
+    assert "13 cases, 0 failed" in out.stdout
     assert len(re.findall(r"redo=[1-9]", out.stdout)) >= 3      # the second pass really ran
 
 
