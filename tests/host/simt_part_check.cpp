@@ -314,6 +314,7 @@ int main()
         {22, 8, 2, 1536, 200, 100, 1800, 1.0},    // eight ranks
         {6, 2, 3, 1536, 60, 60, 0, 1.0},          // short l-mers: palindromes, k < m
         {32, 16, 1, 1536, 120, 120, 900, 1.0},    // the most ranks the run reservation holds, one bucket each, some shards empty
+        {22, 3, 3, 1536, 150, 120, -1, 1.0},      // homopolymers and tandem repeats: long runs of one minimizer, many chunk-leading pieces
         {32, 3, 4, 1536, 160, 140, 1500, 0.5},    // streams too small: flag, capped counts, nothing behind the area
     };
     int fails = 0, n = 0;

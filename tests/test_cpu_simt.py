@@ -56,4 +56,4 @@ def test_partition_kernels_under_the_simt_emulator():
                                os.path.join(HOST, "simt_part_check.cpp"), "-o", exe])
         out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "8 cases, 0 failed" in out.stdout
+    assert "9 cases, 0 failed" in out.stdout
